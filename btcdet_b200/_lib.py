@@ -1,0 +1,85 @@
+"""ctypes binding of the C-ABI library `libbtcdet_b200.so` (include/btcdet_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, the caller gets an
+exception.  The product path never routes through `oracle/` or CPU code.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbtcdet_b200.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+
+# name -> (restype, argtypes); mirrors include/btcdet_b200.h one to one
+SIGNATURES = {
+    "btc_abi_version": (_i, []),
+    "btc_compiled_sm": (_i, []),
+    "btc_last_error": (ctypes.c_char_p, []),
+    "btc_voxelize_workspace_bytes": (_i64, [_i64, _i, _i, _i]),
+    "btc_voxelize": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_index_entries": (_i64, [_i, _p]),
+    "btc_index_workspace_bytes": (_i64, [_i64]),
+    "btc_index_build": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _p, _p, _i64, _p]),
+    "btc_index_clear": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p]),
+    "btc_rulebook_subm": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "btc_rulebook_conv": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _i, _p, _p, _p, _p, _i64, _p]),
+    "btc_rulebook_pairs_workspace_bytes": (_i64, [_i, _i]),
+    "btc_rulebook_pairs": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i64, _p]),
+    "btc_sparse_conv_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "btc_sparse_conv_bwd_workspace_bytes": (_i64, [_i, _i, _i]),
+    "btc_sparse_conv_bwd_data": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _i64, _p]),
+    "btc_sparse_conv_bwd_weight": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
+    "btc_maxpool_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _p]),
+    "btc_maxpool_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _p]),
+    "btc_to_dense": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "btc_from_dense": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "btc_revoxelize_workspace_bytes": (_i64, [_i, _i64]),
+    "btc_revoxelize": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_revoxelize_fill": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _i, _p]),
+}
+
+_lib = None
+
+
+class BtcError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BtcError(
+            "CUDA extension %s is missing — run `python -m btcdet_b200.build` "
+            "(there is no CPU fallback in this package)" % LIB_PATH
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.btc_compiled_sm() != 100:
+        raise BtcError("libbtcdet_b200.so was not built for sm_100a")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().btc_last_error()
+        raise BtcError("%s failed with status %d: %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def int3(values):
+    """Host int[3] array for geometry arguments."""
+    a = (ctypes.c_int * 3)(*[int(v) for v in values])
+    return a
+
+
+def float_array(values):
+    return (ctypes.c_float * len(values))(*[float(v) for v in values])

@@ -1,0 +1,217 @@
+// Rank-bitmap coordinate index + device-wide scans (see include/btcdet_b200.h).
+//
+// Replaces spconv 1.2.1's dense int32 grid / cuckoo hash as the coordinate -> row map.
+// HBM layout: one uint2 per 32 cells {occupancy bits, rank before the word}; a KITTI det
+// grid [41,1600,1408] is 2.9 M entries = 23 MB per scene and stays L2-resident (126 MB),
+// so the 27 neighbour probes per voxel of a submanifold rulebook are L2 hits, one 8-byte
+// load each.  rank() order == ascending flat (b,z,y,x) key == spconv's output order.
+#include "common.cuh"
+
+namespace btc {
+
+thread_local char g_last_error[256] = {0};
+
+int set_error(int code, const char* what, cudaError_t e) {
+    if (e != cudaSuccess)
+        snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+    else
+        snprintf(g_last_error, sizeof(g_last_error), "%s", what);
+    return code;
+}
+
+// ---- scan kernels -------------------------------------------------------------
+struct PopcLoad {
+    const uint2* p;
+    __device__ __forceinline__ int operator()(int64_t i) const { return __popc(__ldg(&p[i].x)); }
+};
+struct FlagLoad {
+    const int* p;
+    __device__ __forceinline__ int operator()(int64_t i) const { return __ldg(p + i) != 0; }
+};
+
+template <class Load>
+__global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(Load load, int64_t n, int* __restrict__ block_sums) {
+    __shared__ int s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        int64_t i = base + (int64_t)j * kScanThreads + threadIdx.x;
+        if (i < n) sum += load(i);
+    }
+    // block reduce
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (kScanThreads / 32) ? s_warp[threadIdx.x] : 0;
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+    }
+}
+
+// Single block: exclusive scan of block_sums[0..nb) in place, total -> block_sums[nb] and *total.
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ total) {
+    __shared__ int s_warp[33];
+    int carry = 0;
+    for (int base = 0; base < nb; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? block_sums[i] : 0;
+        int tot;
+        int ex = block_exclusive_scan(v, s_warp, &tot);
+        if (i < nb) block_sums[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        block_sums[nb] = carry;
+        if (total) *total = carry;
+    }
+}
+
+struct RankStore {
+    uint2* p;
+    __device__ __forceinline__ void operator()(int64_t i, int v) const { p[i].y = (unsigned)v; }
+};
+struct IntStore {
+    int* p;
+    __device__ __forceinline__ void operator()(int64_t i, int v) const { p[i] = v; }
+};
+
+template <class Load, class Store>
+__global__ void __launch_bounds__(kScanThreads) scan_write_kernel(Load load, Store store, int64_t n,
+                                                                 const int* __restrict__ block_sums) {
+    __shared__ int s_warp[33];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int carry = block_sums[blockIdx.x];
+#pragma unroll 1
+    for (int j = 0; j < kScanItems; ++j) {
+        int64_t i = base + (int64_t)j * kScanThreads + threadIdx.x;
+        if (base + (int64_t)j * kScanThreads >= n) break;
+        int v = i < n ? load(i) : 0;
+        int tot;
+        int ex = block_exclusive_scan(v, s_warp, &tot);
+        if (i < n) store(i, carry + ex);
+        carry += tot;
+    }
+}
+
+int launch_index_scan(uint2* index, int64_t n_entries, int* block_sums, int* total, cudaStream_t stream) {
+    int nb = scan_num_blocks(n_entries);
+    PopcLoad ld{index};
+    scan_partials_kernel<<<nb, kScanThreads, 0, stream>>>(ld, n_entries, block_sums);
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
+    scan_write_kernel<<<nb, kScanThreads, 0, stream>>>(ld, RankStore{index}, n_entries, block_sums);
+    BTC_CHECK_LAUNCH("index scan");
+    return BTC_OK;
+}
+
+int launch_flag_scan(const int* flags, int* out, int n_cap, int* block_sums, int* total, cudaStream_t stream) {
+    int nb = scan_num_blocks(n_cap);
+    FlagLoad ld{flags};
+    scan_partials_kernel<<<nb, kScanThreads, 0, stream>>>(ld, (int64_t)n_cap, block_sums);
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
+    scan_write_kernel<<<nb, kScanThreads, 0, stream>>>(ld, IntStore{out}, (int64_t)n_cap, block_sums);
+    BTC_CHECK_LAUNCH("flag scan");
+    return BTC_OK;
+}
+
+// ---- mark / perm / clear ------------------------------------------------------
+__global__ void index_mark_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                                  Shape3 shape, int batch, unsigned* __restrict__ index_words) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = __ldg(coords + i);  // (b, z, y, x)
+        if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)shape.d ||
+            (unsigned)c.z >= (unsigned)shape.h || (unsigned)c.w >= (unsigned)shape.w)
+            continue;
+        int64_t key = flat_key(c.x, c.y, c.z, c.w, shape);
+        atomicOr(index_words + 2 * (key >> 5), 1u << (unsigned)(key & 31));
+    }
+}
+
+__global__ void index_perm_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                                  Shape3 shape, int batch, const uint2* __restrict__ index, int* __restrict__ perm) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = __ldg(coords + i);
+        if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)shape.d ||
+            (unsigned)c.z >= (unsigned)shape.h || (unsigned)c.w >= (unsigned)shape.w)
+            continue;
+        int r = index_lookup(index, flat_key(c.x, c.y, c.z, c.w, shape));
+        if (r >= 0 && r < n_cap) perm[r] = i;
+    }
+}
+
+__global__ void index_clear_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                                   Shape3 shape, int batch, uint2* __restrict__ index) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = __ldg(coords + i);
+        if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)shape.d ||
+            (unsigned)c.z >= (unsigned)shape.h || (unsigned)c.w >= (unsigned)shape.w)
+            continue;
+        int64_t key = flat_key(c.x, c.y, c.z, c.w, shape);
+        index[key >> 5] = make_uint2(0u, 0u);
+    }
+}
+
+}  // namespace btc
+
+using namespace btc;
+
+extern "C" {
+
+int btc_abi_version(void) { return 1; }
+int btc_compiled_sm(void) {
+#ifdef BTC_SM
+    return BTC_SM;
+#else
+    return 0;
+#endif
+}
+const char* btc_last_error(void) { return btc::g_last_error; }
+
+int64_t btc_index_entries(int batch, const int* shape) {
+    int64_t cells = (int64_t)batch * shape[0] * shape[1] * shape[2];
+    return (cells + 31) / 32;
+}
+
+int64_t btc_index_workspace_bytes(int64_t n_entries) {
+    return align_up((int64_t)(scan_num_blocks(n_entries) + 2) * sizeof(int), 256);
+}
+
+int btc_index_build(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, uint64_t* index,
+                    int64_t n_entries, int* perm, int* total, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!coords || !index || !shape || !workspace) return badarg("btc_index_build: null argument");
+    if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_index_build: n_entries mismatch");
+    if (workspace_bytes < btc_index_workspace_bytes(n_entries)) return badarg("btc_index_build: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    Shape3 s{shape[0], shape[1], shape[2]};
+    if (n_cap > 0) {
+        index_mark_kernel<<<grid_for(n_cap, 256), 256, 0, st>>>((const int4*)coords, n_cap, n_dev, s, batch,
+                                                                (unsigned*)index);
+        BTC_CHECK_LAUNCH("index_mark");
+    }
+    int rc = launch_index_scan((uint2*)index, n_entries, (int*)workspace, total, st);
+    if (rc) return rc;
+    if (perm && n_cap > 0) {
+        index_perm_kernel<<<grid_for(n_cap, 256), 256, 0, st>>>((const int4*)coords, n_cap, n_dev, s, batch,
+                                                                (const uint2*)index, perm);
+        BTC_CHECK_LAUNCH("index_perm");
+    }
+    return BTC_OK;
+}
+
+int btc_index_clear(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, uint64_t* index,
+                    int64_t n_entries, void* stream) {
+    if (!coords || !index || !shape) return badarg("btc_index_clear: null argument");
+    if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_index_clear: n_entries mismatch");
+    if (n_cap <= 0) return BTC_OK;
+    Shape3 s{shape[0], shape[1], shape[2]};
+    index_clear_kernel<<<grid_for(n_cap, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, s,
+                                                                             batch, (uint2*)index);
+    BTC_CHECK_LAUNCH("index_clear");
+    return BTC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// Rulebook ("indice pairs") construction — replaces spconv 1.2.1 src/spconv/indice.cu
+// (getSubMIndicePairs / getIndicePairsConv / ...DeConv + torch::_unique) reached from
+// SparseConvolution.forward; reference call sites
+// btcdet/models/backbones_3d/spconv_backbone.py:12-29 (post_act_block) and every
+// SubMConv3d / SparseConv3d / SparseConvTranspose3d / SparseMaxPool3d layer built there.
+//
+// Design (B200-first): no sort, no atomics on counters, no host sync.
+//   * output sites of a strided / transposed conv are marked in a rank bitmap of the output
+//     grid (L2-resident); one popcount scan yields both the number of sites and, for each
+//     site, its row = rank in ascending flat-key order (the order torch::_unique gave spconv);
+//   * neighbour tables are written output-stationary (nbr_out[o][k]) for the conv kernels and
+//     input-major (nbr_in[i][k]) for backward / the spconv-format pair list;
+//   * the spconv-format pair list is produced in canonical (offset, input row) order with a
+//     warp-ballot + prefix-sum stream compaction per offset — deterministic, unlike the
+//     atomicAdd slot order of the original.
+#include "common.cuh"
+
+namespace btc {
+
+__device__ __forceinline__ void offset_of(int k, const int* ks, int& kz, int& ky, int& kx) {
+    kx = k % ks[2];
+    int t = k / ks[2];
+    ky = t % ks[1];
+    kz = t / ks[1];
+}
+
+// Output coordinate along one axis for input coordinate `in`, kernel tap `kk`.
+// regular:    out*s - p + kk*d == in   ->  out = (in + p - kk*d) / s  when divisible
+// transposed: out = in*s - p + kk*d
+__device__ __forceinline__ bool out_coord(int in, int kk, int s, int p, int d, int out_dim, int transposed, int& o) {
+    if (transposed) {
+        o = in * s - p + kk * d;
+    } else {
+        int t = in + p - kk * d;
+        if (t < 0) return false;
+        if (s != 1) {
+            if (t % s) return false;
+            t /= s;
+        }
+        o = t;
+    }
+    return o >= 0 && o < out_dim;
+}
+
+// ---- submanifold ----------------------------------------------------------------
+// One thread per (site, tap); the 27 probes of a site hit 9 index words that sit in L1/L2.
+__global__ void subm_table_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                                  ConvGeom g, const uint2* __restrict__ index, const int* __restrict__ perm,
+                                  int* __restrict__ nbr_out) {
+    const int n = live_count(n_cap, n_dev);
+    const int K = g.K;
+    const int64_t work = (int64_t)n * K;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
+        int4 c = __ldg(coords + i);
+        int kz, ky, kx;
+        offset_of(k, g.k, kz, ky, kx);
+        int z = c.y + (kz - g.k[0] / 2) * g.dil[0];
+        int y = c.z + (ky - g.k[1] / 2) * g.dil[1];
+        int x = c.w + (kx - g.k[2] / 2) * g.dil[2];
+        int j = -1;
+        if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w) {
+            int r = index_lookup(index, flat_key(c.x, z, y, x, g.in));
+            if (r >= 0) j = perm ? __ldg(perm + r) : r;
+        }
+        nbr_out[t] = j;
+    }
+}
+
+// ---- strided / transposed -----------------------------------------------------------
+__global__ void conv_mark_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
+                                 unsigned* __restrict__ out_index_words) {
+    const int n = live_count(n_cap, n_dev);
+    const int K = g.K;
+    const int64_t work = (int64_t)n * K;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
+        int4 c = __ldg(coords + i);
+        int kz, ky, kx, oz, oy, ox;
+        offset_of(k, g.k, kz, ky, kx);
+        if (!out_coord(c.y, kz, g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, oz)) continue;
+        if (!out_coord(c.z, ky, g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, oy)) continue;
+        if (!out_coord(c.w, kx, g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, ox)) continue;
+        int64_t key = flat_key(c.x, oz, oy, ox, g.out);
+        unsigned bit = 1u << (unsigned)(key & 31);
+        unsigned* wptr = out_index_words + 2 * (key >> 5);
+        // most taps of neighbouring inputs hit an already-set bit: test before the atomic
+        if (!(*(volatile unsigned*)wptr & bit)) atomicOr(wptr, bit);
+    }
+}
+
+// Decode every occupied cell of the output index into a coordinate row; init its table row.
+__global__ void conv_emit_kernel(const uint2* __restrict__ out_index, int64_t n_entries, Shape3 out, int out_cap,
+                                 int K, int4* __restrict__ out_coords, int* __restrict__ nbr_out) {
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_entries; w += (int64_t)gridDim.x * blockDim.x) {
+        uint2 e = __ldg(out_index + w);
+        unsigned bits = e.x;
+        int row = (int)e.y;
+        while (bits) {
+            int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (row < out_cap) {
+                int64_t key = (w << 5) + bpos;
+                int x = (int)(key % out.w);
+                int64_t t = key / out.w;
+                int y = (int)(t % out.h);
+                t /= out.h;
+                int z = (int)(t % out.d);
+                int b = (int)(t / out.d);
+                out_coords[row] = make_int4(b, z, y, x);
+            }
+            ++row;
+        }
+    }
+}
+
+__global__ void fill_table_kernel(int* __restrict__ table, int n_cap, const int* __restrict__ n_dev, int K) {
+    const int64_t work = (int64_t)live_count(n_cap, n_dev) * K;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x)
+        table[t] = -1;
+}
+
+__global__ void conv_tables_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
+                                   const uint2* __restrict__ out_index, int out_cap, int* __restrict__ nbr_out,
+                                   int* __restrict__ nbr_in) {
+    const int n = live_count(n_cap, n_dev);
+    const int K = g.K;
+    const int64_t work = (int64_t)n * K;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
+        int4 c = __ldg(coords + i);
+        int kz, ky, kx, oz, oy, ox;
+        offset_of(k, g.k, kz, ky, kx);
+        int o = -1;
+        if (out_coord(c.y, kz, g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, oz) &&
+            out_coord(c.z, ky, g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, oy) &&
+            out_coord(c.w, kx, g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, ox)) {
+            o = index_lookup(out_index, flat_key(c.x, oz, oy, ox, g.out));
+            if (o >= out_cap) o = -1;
+        }
+        if (nbr_in) nbr_in[t] = o;
+        if (nbr_out && o >= 0) nbr_out[(int64_t)o * K + k] = i;
+    }
+}
+
+// ---- spconv-format pair list, canonical order ------------------------------------------------
+constexpr int kPairThreads = 256;
+constexpr int kPairRowsPerBlock = 2048;
+
+__device__ __forceinline__ int table_at(const int* __restrict__ table, int i, int k, int K, int mirror) {
+    return __ldg(table + (int64_t)i * K + (mirror ? K - 1 - k : k));
+}
+
+// grid (row blocks, K): count valid entries of column k inside the block's row range.
+__global__ void __launch_bounds__(kPairThreads) pairs_count_kernel(const int* __restrict__ table, int n_cap,
+                                                                  const int* __restrict__ n_dev, int K, int mirror,
+                                                                  int* __restrict__ block_counts /*[K][nblk]*/) {
+    __shared__ int s_warp[kPairThreads / 32];
+    const int n = live_count(n_cap, n_dev);
+    const int k = blockIdx.y;
+    const int r0 = blockIdx.x * kPairRowsPerBlock;
+    int cnt = 0;
+    for (int r = r0 + threadIdx.x; r < r0 + kPairRowsPerBlock && r < n; r += kPairThreads)
+        cnt += table_at(table, r, k, K, mirror) >= 0;
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < kPairThreads / 32; ++w) tot += s_warp[w];
+        block_counts[k * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+// grid K blocks: exclusive scan over the row blocks of one offset; writes pair_num[k].
+__global__ void __launch_bounds__(256) pairs_scan_kernel(int* __restrict__ block_counts, int nblk,
+                                                        int* __restrict__ pair_num) {
+    __shared__ int s_warp[33];
+    int* row = block_counts + (int64_t)blockIdx.x * nblk;
+    int carry = 0;
+    for (int base = 0; base < nblk; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = i < nblk ? row[i] : 0;
+        int tot;
+        int ex = block_exclusive_scan(v, s_warp, &tot);
+        if (i < nblk) row[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) pair_num[blockIdx.x] = carry;
+}
+
+// grid (row blocks, K): ballot + popc compaction, rows ascending.
+__global__ void __launch_bounds__(kPairThreads) pairs_write_kernel(const int* __restrict__ table, int n_cap,
+                                                                  const int* __restrict__ n_dev, int K, int mirror,
+                                                                  const int* __restrict__ block_offsets,
+                                                                  int* __restrict__ pairs) {
+    __shared__ int s_warp[33];
+    const int n = live_count(n_cap, n_dev);
+    const int k = blockIdx.y;
+    const int r0 = blockIdx.x * kPairRowsPerBlock;
+    int carry = block_offsets[k * gridDim.x + blockIdx.x];
+    int* p_in = pairs + (int64_t)k * n_cap;
+    int* p_out = pairs + ((int64_t)K + k) * n_cap;
+    for (int base = r0; base < r0 + kPairRowsPerBlock; base += kPairThreads) {
+        if (base >= n) break;
+        int r = base + threadIdx.x;
+        int o = r < n ? table_at(table, r, k, K, mirror) : -1;
+        int valid = o >= 0;
+        int tot;
+        int ex = block_exclusive_scan(valid, s_warp, &tot);
+        if (valid) {
+            p_in[carry + ex] = r;
+            p_out[carry + ex] = o;
+        }
+        carry += tot;
+    }
+}
+
+static int make_geom(ConvGeom& g, int batch, const int* in_shape, const int* out_shape, const int* ksize,
+                     const int* stride, const int* padding, const int* dilation, int transposed) {
+    g.batch = batch;
+    g.in = Shape3{in_shape[0], in_shape[1], in_shape[2]};
+    g.out = Shape3{out_shape[0], out_shape[1], out_shape[2]};
+    g.transposed = transposed;
+    g.K = 1;
+    for (int a = 0; a < 3; ++a) {
+        g.k[a] = ksize[a];
+        g.s[a] = stride ? stride[a] : 1;
+        g.p[a] = padding ? padding[a] : 0;
+        g.dil[a] = dilation ? dilation[a] : 1;
+        if (g.k[a] < 1 || g.s[a] < 1 || g.dil[a] < 1 || g.p[a] < 0) return BTC_E_BADARG;
+        g.K *= g.k[a];
+    }
+    return BTC_OK;
+}
+
+}  // namespace btc
+
+using namespace btc;
+
+extern "C" {
+
+int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, const int* ksize,
+                      const int* dilation, const uint64_t* index, int64_t n_entries, const int* perm, int* nbr_out,
+                      void* stream) {
+    if (!coords || !shape || !ksize || !index || !nbr_out) return badarg("btc_rulebook_subm: null argument");
+    if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_rulebook_subm: n_entries mismatch");
+    ConvGeom g;
+    int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+    if (make_geom(g, batch, shape, shape, ksize, one, zero, dilation, 0)) return badarg("btc_rulebook_subm: bad geometry");
+    if (n_cap <= 0) return BTC_OK;
+    int64_t work = (int64_t)n_cap * g.K;
+    subm_table_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, g,
+                                                                            (const uint2*)index, perm, nbr_out);
+    BTC_CHECK_LAUNCH("subm_table");
+    return BTC_OK;
+}
+
+int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, int batch, const int* in_shape,
+                      const int* out_shape, const int* ksize, const int* stride, const int* padding,
+                      const int* dilation, int transposed, uint64_t* out_index, int64_t out_entries, int* out_coords,
+                      int out_cap, int* n_out, int* nbr_out, int* nbr_in, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+    if (!coords_in || !in_shape || !out_shape || !ksize || !out_index || !out_coords || !n_out || !workspace)
+        return badarg("btc_rulebook_conv: null argument");
+    if (out_entries != btc_index_entries(batch, out_shape)) return badarg("btc_rulebook_conv: out_entries mismatch");
+    if (workspace_bytes < btc_index_workspace_bytes(out_entries)) return badarg("btc_rulebook_conv: workspace too small");
+    ConvGeom g;
+    if (make_geom(g, batch, in_shape, out_shape, ksize, stride, padding, dilation, transposed))
+        return badarg("btc_rulebook_conv: bad geometry");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = 256;
+    int64_t work = (int64_t)(n_in_cap > 0 ? n_in_cap : 1) * g.K;
+    if (n_in_cap > 0) {
+        conv_mark_kernel<<<grid_for(work, T), T, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+                                                          (unsigned*)out_index);
+        BTC_CHECK_LAUNCH("conv_mark");
+    }
+    int rc = launch_index_scan((uint2*)out_index, out_entries, (int*)workspace, n_out, st);
+    if (rc) return rc;
+    conv_emit_kernel<<<grid_for(out_entries, T), T, 0, st>>>((const uint2*)out_index, out_entries, g.out, out_cap, g.K,
+                                                            (int4*)out_coords, nbr_out);
+    if (nbr_out && out_cap > 0)
+        fill_table_kernel<<<grid_for((int64_t)out_cap * g.K, T), T, 0, st>>>(nbr_out, out_cap, n_out, g.K);
+    if (n_in_cap > 0 && (nbr_out || nbr_in))
+        conv_tables_kernel<<<grid_for(work, T), T, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+                                                            (const uint2*)out_index, out_cap, nbr_out, nbr_in);
+    BTC_CHECK_LAUNCH("conv rulebook");
+    return BTC_OK;
+}
+
+int64_t btc_rulebook_pairs_workspace_bytes(int n_in_cap, int K) {
+    int nblk = (n_in_cap + kPairRowsPerBlock - 1) / kPairRowsPerBlock;
+    if (nblk < 1) nblk = 1;
+    return align_up((int64_t)nblk * K * 4, 256);
+}
+
+int btc_rulebook_pairs(const int* table, int n_in_cap, const int* n_in_dev, int K, int mirror, int* pairs, int* pair_num,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!table || !pairs || !pair_num || !workspace) return badarg("btc_rulebook_pairs: null argument");
+    if (K < 1 || n_in_cap < 0) return badarg("btc_rulebook_pairs: bad sizes");
+    if (workspace_bytes < btc_rulebook_pairs_workspace_bytes(n_in_cap, K)) return badarg("btc_rulebook_pairs: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_in_cap == 0) {
+        BTC_CUDA(cudaMemsetAsync(pair_num, 0, (size_t)K * 4, st), "pairs memset");
+        return BTC_OK;
+    }
+    BTC_CUDA(cudaMemsetAsync(pairs, 0xff, (size_t)2 * K * n_in_cap * 4, st), "pairs memset");
+    int nblk = (n_in_cap + kPairRowsPerBlock - 1) / kPairRowsPerBlock;
+    dim3 grid(nblk, K);
+    int* counts = (int*)workspace;
+    pairs_count_kernel<<<grid, kPairThreads, 0, st>>>(table, n_in_cap, n_in_dev, K, mirror, counts);
+    pairs_scan_kernel<<<K, 256, 0, st>>>(counts, nblk, pair_num);
+    pairs_write_kernel<<<grid, kPairThreads, 0, st>>>(table, n_in_cap, n_in_dev, K, mirror, counts, pairs);
+    BTC_CHECK_LAUNCH("rulebook_pairs");
+    return BTC_OK;
+}
+
+}  // extern "C"

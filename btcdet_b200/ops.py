@@ -1,0 +1,411 @@
+"""Torch-facing wrappers over the C ABI (include/btcdet_b200.h).
+
+PyTorch is plumbing here: it owns device memory (caching allocator), streams and autograd
+bookkeeping.  Every computation is a call into libbtcdet_b200.so on the current stream.
+Mirrors the operator surface of spconv 1.2.1 `spconv.ops` (get_indice_pairs, indice_conv,
+indice_maxpool) that the reference reaches from btcdet/models/backbones_3d/spconv_backbone.py.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, float_array, int3
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.BtcError("btcdet_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3, v
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+def conv_output_shape(in_shape, ksize, stride, padding, dilation):
+    """spconv get_conv_output_size: (in + 2p - d(k-1) - 1)//s + 1."""
+    return [(i + 2 * p - d * (k - 1) - 1) // s + 1 for i, k, s, p, d in zip(in_shape, ksize, stride, padding, dilation)]
+
+
+def deconv_output_shape(in_shape, ksize, stride, padding, dilation, output_padding):
+    """spconv get_deconv_output_size: (in-1)s - 2p + k + output_padding."""
+    return [(i - 1) * s - 2 * p + k + op for i, k, s, p, op in zip(in_shape, ksize, stride, padding, output_padding)]
+
+
+# ------------------------------------------------------------------------------------------
+# coordinate index
+# ------------------------------------------------------------------------------------------
+@dataclass
+class CoordIndex:
+    """Rank bitmap over batch x spatial_shape (+ rank->row permutation when rows are unsorted)."""
+    entries: torch.Tensor  # int64 [n_entries]  ({bits, rank} packed)
+    perm: Optional[torch.Tensor]  # int32 [N] or None when rows are in ascending key order
+    batch: int
+    shape: Sequence[int]
+
+
+def index_entries(batch, shape):
+    return int(_lib.load().btc_index_entries(int(batch), int3(shape)))
+
+
+def build_index(coords: torch.Tensor, batch: int, shape, need_perm=True, n_dev=None) -> CoordIndex:
+    _require_cuda(coords)
+    lib = _lib.load()
+    assert coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 4 and coords.is_contiguous()
+    n = coords.shape[0]
+    n_entries = index_entries(batch, shape)
+    entries = torch.zeros(n_entries, dtype=torch.int64, device=coords.device)
+    ws_bytes = int(lib.btc_index_workspace_bytes(n_entries))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=coords.device)
+    perm = torch.empty(max(n, 1), dtype=torch.int32, device=coords.device) if need_perm else None
+    check(lib.btc_index_build(_ptr(coords), n, _ptr(n_dev), int(batch), int3(shape), _ptr(entries), n_entries,
+                              _ptr(perm), None, _ptr(ws), ws_bytes, _stream()), "btc_index_build")
+    return CoordIndex(entries, perm, int(batch), list(shape))
+
+
+# ------------------------------------------------------------------------------------------
+# rulebooks
+# ------------------------------------------------------------------------------------------
+@dataclass
+class Rulebook:
+    """What spconv keeps in `indice_dict[key]`, in the layout the B200 kernels want.
+
+    nbr_out [N_out, K]: input row feeding output row o through offset k (or -1).
+    nbr_in  [N_in, K] : output row fed by input row i through offset k (None for submanifold
+                        rulebooks, whose nbr_in is the mirror image of nbr_out).
+    """
+    nbr_out: torch.Tensor
+    nbr_in: Optional[torch.Tensor]
+    out_coords: torch.Tensor
+    n_in: int
+    n_out: int
+    K: int
+    subm: bool
+    in_shape: list
+    out_shape: list
+    ksize: list
+    stride: list
+    padding: list
+    dilation: list
+    transposed: bool = False
+    out_index: Optional[CoordIndex] = None
+    _pairs: Optional[tuple] = field(default=None, repr=False)
+
+    def inverse(self) -> "Rulebook":
+        """Rulebook of SparseInverseConv3d: swap the pair directions."""
+        if self.subm:
+            nbr_out_inv = self.nbr_out.flip(1).contiguous()
+            nbr_in_inv = None
+        else:
+            nbr_out_inv, nbr_in_inv = self.nbr_in, self.nbr_out
+        return Rulebook(nbr_out_inv, nbr_in_inv, None, self.n_out, self.n_in, self.K, self.subm, self.out_shape,
+                        self.in_shape, self.ksize, self.stride, self.padding, self.dilation, not self.transposed)
+
+    def pairs(self):
+        """spconv-1.2.1-format (indice_pairs [2,K,N_in], indice_pair_num [K]) in canonical order."""
+        if self._pairs is None:
+            table = self.nbr_out if self.subm else self.nbr_in
+            self._pairs = rulebook_pairs(table, self.n_in, self.K, mirror=self.subm)
+        return self._pairs
+
+
+def rulebook_subm(coords: torch.Tensor, batch: int, shape, ksize, dilation=1,
+                  index: Optional[CoordIndex] = None) -> Rulebook:
+    _require_cuda(coords)
+    lib = _lib.load()
+    ksize, dilation = _triple(ksize), _triple(dilation)
+    for k in ksize:
+        if k % 2 != 1:
+            raise _lib.BtcError("submanifold convolution needs odd kernel sizes")
+    n = coords.shape[0]
+    K = ksize[0] * ksize[1] * ksize[2]
+    if index is None:
+        index = build_index(coords, batch, shape, need_perm=True)
+    nbr = torch.empty((n, K), dtype=torch.int32, device=coords.device)
+    check(lib.btc_rulebook_subm(_ptr(coords), n, None, int(batch), int3(shape), int3(ksize), int3(dilation),
+                                _ptr(index.entries), index.entries.numel(), _ptr(index.perm), _ptr(nbr), _stream()),
+          "btc_rulebook_subm")
+    return Rulebook(nbr, None, coords, n, n, K, True, list(shape), list(shape), ksize, [1, 1, 1],
+                    [k // 2 for k in ksize], dilation, False, index)
+
+
+def _out_bound(n_in, ksize, stride, transposed, cells):
+    if transposed:
+        b = n_in * ksize[0] * ksize[1] * ksize[2]
+    else:
+        b = n_in
+        for k, s in zip(ksize, stride):
+            b *= -(-k // s)
+    return max(1, min(b, cells))
+
+
+def rulebook_conv(coords: torch.Tensor, batch: int, in_shape, ksize, stride=1, padding=0, dilation=1,
+                  transposed=False, output_padding=0, out_cap: Optional[int] = None) -> Rulebook:
+    """Regular / transposed sparse conv (and pooling) rulebook.  One host read of n_out."""
+    _require_cuda(coords)
+    lib = _lib.load()
+    ksize, stride, padding, dilation = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    output_padding = _triple(output_padding)
+    in_shape = [int(v) for v in in_shape]
+    if transposed:
+        out_shape = deconv_output_shape(in_shape, ksize, stride, padding, dilation, output_padding)
+    else:
+        out_shape = conv_output_shape(in_shape, ksize, stride, padding, dilation)
+    if min(out_shape) <= 0:
+        raise _lib.BtcError("sparse conv output shape %s is empty" % (out_shape,))
+    n_in = coords.shape[0]
+    K = ksize[0] * ksize[1] * ksize[2]
+    dev = coords.device
+    out_entries = index_entries(batch, out_shape)
+    cells = batch * out_shape[0] * out_shape[1] * out_shape[2]
+    cap = out_cap if out_cap is not None else _out_bound(n_in, ksize, stride, transposed, cells)
+    out_index = torch.zeros(out_entries, dtype=torch.int64, device=dev)
+    out_coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    nbr_out = torch.empty((cap, K), dtype=torch.int32, device=dev)
+    nbr_in = torch.empty((max(n_in, 1), K), dtype=torch.int32, device=dev)
+    n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.btc_index_workspace_bytes(out_entries))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.btc_rulebook_conv(_ptr(coords), n_in, None, int(batch), int3(in_shape), int3(out_shape), int3(ksize),
+                                int3(stride), int3(padding), int3(dilation), int(bool(transposed)), _ptr(out_index),
+                                out_entries, _ptr(out_coords), cap, _ptr(n_out_dev), _ptr(nbr_out), _ptr(nbr_in),
+                                _ptr(ws), ws_bytes, _stream()), "btc_rulebook_conv")
+    n_out = int(n_out_dev.item())  # the one host sync of a new rulebook (exact tensor shapes for torch)
+    if n_out > cap:
+        raise _lib.BtcError("rulebook capacity exceeded: %d output sites > capacity %d" % (n_out, cap))
+    idx = CoordIndex(out_index, None, int(batch), out_shape)
+    return Rulebook(nbr_out[:n_out], nbr_in[:n_in], out_coords[:n_out], n_in, n_out, K, False, in_shape, out_shape,
+                    ksize, stride, padding, dilation, bool(transposed), idx)
+
+
+def rulebook_pairs(table: torch.Tensor, n_in: int, K: int, mirror: bool):
+    lib = _lib.load()
+    dev = table.device
+    table = table.contiguous()
+    pairs = torch.empty((2, K, max(n_in, 1)), dtype=torch.int32, device=dev)
+    pair_num = torch.empty(K, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.btc_rulebook_pairs_workspace_bytes(n_in, K))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.btc_rulebook_pairs(_ptr(table), n_in, None, K, int(mirror), _ptr(pairs), _ptr(pair_num), _ptr(ws),
+                                 ws_bytes, _stream()), "btc_rulebook_pairs")
+    return pairs[:, :, :n_in], pair_num
+
+
+# ------------------------------------------------------------------------------------------
+# arithmetic
+# ------------------------------------------------------------------------------------------
+def sparse_conv_fwd(features, nbr_out, weight, bias=None, scale=None, shift=None, relu=False, algo=0,
+                    n_out_dev=None, out=None):
+    """features [N_in,Cin], nbr_out [N_out,K], weight [K,Cin,Cout] (any [...,Cin,Cout] view) -> [N_out,Cout]."""
+    _require_cuda(features, nbr_out, weight)
+    lib = _lib.load()
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    n_out, K = nbr_out.shape
+    assert features.dtype == torch.float32 and weight.dtype == torch.float32
+    assert features.shape[1] == c_in and weight.numel() == K * c_in * c_out
+    features, weight, nbr_out = features.contiguous(), weight.contiguous(), nbr_out.contiguous()
+    if out is None:
+        out = torch.empty((n_out, c_out), dtype=torch.float32, device=features.device)
+    check(lib.btc_sparse_conv_fwd(_ptr(features), _ptr(nbr_out), _ptr(weight), _ptr(bias), _ptr(scale), _ptr(shift),
+                                  int(bool(relu)), _ptr(out), n_out, _ptr(n_out_dev), K, c_in, c_out, int(algo),
+                                  _stream()), "btc_sparse_conv_fwd")
+    return out
+
+
+def sparse_conv_bwd_data(d_out, table, mirror, weight, n_in):
+    lib = _lib.load()
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    K = table.shape[1]
+    d_out, table, weight = d_out.contiguous(), table.contiguous(), weight.contiguous()
+    d_in = torch.empty((n_in, c_in), dtype=torch.float32, device=d_out.device)
+    ws_bytes = int(lib.btc_sparse_conv_bwd_workspace_bytes(K, c_in, c_out))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d_out.device)
+    check(lib.btc_sparse_conv_bwd_data(_ptr(d_out), _ptr(table), int(bool(mirror)), _ptr(weight), _ptr(d_in), n_in,
+                                       None, K, c_in, c_out, _ptr(ws), ws_bytes, _stream()),
+          "btc_sparse_conv_bwd_data")
+    return d_in
+
+
+def sparse_conv_bwd_weight(features, d_out, nbr_out, weight_shape, want_bias):
+    lib = _lib.load()
+    c_in, c_out = weight_shape[-2], weight_shape[-1]
+    n_out, K = nbr_out.shape
+    features, d_out, nbr_out = features.contiguous(), d_out.contiguous(), nbr_out.contiguous()
+    d_w = torch.empty(weight_shape, dtype=torch.float32, device=d_out.device)
+    d_b = torch.empty(c_out, dtype=torch.float32, device=d_out.device) if want_bias else None
+    check(lib.btc_sparse_conv_bwd_weight(_ptr(features), _ptr(d_out), _ptr(nbr_out), _ptr(d_w), _ptr(d_b), n_out,
+                                         None, K, c_in, c_out, _stream()), "btc_sparse_conv_bwd_weight")
+    return d_w, d_b
+
+
+class SparseConvFunction(torch.autograd.Function):
+    """indice_conv of spconv.ops with autograd (forward + dX + dW + db on the CUDA library)."""
+
+    @staticmethod
+    def forward(ctx, features, weight, bias, rulebook: Rulebook, algo):
+        out = sparse_conv_fwd(features, rulebook.nbr_out, weight, bias, algo=algo)
+        ctx.save_for_backward(features, weight)
+        ctx.rulebook = rulebook
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        features, weight = ctx.saved_tensors
+        rb = ctx.rulebook
+        d_out = d_out.contiguous()
+        d_feat = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            table, mirror = (rb.nbr_out, True) if rb.subm else (rb.nbr_in, False)
+            d_feat = sparse_conv_bwd_data(d_out, table, mirror, weight, features.shape[0])
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            d_w, d_b = sparse_conv_bwd_weight(features, d_out, rb.nbr_out, tuple(weight.shape), ctx.has_bias)
+        return d_feat, d_w, d_b, None, None
+
+
+def maxpool_fwd(features, nbr_out):
+    lib = _lib.load()
+    _require_cuda(features, nbr_out)
+    n_out, K = nbr_out.shape
+    c = features.shape[1]
+    features, nbr_out = features.contiguous(), nbr_out.contiguous()
+    out = torch.empty((n_out, c), dtype=torch.float32, device=features.device)
+    check(lib.btc_maxpool_fwd(_ptr(features), _ptr(nbr_out), _ptr(out), n_out, None, K, c, _stream()),
+          "btc_maxpool_fwd")
+    return out
+
+
+class SparseMaxPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rulebook: Rulebook):
+        out = maxpool_fwd(features, rulebook.nbr_out)
+        ctx.save_for_backward(features, out)
+        ctx.rulebook = rulebook
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        features, out = ctx.saved_tensors
+        rb = ctx.rulebook
+        d_out = d_out.contiguous()
+        n_in, c = features.shape
+        d_in = torch.empty_like(features)
+        check(lib.btc_maxpool_bwd(_ptr(features), _ptr(out), _ptr(d_out), _ptr(rb.nbr_out.contiguous()), _ptr(d_in),
+                                  n_in, rb.nbr_out.shape[0], None, rb.K, c, _stream()), "btc_maxpool_bwd")
+        return d_in, None
+
+
+class ToDenseFunction(torch.autograd.Function):
+    """SparseConvTensor.dense(): [N,C] rows -> [B,C,D,H,W] (channels first)."""
+
+    @staticmethod
+    def forward(ctx, features, coords, batch, shape):
+        lib = _lib.load()
+        _require_cuda(features, coords)
+        features, coords = features.contiguous(), coords.contiguous()
+        n, c = features.shape
+        out = torch.empty((batch, c, shape[0], shape[1], shape[2]), dtype=torch.float32, device=features.device)
+        check(lib.btc_to_dense(_ptr(features), _ptr(coords), n, None, c, int(batch), int3(shape), _ptr(out), _stream()),
+              "btc_to_dense")
+        ctx.save_for_backward(coords)
+        ctx.geom = (n, c, int(batch), list(shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        (coords,) = ctx.saved_tensors
+        n, c, batch, shape = ctx.geom
+        d_out = d_out.contiguous()
+        d_feat = torch.empty((n, c), dtype=torch.float32, device=d_out.device)
+        check(lib.btc_from_dense(_ptr(d_out), _ptr(coords), n, None, c, batch, int3(shape), _ptr(d_feat), _stream()),
+              "btc_from_dense")
+        return d_feat, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# voxelisation
+# ------------------------------------------------------------------------------------------
+def voxelize(points: torch.Tensor, scene_offsets: torch.Tensor, voxel_size, coors_range, max_points: int,
+             max_voxels: int, want_mean=False, grid=None):
+    """GPU VoxelGeneratorV2.generate over a batch of scenes.
+
+    points [N, C] f32 cuda (all scenes concatenated), scene_offsets [B+1] i32 cuda.
+    Returns (voxels [cap,P,C], coords [cap,4] (b,z,y,x), num_points [cap], mean or None, n_voxels [B+1] device).
+    Rows beyond n_voxels[B] are unspecified; no host sync is performed.
+    """
+    _require_cuda(points, scene_offsets)
+    lib = _lib.load()
+    assert points.dtype == torch.float32 and points.dim() == 2 and points.is_contiguous()
+    assert scene_offsets.dtype == torch.int32
+    n, c = points.shape
+    n_scenes = scene_offsets.numel() - 1
+    if grid is None:
+        grid = voxel_grid_size(voxel_size, coors_range)
+    dev = points.device
+    cap = n_scenes * max_voxels
+    voxels = torch.empty((cap, max_points, c), dtype=torch.float32, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num_points = torch.empty(cap, dtype=torch.int32, device=dev)
+    mean = torch.empty((cap, c), dtype=torch.float32, device=dev) if want_mean else None
+    n_voxels = torch.empty(n_scenes + 1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.btc_voxelize_workspace_bytes(n, n_scenes, max_voxels, max_points))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.btc_voxelize(_ptr(points), n, c, _ptr(scene_offsets), n_scenes, float_array(voxel_size),
+                           float_array(coors_range), int3(grid), int(max_points), int(max_voxels), _ptr(voxels),
+                           _ptr(coords), _ptr(num_points), _ptr(mean), _ptr(n_voxels), _ptr(ws), ws_bytes, _stream()),
+          "btc_voxelize")
+    return voxels, coords, num_points, mean, n_voxels
+
+
+def voxel_grid_size(voxel_size, coors_range):
+    """grid = round((max - min) / voxel_size) with float32 operands, as VoxelGeneratorV2.__init__ computes it."""
+    import numpy as np
+    r = np.array(coors_range, dtype=np.float32)
+    v = np.array(voxel_size, dtype=np.float32)
+    return [int(g) for g in np.round((r[3:] - r[:3]) / v).astype(np.int64)]
+
+
+def revoxelize_sorted(pt_coords: torch.Tensor, pt_feat: torch.Tensor, batch: int, shape):
+    """torch.unique(coords, dim=0, sorted)+pad of add_occ_template.py:248-268 on the rank bitmap.
+
+    Returns (voxels [M, Pmax, C], voxel_num_points [M] i64, voxel_coords [M,4] i64) like the reference.
+    """
+    _require_cuda(pt_coords, pt_feat)
+    lib = _lib.load()
+    dev = pt_coords.device
+    pc = pt_coords.to(torch.int32).contiguous()
+    pt_feat = pt_feat.to(torch.float32).contiguous()
+    n, c = pt_feat.shape
+    n_entries = index_entries(batch, shape)
+    index = torch.zeros(n_entries, dtype=torch.int64, device=dev)
+    vox_coords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    vox_count = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    slots = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    pt_voxel = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.btc_revoxelize_workspace_bytes(n, n_entries))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.btc_revoxelize(_ptr(pc), n, None, int(batch), int3(shape), _ptr(index), n_entries, _ptr(vox_coords), n,
+                             _ptr(vox_count), _ptr(slots), _ptr(pt_voxel), _ptr(counts[0:1]), _ptr(counts[1:2]),
+                             _ptr(ws), ws_bytes, _stream()), "btc_revoxelize")
+    m, pmax = [int(v) for v in counts.tolist()]  # one host read: exact shapes for the torch modules downstream
+    voxels = torch.empty((m, pmax, c), dtype=torch.float32, device=dev)
+    check(lib.btc_revoxelize_fill(_ptr(pt_feat), _ptr(pt_voxel), _ptr(slots), n, None, c, pmax, _ptr(voxels), m,
+                                  _stream()), "btc_revoxelize_fill")
+    return voxels, vox_count[:m].to(torch.int64), vox_coords[:m].to(torch.int64)

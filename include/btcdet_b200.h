@@ -1,0 +1,289 @@
+/*
+ * btcdet_b200.h — C ABI of the B200-native (sm_100a) hot path of BtcDet.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI of
+ * its own: its sparse path is reached through the `spconv` Python package
+ * (spconv v1.2.1, un-vendored) and through torch index ops.  Every entry point
+ * below names the reference call site / interface it replaces (paths relative
+ * to the reference checkout).  The host side (the `spconv/` shim package and
+ * `btcdet_b200/`) binds these with ctypes — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", POD arguments only: device pointers, sizes, host geometry
+ *     arrays, a `void* stream` (cudaStream_t).  No torch types.
+ *   - The caller owns every buffer, including workspaces (`*_workspace_bytes`
+ *     query functions).  The library never calls cudaMalloc / cudaFree /
+ *     cudaDeviceSynchronize and is safe under CUDA-graph capture.
+ *   - Counts produced on the device (number of voxels, number of output
+ *     sites, pairs per offset) are written to device memory; the caller may
+ *     copy them to the host when it needs exact tensor shapes.
+ *   - Counts consumed by a kernel come as a capacity (`n_cap`, host int, sizes
+ *     the grid) plus an optional device pointer `n_dev` holding the live
+ *     count (NULL → the capacity is the count).
+ *   - Coordinates are int32 rows (b, z, y, x) as in spconv.SparseConvTensor
+ *     (.indices, btcdet/models/backbones_3d/spconv_backbone.py:155-160).
+ *   - Kernel offsets are numbered row-major over (kz, ky, kx), kx fastest; a
+ *     pair (in -> out) exists at offset k iff  out*stride - pad + k*dil == in
+ *     per axis (transposed: out == in*stride - pad + k*dil).
+ *   - "Neighbour tables" are int32 [N, K] arrays holding a row index or -1.
+ *     `nbr_out[o][k]` = the input row feeding output row o through offset k
+ *     (output-stationary, what the conv kernels consume); `nbr_in[i][k]` =
+ *     the output row that input row i feeds through offset k.
+ *   - Return value: 0 on success, negative BTC_E_* otherwise.  No exceptions,
+ *     no exit().
+ */
+#ifndef BTCDET_B200_H
+#define BTCDET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTC_OK 0
+#define BTC_E_BADARG (-1)
+#define BTC_E_CAPACITY (-2)
+#define BTC_E_CUDA (-3)
+#define BTC_E_UNSUPPORTED (-4)
+
+/* Library / build identification. Returns e.g. 100 for sm_100a builds. */
+int btc_abi_version(void);
+int btc_compiled_sm(void);
+/* Last CUDA error string captured by a failing call (thread-local, static storage). */
+const char* btc_last_error(void);
+
+/* ------------------------------------------------------------------------- */
+/* Point -> voxel grouping                                                    */
+/* Replaces spconv.utils.VoxelGeneratorV2.generate (spconv 1.2.1             */
+/* points_to_voxel_3d_np), call sites                                         */
+/* btcdet/datasets/processor/data_processor.py:68-73,85 / :112-117,136 /      */
+/* :165-170,177, plus the batch-index padding of                              */
+/* btcdet/datasets/dataset.py:187-192 (collate_batch).                        */
+/*                                                                            */
+/* Semantics (bit-exact with the sequential reference): per scene, points in  */
+/* input order; c = floor((p - range_min) / voxel_size) per axis in fp32;     */
+/* dropped if outside [0, grid); voxel ids in first-come order; at most       */
+/* `max_voxels` voxels per scene (later-first-seen voxels dropped); the first */
+/* `max_points` points of a voxel kept in input order; padding slots zero.    */
+/* ------------------------------------------------------------------------- */
+
+/* Bytes of workspace btc_voxelize needs for up to n_points points. */
+int64_t btc_voxelize_workspace_bytes(int64_t n_points, int n_scenes, int max_voxels, int max_points);
+
+/*
+ * points        [n_points, n_feat] f32 device; columns 0..2 are the coordinates
+ *               that get quantised (x, y, z order of voxel_size / range).
+ * scene_offsets [n_scenes + 1] i32 device: points of scene b are rows
+ *               [scene_offsets[b], scene_offsets[b+1]).
+ * voxel_size[3], range[6]  host, same order as the reference ctor kwargs.
+ * grid[3]       host (x, y, z) = round((max - min) / voxel_size).
+ * Outputs (capacity n_scenes * max_voxels rows):
+ *   voxels     [cap, max_points, n_feat] f32   (zero padded)
+ *   coords     [cap, 4] i32 (b, z, y, x)
+ *   num_points [cap] i32
+ *   voxel_mean [cap, n_feat] f32 or NULL: sum over valid slots / max(count,1)
+ *              (MeanVFE, btcdet/models/backbones_3d/vfe/mean_vfe.py:27-44)
+ *   n_voxels   [n_scenes + 1] i32 device: [0..n_scenes) per-scene counts,
+ *              [n_scenes] the total (rows are scene-major, compact).
+ */
+int btc_voxelize(const float* points, int n_points, int n_feat,
+                 const int* scene_offsets, int n_scenes,
+                 const float* voxel_size, const float* range, const int* grid,
+                 int max_points, int max_voxels,
+                 float* voxels, int* coords, int* num_points, float* voxel_mean,
+                 int* n_voxels,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Coordinate index ("rank bitmap")                                            */
+/* Replaces the dense int32 `grid` / cuckoo hash of spconv 1.2.1              */
+/* (SparseConvTensor.grid, ops.get_indice_pairs use_hash) as the coordinate → */
+/* row lookup.  One 8-byte entry per 32 cells: low word = occupancy bits of   */
+/* cells [32w, 32w+32) in flat (b,z,y,x) row-major order, high word = number  */
+/* of occupied cells before the word.  rank(cell) is therefore the position   */
+/* of the cell in ascending flat-key order — the order spconv's GPU path      */
+/* gives to conv outputs (torch::_unique of flat indices).                    */
+/* ------------------------------------------------------------------------- */
+
+/* Number of 8-byte entries of an index over batch × shape[0..2] (z, y, x) cells. */
+int64_t btc_index_entries(int batch, const int* shape);
+/* Workspace bytes for btc_index_build / rulebook builds over that many entries. */
+int64_t btc_index_workspace_bytes(int64_t n_entries);
+
+/*
+ * Build the index of `coords` (rows must be unique).  `index` must be zeroed
+ * by the caller (cudaMemsetAsync) or cleared with btc_index_clear.
+ *   perm  [n_cap] i32 or NULL: perm[rank(coords[i])] = i, needed when the rows
+ *         are not already in ascending flat-key order.
+ *   total [1] i32 device or NULL: number of occupied cells.
+ */
+int btc_index_build(const int* coords, int n_cap, const int* n_dev,
+                    int batch, const int* shape,
+                    uint64_t* index, int64_t n_entries, int* perm, int* total,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Zero the index words touched by `coords` (cheaper than a full memset). */
+int btc_index_clear(const int* coords, int n_cap, const int* n_dev,
+                    int batch, const int* shape, uint64_t* index, int64_t n_entries,
+                    void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Rulebooks ("indice pairs")                                                  */
+/* Replace spconv.ops.get_indice_pairs (spconv 1.2.1 src/spconv/indice.cu:    */
+/* prepareSubMGridKernel/getSubMIndicePairsKernel, prepareIndicePairsKernel/  */
+/* assignGridAndIndiceOutKernel/assignIndicePairsKernel) reached from         */
+/* SparseConvolution.forward — reference call sites                           */
+/* btcdet/models/backbones_3d/spconv_backbone.py:12-29,106-128,657-707.       */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Submanifold rulebook: output sites == input sites, same row order.
+ * `index`/`perm` must have been built over `coords` with btc_index_build.
+ *   nbr_out [n_cap, K] i32: nbr_out[o][k] = input row at coords[o] + (k - K/2)*dil, or -1.
+ * (nbr_in is the mirror image: nbr_in[i][k] == nbr_out[i][K-1-k].)
+ */
+int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev,
+                      int batch, const int* shape, const int* ksize, const int* dilation,
+                      const uint64_t* index, int64_t n_entries, const int* perm,
+                      int* nbr_out, void* stream);
+
+/*
+ * Regular (strided) or transposed sparse convolution / pooling rulebook.
+ *   out_index [out_entries] zeroed by the caller; on return it is the rank
+ *             bitmap of the output sites (rows in ascending flat-key order,
+ *             so no perm is needed for it).
+ *   out_coords [out_cap, 4], n_out [1] device: the output sites, ascending.
+ *   nbr_out [out_cap, K], nbr_in [n_in_cap, K] (either may be NULL).
+ * Returns BTC_E_CAPACITY semantics on the device: if the number of output
+ * sites exceeds out_cap, n_out still holds the true count and rows >= out_cap
+ * are not written (the caller checks n_out when it reads it back).
+ */
+int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev,
+                      int batch, const int* in_shape, const int* out_shape,
+                      const int* ksize, const int* stride, const int* padding,
+                      const int* dilation, int transposed,
+                      uint64_t* out_index, int64_t out_entries,
+                      int* out_coords, int out_cap, int* n_out,
+                      int* nbr_out, int* nbr_in,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Workspace bytes for btc_rulebook_pairs. */
+int64_t btc_rulebook_pairs_workspace_bytes(int n_in_cap, int K);
+
+/*
+ * spconv-1.2.1-format rulebook in canonical order:
+ *   pairs    [2, K, n_in_cap] i32, -1 padded: pairs[0][k][s] = input row,
+ *            pairs[1][k][s] = output row, sorted by input row within offset k.
+ *   pair_num [K] i32.
+ * Built from an input-major table nbr_in [n_in_cap, K]; `mirror` != 0 reads
+ * nbr_in[i][k] as table[i][K-1-k] (submanifold tables, see btc_rulebook_subm).
+ */
+int btc_rulebook_pairs(const int* table, int n_in_cap, const int* n_in_dev, int K, int mirror,
+                       int* pairs, int* pair_num,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Sparse convolution arithmetic                                               */
+/* Replaces spconv.ops.indice_conv / indice_conv_backward (spconv 1.2.1       */
+/* src/spconv/spconv_ops.cc: per-offset gather -> torch::mm -> scatter-add,   */
+/* reordering.cu gather/scatter kernels) behind SubMConv3d / SparseConv3d /   */
+/* SparseConvTranspose3d / SparseInverseConv3d.forward.                       */
+/* The replacement is one output-stationary gather-GEMM kernel: each output   */
+/* row accumulates sum_k feat_in[nbr_out[o][k]] @ W[k] in ascending k, is     */
+/* written once, no atomics (deterministic).                                  */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * feat_in  [n_in, c_in] f32, nbr_out [n_out_cap, K] i32,
+ * weight   [K, c_in, c_out] f32 (spconv 1.2.1 layout [kD,kH,kW,Cin,Cout]),
+ * bias     [c_out] or NULL,
+ * scale/shift [c_out] or NULL: fused per-channel affine applied after bias
+ *          (eval-mode BatchNorm1d folded: y = conv*scale + shift),
+ * relu     != 0: fused ReLU after the affine,
+ * feat_out [n_out_cap, c_out] f32.
+ * algo: 0 = auto, 1 = fp32 FFMA tiles, 2 = tcgen05 3xTF32 tensor-core tiles
+ *       (returns BTC_E_UNSUPPORTED when the shape does not qualify).
+ */
+int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out,
+                        const float* weight, const float* bias,
+                        const float* scale, const float* shift, int relu,
+                        float* feat_out, int n_out_cap, const int* n_out_dev,
+                        int K, int c_in, int c_out, int algo, void* stream);
+
+/*
+ * d feat_in [n_in_cap, c_in] = sum_k d_out[nbr_in[i][k]] @ W[k]^T.
+ * `mirror` != 0 reads nbr_in[i][k] as table[i][K-1-k] (submanifold).
+ * workspace: K * c_in * c_out floats (transposed weights).
+ */
+int64_t btc_sparse_conv_bwd_workspace_bytes(int K, int c_in, int c_out);
+int btc_sparse_conv_bwd_data(const float* d_out, const int* table, int mirror,
+                             const float* weight,
+                             float* d_in, int n_in_cap, const int* n_in_dev,
+                             int K, int c_in, int c_out,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * d weight [K, c_in, c_out] = sum_o feat_in[nbr_out[o][k]]^T (x) d_out[o];
+ * d_bias [c_out] (or NULL) = sum_o d_out[o].   d_weight is overwritten.
+ */
+int btc_sparse_conv_bwd_weight(const float* feat_in, const float* d_out, const int* nbr_out,
+                               float* d_weight, float* d_bias,
+                               int n_out_cap, const int* n_out_dev,
+                               int K, int c_in, int c_out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* SparseMaxPool3d (spconv 1.2.1 src/spconv/maxpool.cu) —                     */
+/* btcdet/models/backbones_3d/spconv_backbone.py:29,831-847.                  */
+/* out is zero-initialised, out[o] = max(out[o], in[i]) over the pairs        */
+/* (negative inputs clamp to 0).                             */
+/* ------------------------------------------------------------------------- */
+int btc_maxpool_fwd(const float* feat_in, const int* nbr_out, float* feat_out,
+                    int n_out_cap, const int* n_out_dev, int K, int c, void* stream);
+/* d_in[i] += d_out[o] where feat_in[i] == feat_out[o] over the pairs (d_in zeroed inside). */
+int btc_maxpool_bwd(const float* feat_in, const float* feat_out, const float* d_out,
+                    const int* nbr_out, float* d_in, int n_in,
+                    int n_out_cap, const int* n_out_dev, int K, int c, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* SparseConvTensor.dense()  (spconv 1.2.1 SparseConvTensor.dense; call sites */
+/* occ_head_3D.py:46,51, height_compression.py:21, spconv_backbone.py:890,930)*/
+/* out [batch, c, D, H, W] f32 is zero-filled then rows are scattered.        */
+/* ------------------------------------------------------------------------- */
+int btc_to_dense(const float* feat, const int* coords, int n_cap, const int* n_dev,
+                 int c, int batch, const int* shape, float* out, void* stream);
+/* Backward of dense(): d_feat[i][ch] = d_out[b, ch, z, y, x]. */
+int btc_from_dense(const float* d_out, const int* coords, int n_cap, const int* n_dev,
+                   int c, int batch, const int* shape, float* d_feat, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Sorted re-voxelisation of labelled points                                   */
+/* Replaces AddOccTemplate.combine_gt_occ_voxel_point + voxelize_pad          */
+/* (btcdet/models/occ_pnt/add_occ_template.py:248-268): torch.unique(coords,  */
+/* dim=0, sorted) + sort(inverse) + dense pad, without the host sync.         */
+/* ------------------------------------------------------------------------- */
+int64_t btc_revoxelize_workspace_bytes(int n_points, int64_t n_entries);
+/*
+ * pt_coords [n, 4] i32 (b,z,y,x), pt_feat [n, c] f32.
+ * index [n_entries] zeroed by the caller (rank bitmap of the det grid).
+ * Outputs: vox_coords [cap,4] ascending (b,z,y,x); vox_count [cap];
+ *          slots [n] i32: position of point i inside its voxel (stable, by
+ *          input order); pt_voxel [n] i32: voxel row of point i;
+ *          n_voxels [1], max_count [1] device.
+ * The caller pads with btc_revoxelize_fill once it knows / bounds max_count.
+ */
+int btc_revoxelize(const int* pt_coords, int n_cap, const int* n_dev,
+                   int batch, const int* shape,
+                   uint64_t* index, int64_t n_entries,
+                   int* vox_coords, int vox_cap, int* vox_count,
+                   int* slots, int* pt_voxel, int* n_voxels, int* max_count,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+/* voxels [vox_rows, p_max, c] zero-filled, then voxels[pt_voxel[i]][slots[i]] = pt_feat[i] (slots >= p_max dropped). */
+int btc_revoxelize_fill(const float* pt_feat, const int* pt_voxel, const int* slots,
+                        int n_cap, const int* n_dev, int c, int p_max,
+                        float* voxels, int vox_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTCDET_B200_H */
