@@ -182,7 +182,8 @@ int64_t btc_index_workspace_bytes(int64_t n_entries) {
 
 int btc_index_build(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, uint64_t* index,
                     int64_t n_entries, int* perm, int* total, void* workspace, int64_t workspace_bytes, void* stream) {
-    if (!coords || !index || !shape || !workspace) return badarg("btc_index_build: null argument");
+    if (!index || !shape || !workspace) return badarg("btc_index_build: null argument");
+    if (n_cap > 0 && !coords) return badarg("btc_index_build: null coordinates");
     if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_index_build: n_entries mismatch");
     if (workspace_bytes < btc_index_workspace_bytes(n_entries)) return badarg("btc_index_build: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -204,7 +205,8 @@ int btc_index_build(const int* coords, int n_cap, const int* n_dev, int batch, c
 
 int btc_index_clear(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, uint64_t* index,
                     int64_t n_entries, void* stream) {
-    if (!coords || !index || !shape) return badarg("btc_index_clear: null argument");
+    if (!index || !shape) return badarg("btc_index_clear: null argument");
+    if (n_cap > 0 && !coords) return badarg("btc_index_clear: null coordinates");
     if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_index_clear: n_entries mismatch");
     if (n_cap <= 0) return BTC_OK;
     Shape3 s{shape[0], shape[1], shape[2]};

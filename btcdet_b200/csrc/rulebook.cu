@@ -243,7 +243,8 @@ extern "C" {
 int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, const int* ksize,
                       const int* dilation, const uint64_t* index, int64_t n_entries, const int* perm, int* nbr_out,
                       void* stream) {
-    if (!coords || !shape || !ksize || !index || !nbr_out) return badarg("btc_rulebook_subm: null argument");
+    if (!shape || !ksize || !index) return badarg("btc_rulebook_subm: null argument");
+    if (n_cap > 0 && (!coords || !nbr_out)) return badarg("btc_rulebook_subm: null coordinates");
     if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_rulebook_subm: n_entries mismatch");
     ConvGeom g;
     int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
@@ -261,8 +262,9 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, i
                       const int* dilation, int transposed, uint64_t* out_index, int64_t out_entries, int* out_coords,
                       int out_cap, int* n_out, int* nbr_out, int* nbr_in, void* workspace, int64_t workspace_bytes,
                       void* stream) {
-    if (!coords_in || !in_shape || !out_shape || !ksize || !out_index || !out_coords || !n_out || !workspace)
+    if (!in_shape || !out_shape || !ksize || !out_index || !n_out || !workspace)
         return badarg("btc_rulebook_conv: null argument");
+    if (n_in_cap > 0 && (!coords_in || !out_coords)) return badarg("btc_rulebook_conv: null coordinates");
     if (out_entries != btc_index_entries(batch, out_shape)) return badarg("btc_rulebook_conv: out_entries mismatch");
     if (workspace_bytes < btc_index_workspace_bytes(out_entries)) return badarg("btc_rulebook_conv: workspace too small");
     ConvGeom g;
@@ -278,8 +280,9 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, i
     }
     int rc = launch_index_scan((uint2*)out_index, out_entries, (int*)workspace, n_out, st);
     if (rc) return rc;
-    conv_emit_kernel<<<grid_for(out_entries, T), T, 0, st>>>((const uint2*)out_index, out_entries, g.out, out_cap, g.K,
-                                                            (int4*)out_coords, nbr_out);
+    if (out_cap > 0 && out_coords)
+        conv_emit_kernel<<<grid_for(out_entries, T), T, 0, st>>>((const uint2*)out_index, out_entries, g.out, out_cap, g.K,
+                                                                (int4*)out_coords, nbr_out);
     if (nbr_out && out_cap > 0)
         fill_table_kernel<<<grid_for((int64_t)out_cap * g.K, T), T, 0, st>>>(nbr_out, out_cap, n_out, g.K);
     if (n_in_cap > 0 && (nbr_out || nbr_in))

@@ -1,0 +1,245 @@
+"""Sync-free planned forward of a sparse backbone, replayed as ONE CUDA graph per step.
+
+The eager `spconv` shim keeps spconv-1.2.1 semantics for arbitrary torch code (exact tensor shapes,
+one host read per new rulebook).  For serving, the same layers are compiled here into a static
+launch sequence over capacity-sized buffers: every C-ABI call takes its live row count from device
+memory (`n_dev`), so points -> voxels -> rulebooks -> convolutions run without a single host
+synchronisation and the whole step is captured in a CUDA graph (one launch from the host instead of
+the ~2 000 launches of the reference's per-offset gather/SGEMM/scatter path).
+Eval-mode BatchNorm1d (btcdet/models/backbones_3d/spconv_backbone.py:33-38, eps 1e-3) is folded into
+the conv epilogue as a per-channel affine, ReLU fused.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+import spconv
+
+from . import _lib, ops
+from ._lib import check, float_array, int3
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+@dataclass
+class _Level:
+    shape: list          # [D, H, W]
+    cap: int
+    coords: torch.Tensor     # [cap, 4] i32
+    n_dev: torch.Tensor      # [1] i32 view
+    index: Optional[torch.Tensor] = None   # rank bitmap (int64 entries)
+    perm: Optional[torch.Tensor] = None
+
+
+@dataclass
+class _Step:
+    kind: str            # "index_build" | "subm_rb" | "conv_rb" | "conv"
+    args: tuple
+
+
+def fold_bn(bn: torch.nn.BatchNorm1d):
+    """Eval-mode BN as y = x*scale + shift."""
+    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+    shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+    return scale, shift
+
+
+class BackbonePlan:
+    """points [N,4] -> GPU voxelisation -> MeanVFE -> sequential sparse backbone, one CUDA graph.
+
+    layer_specs: list of (spconv.SparseConvolution, BatchNorm1d | None) in execution order
+    (e.g. backbones.VoxelBackBone8x.layer_specs()), each consuming the previous layer's output.
+    """
+
+    def __init__(self, layer_specs, sparse_shape, batch, max_points_total, voxel_size, point_range, max_points=5,
+                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.batch = int(batch)
+        self.voxel_size, self.point_range = list(voxel_size), list(point_range)
+        self.grid = ops.voxel_grid_size(voxel_size, point_range)
+        self.max_points, self.max_voxels = int(max_points), int(max_voxels)
+        self.n_cap = int(max_points_total)
+        self.algo = int(algo)
+        self.use_graph = use_graph
+        dev = self.device
+        B = self.batch
+        # ---- static input + voxelisation buffers ------------------------------------------
+        self.points = torch.zeros((self.n_cap, 4), dtype=torch.float32, device=dev)
+        self.scene_offsets = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        cap1 = B * self.max_voxels
+        self.voxels = torch.empty((cap1, self.max_points, 4), dtype=torch.float32, device=dev)
+        self.num_points = torch.empty(cap1, dtype=torch.int32, device=dev)
+        self.n_voxels = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.vox_ws = torch.empty(int(self.lib.btc_voxelize_workspace_bytes(self.n_cap, B, self.max_voxels,
+                                                                             self.max_points)),
+                                  dtype=torch.uint8, device=dev)
+        self.counts = []          # device count tensors to read back (overflow check / output size)
+        # ---- levels, rulebooks, feature buffers ---------------------------------------------
+        shape0 = [int(s) for s in sparse_shape]
+        lvl = _Level(shape0, cap1, torch.empty((cap1, 4), dtype=torch.int32, device=dev), self.n_voxels[B:B + 1])
+        self.levels = [lvl]
+        self.feat0 = torch.empty((cap1, 4), dtype=torch.float32, device=dev)   # MeanVFE output
+        self.steps: List[_Step] = []
+        self.rulebooks = {}
+        self._ws = {}
+        cur_feat, cur_lvl = self.feat0, lvl
+        self.params = []  # keep folded tensors alive
+        for conv, bn in layer_specs:
+            assert isinstance(conv, spconv.SparseConvolution) and conv.ndim == 3 and not conv.inverse
+            K = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
+            key = conv.indice_key
+            rb = self.rulebooks.get(key) if key is not None else None
+            if rb is None:
+                if conv.subm:
+                    if cur_lvl.index is None:
+                        self._add_index(cur_lvl)
+                    nbr = torch.empty((cur_lvl.cap, K), dtype=torch.int32, device=dev)
+                    self.steps.append(_Step("subm_rb", (cur_lvl, conv.kernel_size, conv.dilation, nbr)))
+                    rb = (nbr, cur_lvl)
+                else:
+                    assert not conv.transposed, "planned engine covers the det backbone (no transposed convs)"
+                    out_shape = ops.conv_output_shape(cur_lvl.shape, conv.kernel_size, conv.stride, conv.padding,
+                                                      conv.dilation)
+                    cells = B * out_shape[0] * out_shape[1] * out_shape[2]
+                    cap = int(min(cells, max(1024, level_growth * cur_lvl.cap)))
+                    n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+                    out_lvl = _Level(out_shape, cap, torch.empty((cap, 4), dtype=torch.int32, device=dev), n_dev)
+                    out_lvl.index = torch.zeros(ops.index_entries(B, out_shape), dtype=torch.int64, device=dev)
+                    nbr = torch.empty((cap, K), dtype=torch.int32, device=dev)
+                    self.steps.append(_Step("conv_rb", (cur_lvl, out_lvl, conv.kernel_size, conv.stride, conv.padding,
+                                                        conv.dilation, nbr)))
+                    self.levels.append(out_lvl)
+                    self.counts.append((n_dev, cap))
+                    rb = (nbr, out_lvl)
+                if key is not None:
+                    self.rulebooks[key] = rb
+            nbr, out_lvl = rb
+            w = conv.weight.detach().to(dev, torch.float32).reshape(K, conv.in_channels, conv.out_channels).contiguous()
+            bias = None if conv.bias is None else conv.bias.detach().to(dev, torch.float32).contiguous()
+            scale = shift = None
+            if bn is not None:
+                scale, shift = (t.to(dev) for t in fold_bn(bn))
+            out_feat = torch.empty((out_lvl.cap, conv.out_channels), dtype=torch.float32, device=dev)
+            self.params.append((w, bias, scale, shift))
+            self.steps.append(_Step("conv", (cur_feat, nbr, w, bias, scale, shift, bn is not None, out_feat, out_lvl, K,
+                                             conv.in_channels, conv.out_channels)))
+            cur_feat, cur_lvl = out_feat, out_lvl
+        self.out_feat, self.out_lvl = cur_feat, cur_lvl
+        self.graph = None
+        self.launches_per_step = 0
+        self.host_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32).pin_memory()
+        self.dev_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------------------------
+    def _add_index(self, lvl: _Level):
+        lvl.index = torch.zeros(ops.index_entries(self.batch, lvl.shape), dtype=torch.int64, device=self.device)
+        lvl.perm = torch.empty(lvl.cap, dtype=torch.int32, device=self.device)
+        self.steps.append(_Step("index_build", (lvl,)))
+
+    def _workspace(self, nbytes):
+        ws = self._ws.get("ws")
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws["ws"] = ws
+        return ws
+
+    def _run(self):
+        """Enqueue the whole step on the current stream (no host synchronisation anywhere)."""
+        lib, B = self.lib, self.batch
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        launches = 0
+        lvl0 = self.levels[0]
+        check(lib.btc_voxelize(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
+                               float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
+                               self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
+                               _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
+                               self.vox_ws.numel(), st), "btc_voxelize")
+        launches += 9
+        for s in self.steps:
+            if s.kind == "index_build":
+                (lvl,) = s.args
+                lvl.index.zero_()
+                ws = self._workspace(lib.btc_index_workspace_bytes(lvl.index.numel()))
+                check(lib.btc_index_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                          _ptr(lvl.index), lvl.index.numel(), _ptr(lvl.perm), None, _ptr(ws),
+                                          ws.numel(), st), "btc_index_build")
+                launches += 6
+            elif s.kind == "subm_rb":
+                lvl, ksize, dil, nbr = s.args
+                check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape), int3(ksize),
+                                            int3(dil), _ptr(lvl.index), lvl.index.numel(), _ptr(lvl.perm), _ptr(nbr),
+                                            st), "btc_rulebook_subm")
+                launches += 1
+            elif s.kind == "conv_rb":
+                lin, lout, ksize, stride, pad, dil, nbr = s.args
+                lout.index.zero_()
+                ws = self._workspace(lib.btc_index_workspace_bytes(lout.index.numel()))
+                check(lib.btc_rulebook_conv(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
+                                            int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
+                                            _ptr(lout.index), lout.index.numel(), _ptr(lout.coords), lout.cap,
+                                            _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
+                      "btc_rulebook_conv")
+                launches += 8
+            else:
+                fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout = s.args
+                check(lib.btc_sparse_conv_fwd(_ptr(fin), _ptr(nbr), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift),
+                                              int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K, cin, cout, self.algo,
+                                              st), "btc_sparse_conv_fwd")
+                launches += 1
+        # gather the live counts of every level into one small tensor (read back lazily by the caller)
+        for i, l in enumerate(self.levels):
+            self.dev_counts[i:i + 1].copy_(l.n_dev)
+        self.launches_per_step = launches
+        return launches
+
+    def capture(self):
+        """Warm up once on a side stream, then capture the step into a CUDA graph."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._run()
+        return self
+
+    def load_points(self, points: torch.Tensor, scene_offsets: torch.Tensor):
+        """Copy one batch (device or pinned-host tensors) into the static input buffers (async)."""
+        n = points.shape[0]
+        if n > self.n_cap:
+            raise _lib.BtcError("batch of %d points exceeds the planned capacity %d" % (n, self.n_cap))
+        self.points[:n].copy_(points, non_blocking=True)
+        self.scene_offsets.copy_(scene_offsets, non_blocking=True)
+
+    def step(self):
+        """Replay the captured step (or enqueue it eagerly when graphs are disabled)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._run()
+
+    def forward(self, points, scene_offsets):
+        self.load_points(points, scene_offsets)
+        self.step()
+        return self.out_feat, self.out_lvl.coords, self.out_lvl.n_dev
+
+    def read_counts(self):
+        """One small D2H copy of every level's live count; raises if a capacity overflowed."""
+        self.host_counts[:len(self.levels)].copy_(self.dev_counts[:len(self.levels)], non_blocking=False)
+        counts = self.host_counts[:len(self.levels)].tolist()
+        for c, l in zip(counts, self.levels):
+            if c > l.cap:
+                raise _lib.BtcError("level capacity exceeded: %d sites > capacity %d — raise level_growth" % (c, l.cap))
+        return counts
+
+    def level_features(self):
+        """(features, coords, n_dev) of the last layer output (capacity-sized buffers)."""
+        return self.out_feat, self.out_lvl.coords, self.out_lvl.n_dev
