@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — scenes/sec of the BtcDet hot path on B200 (BASELINE.json metric, configs[1]).
+
+One step = one pass of  points -> GPU voxelisation (+MeanVFE) -> rulebooks -> VoxelBackBone8x forward
+over one batch of synthetic 20k-point KITTI-range scenes (voxel [0.05,0.05,0.1], C_in=4, fp32,
+random-init weights, eval-mode BatchNorm folded into the conv epilogue).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU)
+  python bench.py --impl reference ...                       the CPU oracle port of the reference path
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: through the host-facing call
+with pinned host buffers, H2D of the points and D2H of the result inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_POINTS = 20000
+N_SCENE_POOL = 24          # distinct pre-generated scenes cycled through the steps
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU")
+    ap.add_argument("--algo", type=int, default=0, help="conv tile: 0 auto, 1 FFMA, 2 tcgen05")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the bounded CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_scenes(rank, count):
+    from btcdet_b200 import synthetic as S
+    return [S.lidar_like(N_POINTS, seed=1000 * rank + i) for i in range(count)]
+
+
+def build_model():
+    from btcdet_b200 import backbones
+    torch.manual_seed(0)
+    return backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+
+
+def layer_bytes_flops(plan, counts):
+    """Algorithmic bytes / flops of every conv launch for the measured live sizes:
+    bytes = 4*N_in*Cin + 4*N_out*Cout + 8*P + 4*K*Cin*Cout ; flops = 2*P*Cin*Cout."""
+    lvl_n = {id(l): c for l, c in zip(plan.levels, counts)}
+    out = []
+    n_in = counts[0]
+    for s in plan.steps:
+        if s.kind != "conv":
+            continue
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout = s.args
+        n_out = lvl_n[id(lout)]
+        pairs = int((nbr[:n_out] >= 0).sum().item())
+        out.append({"n_in": n_in, "n_out": n_out, "pairs": pairs, "K": K, "cin": cin, "cout": cout,
+                    "bytes": 4 * n_in * cin + 4 * n_out * cout + 8 * pairs + 4 * K * cin * cout,
+                    "flops": 2 * pairs * cin * cout})
+        n_in = n_out
+    return out
+
+
+def run_ours(args, rank, world):
+    from btcdet_b200 import _lib, engine, synthetic as S
+    _lib.load()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    B = args.batch
+    model = build_model()
+    plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                               max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
+                               device=dev, use_graph=not args.no_graph).capture()
+    scenes = make_scenes(rank, N_SCENE_POOL)
+    # batches: host pinned (for e2e) and device resident (for value)
+    n_batches = N_SCENE_POOL // B if N_SCENE_POOL >= B else 1
+    host_batches, dev_batches = [], []
+    for i in range(max(n_batches, 1)):
+        sel = [scenes[(i * B + j) % N_SCENE_POOL] for j in range(B)]
+        pts, offs = S.batch_points(sel)
+        hp, ho = torch.from_numpy(pts).pin_memory(), torch.from_numpy(offs).pin_memory()
+        host_batches.append((hp, ho))
+        dev_batches.append((hp.to(dev), ho.to(dev)))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, steps, warmup):
+        for i in range(warmup):
+            run_step(i)
+        barrier()
+        evs = []
+        for i in range(steps):
+            flush.fill_(float(i))          # L2 flush between timed steps (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_step(i)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    def step_dev(i):
+        p, o = dev_batches[i % len(dev_batches)]
+        plan.load_points(p, o)       # D2D into the graph's static input buffer
+        plan.step()
+
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_dev, args.steps, args.warmup)
+    counts = plan.read_counts()
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region -----------------------------------
+    out_host = torch.empty((plan.out_lvl.cap, plan.out_feat.shape[1]), dtype=torch.float32).pin_memory()
+    n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    d2h_bytes = [0]
+
+    def step_e2e(i):
+        p, o = host_batches[i % len(host_batches)]
+        feat, coords, n_dev = plan.forward(p, o)          # pinned H2D + graph replay
+        n_host.copy_(n_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the user needs the row count to size the result
+        n = int(n_host[0])
+        out_host[:n].copy_(feat[:n], non_blocking=True)   # device -> host read of the step's result
+        d2h_bytes[0] = n * feat.shape[1] * 4 + 4
+
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d_bytes = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
+
+    # ---- roofline of the dominant kernel (the gather-GEMM conv), per-launch CUDA events -----------
+    roof = None
+    if rank == 0:
+        specs = layer_bytes_flops(plan, counts)
+        conv_steps = [s for s in plan.steps if s.kind == "conv"]
+        from btcdet_b200._lib import check
+        import ctypes
+        lib = plan.lib
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ptr = engine._ptr
+        tot_ms, reps = 0.0, 5
+        per_layer = []
+        for s, sp in zip(conv_steps, specs):
+            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout = s.args
+            ms_l = 0.0
+            for r in range(reps + 1):
+                flush.fill_(float(r))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                check(lib.btc_sparse_conv_fwd(ptr(fin), ptr(nbr), ptr(w), ptr(bias), ptr(scale), ptr(shift), int(relu),
+                                              ptr(fout), lout.cap, ptr(lout.n_dev), K, cin, cout, args.algo, st),
+                      "btc_sparse_conv_fwd")
+                e1.record()
+                torch.cuda.synchronize()
+                if r > 0:
+                    ms_l += e0.elapsed_time(e1)
+            ms_l /= reps
+            tot_ms += ms_l
+            per_layer.append({"cin": cin, "cout": cout, "n_out": sp["n_out"], "pairs": sp["pairs"], "us": round(ms_l * 1e3, 2),
+                              "gflops": round(sp["flops"] / ms_l / 1e6, 1)})
+        alg_bytes = sum(sp["bytes"] for sp in specs)
+        alg_flops = sum(sp["flops"] for sp in specs)
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes / (tot_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "conv_fwd gather-GEMM (all %d conv launches of a step)" % len(specs),
+                "achieved": round(achieved, 2), "peak": peak_gbs, "unit": "GB/s", "frac": round(achieved / peak_gbs, 5),
+                "peak_source": "measured" if peaks else "fallback", "traffic": None,
+                "alg_bytes_per_step": alg_bytes, "alg_flops_per_step": alg_flops,
+                "conv_ms_per_step": round(tot_ms, 4), "achieved_tflops": round(alg_flops / (tot_ms * 1e-3) / 1e12, 3),
+                "launches": len(specs), "per_layer": per_layer}
+
+    scenes_total = world * B * args.steps
+    res = {
+        "metric": "scenes/sec (KITTI-range 20k-pt clouds, voxel 0.05 m)", "value": round(scenes_total / (ms_dev * 1e-3), 2),
+        "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: VoxelBackBone8x forward (voxelize+MeanVFE+rulebooks+12 sparse convs) on "
+                               "lidar_like 20k-pt KITTI-range clouds, voxel [0.05,0.05,0.1], C_in=4",
+                   "scenes_per_step_per_gpu": B, "points_per_scene": N_POINTS, "parallelism": "dp%d" % world,
+                   "l2": "256 MB buffer written between timed steps (untimed); %d distinct scenes cycled" % N_SCENE_POOL,
+                   "cuda_graph": not args.no_graph, "conv_algo": args.algo,
+                   "level_sites": counts},
+        "e2e": {"value": round(scenes_total / (ms_e2e * 1e-3), 2), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": plan.launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    if roof:
+        res["roofline"] = roof
+    return res, scenes
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference path, on the host cores (allowed use of oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_factory():
+    from btcdet_b200 import synthetic as S
+    from oracle import oracle as O
+    from tests import oracle_net
+    O.build()
+    model = build_model()
+    gen = O.VoxelGeneratorV2(S.DET_VOXEL_SIZE, S.KITTI_RANGE, S.DET_MAX_POINTS, S.DET_MAX_VOXELS["train"])
+
+    def forward(scene):
+        r = gen.generate(scene)
+        coords = np.pad(r["coordinates"], ((0, 0), (1, 0))).astype(np.int32)
+        mean = (r["voxels"].sum(1) / np.maximum(r["num_points_per_voxel"], 1)[:, None]).astype(np.float32)
+        x = oracle_net.to_oracle_tensor(mean, coords, model.sparse_shape, 1)
+        for name in ("conv_input", "conv1", "conv2", "conv3", "conv4", "conv_out"):
+            x = oracle_net.run(getattr(model, name), x)
+        return x
+    return forward
+
+
+def tune_cpu_threads(fwd, scene):
+    """Per-offset matmuls are small: more threads is not always faster.  Time one scene at a few
+    thread counts and keep the best (this is "all the host threads it can use" for this workload)."""
+    cores = os.cpu_count() or 1
+    best = (None, float("inf"))
+    for t in sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)}):
+        torch.set_num_threads(t)
+        t0 = time.perf_counter()
+        fwd(scene)
+        dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (t, dt)
+        if dt > 4 * best[1]:
+            break  # oversubscribed: larger counts only get worse
+    torch.set_num_threads(best[0])
+    return best[0]
+
+
+def run_cpu(scenes, n_scenes, warm=1):
+    fwd = cpu_forward_factory()
+    for i in range(warm):
+        fwd(scenes[i % len(scenes)])
+    cores = tune_cpu_threads(fwd, scenes[0])
+    t0 = time.perf_counter()
+    for i in range(n_scenes):
+        fwd(scenes[(warm + i) % len(scenes)])
+    dt = time.perf_counter() - t0
+    return n_scenes / dt, cores, dt
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+
+    if args.impl == "reference":
+        # rank 0 alone runs the CPU port; other ranks exit 0 without work
+        if rank != 0:
+            return
+        scenes = make_scenes(0, 4)
+        per_step = max(1, args.cpu_scenes or 1)
+        fwd = cpu_forward_factory()
+        fwd(scenes[0])
+        cores = tune_cpu_threads(fwd, scenes[0])
+        for i in range(min(args.warmup, 2)):
+            fwd(scenes[i % len(scenes)])
+        t0 = time.perf_counter()
+        done = 0
+        for i in range(args.steps):
+            for j in range(per_step):
+                fwd(scenes[(i * per_step + j) % len(scenes)])
+                done += 1
+        dt = time.perf_counter() - t0
+        val = done / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "scenes/sec (KITTI-range 20k-pt clouds, voxel 0.05 m)", "value": round(val, 4),
+            "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: VoxelBackBone8x forward on lidar_like 20k-pt KITTI-range clouds "
+                                   "(CPU oracle port of spconv-1.2.1 Native: C rulebooks + per-offset gather/torch.mm/"
+                                   "scatter-add)", "scenes_per_step": per_step, "points_per_scene": N_POINTS},
+            "cpu_baseline": {"value": round(val, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+                             "sample": "%d scenes of 20k points, full voxelize+backbone forward each" % done},
+            "e2e": {"value": round(val, 4), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
+
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+    res, scenes = run_ours(args, rank, world)
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            n_cpu = args.cpu_scenes or 6
+            val, cores, dt = run_cpu(scenes, n_cpu)
+            res["cpu_baseline"] = {"value": round(val, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+                                   "sample": "%d scenes of 20k points (%.1f s of CPU work), full voxelize+backbone "
+                                             "forward on the oracle port" % (n_cpu, dt)}
+        print(json.dumps(res))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,3 +67,34 @@ def test_training_step_runs_and_matches_dense_autograd_direction(cuda, oracle):
     for name, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
     assert sum(float(p.grad.abs().sum()) for p in model.parameters()) > 0
+
+
+@pytest.mark.parametrize("batch,use_graph", [(1, True), (3, True), (2, False)])
+def test_planned_engine_matches_oracle(cuda, oracle, batch, use_graph):
+    """points -> GPU voxelize -> MeanVFE -> folded-BN backbone under one CUDA graph, no host sync."""
+    from btcdet_b200 import backbones, engine, synthetic as S
+    torch.manual_seed(0)
+    model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+    plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, batch, batch * 20000, S.DET_VOXEL_SIZE,
+                               S.KITTI_RANGE, max_points=5, max_voxels=16000, algo=1, use_graph=use_graph).capture()
+    for rep in range(2):  # replay the same graph on different inputs
+        scenes, mean, coords = _inputs(oracle, batch, seed=200 + 10 * rep)
+        ref = _oracle_forward(model, mean, coords, batch)["out"]
+        pts, offs = S.batch_points(scenes)
+        feat, out_coords, n_dev = plan.forward(torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda())
+        counts = plan.read_counts()
+        n = int(n_dev.item())
+        assert counts[0] == coords.shape[0] and counts[-1] == n == ref.indices.shape[0]
+        np.testing.assert_array_equal(out_coords[:n].cpu().numpy(), ref.indices)
+        assert rel_err(feat[:n].cpu().numpy(), ref.features) < REL_TOL
+
+
+def test_planned_engine_reports_capacity_overflow(cuda):
+    from btcdet_b200 import _lib, backbones, engine, synthetic as S
+    model = backbones.VoxelBackBone8x(4).eval()
+    plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, 1, 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                               max_voxels=16000, level_growth=0.05, algo=1, use_graph=False).capture()
+    pts, offs = S.batch_points([S.uniform(20000, seed=1)])   # uniform clouds dilate under strided convs
+    plan.forward(torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda())
+    with pytest.raises(_lib.BtcError):
+        plan.read_counts()
