@@ -116,7 +116,7 @@ def layer_bytes_flops(plan, counts):
     for s in plan.steps:
         if s.kind != "conv":
             continue
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout = s.args
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = s.args
         n_out = lvl_n[id(lout)]
         pairs = int((nbr[:n_out] >= 0).sum().item())
         out.append({"n_in": n_in, "n_out": n_out, "pairs": pairs, "K": K, "cin": cin, "cout": cout,
@@ -208,30 +208,25 @@ def run_ours(args, rank, world):
     if rank == 0:
         specs = layer_bytes_flops(plan, counts)
         conv_steps = [s for s in plan.steps if s.kind == "conv"]
-        from btcdet_b200._lib import check
         import ctypes
-        lib = plan.lib
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ptr = engine._ptr
         tot_ms, reps = 0.0, 5
         per_layer = []
         for s, sp in zip(conv_steps, specs):
-            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout = s.args
+            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = s.args
             ms_l = 0.0
             for r in range(reps + 1):
                 flush.fill_(float(r))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                check(lib.btc_sparse_conv_fwd(ptr(fin), ptr(nbr), ptr(w), ptr(bias), ptr(scale), ptr(shift), int(relu),
-                                              ptr(fout), lout.cap, ptr(lout.n_dev), K, cin, cout, args.algo, st),
-                      "btc_sparse_conv_fwd")
+                plan.launch_conv(s.args, st)
                 e1.record()
                 torch.cuda.synchronize()
                 if r > 0:
                     ms_l += e0.elapsed_time(e1)
             ms_l /= reps
             tot_ms += ms_l
-            per_layer.append({"cin": cin, "cout": cout, "n_out": sp["n_out"], "pairs": sp["pairs"], "us": round(ms_l * 1e3, 2),
+            per_layer.append({"tile": "tcgen05" if packed is not None else "ffma", "cin": cin, "cout": cout, "n_out": sp["n_out"], "pairs": sp["pairs"], "us": round(ms_l * 1e3, 2),
                               "gflops": round(sp["flops"] / ms_l / 1e6, 1)})
         alg_bytes = sum(sp["bytes"] for sp in specs)
         alg_flops = sum(sp["flops"] for sp in specs)

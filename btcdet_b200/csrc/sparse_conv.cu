@@ -346,13 +346,6 @@ __global__ void col_sum_kernel(const float* __restrict__ x, int n_cap, const int
 
 using namespace btc;
 
-namespace btc {
-// implemented in sparse_conv_tc.cu; returns BTC_E_UNSUPPORTED when the shape does not qualify
-int conv_fwd_tc(const float* feat_in, const int* table, int mirror, const float* weight, const float* bias,
-                const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev, int K,
-                int c_in, int c_out, cudaStream_t st);
-}  // namespace btc
-
 extern "C" {
 
 int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out, const float* weight, const float* bias,
@@ -363,11 +356,8 @@ int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out, const float* w
     if ((scale == nullptr) != (shift == nullptr)) return badarg("btc_sparse_conv_fwd: scale/shift must come together");
     if (n_out_cap > 0 && !feat_in) return badarg("btc_sparse_conv_fwd: null feat_in");
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo == 2) return conv_fwd_tc(feat_in, nbr_out, 0, weight, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-    if (algo == 0) {
-        int rc = conv_fwd_tc(feat_in, nbr_out, 0, weight, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        if (rc != BTC_E_UNSUPPORTED) return rc;
-    }
+    if (algo != 0 && algo != 1)
+        return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_fwd: tensor-core tiles take pre-packed weights, use btc_sparse_conv_fwd_tc", cudaSuccess);
     return conv_fwd_ffma(feat_in, nbr_out, 0, weight, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in,
                          c_out, st);
 }

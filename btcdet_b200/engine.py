@@ -125,9 +125,15 @@ class BackbonePlan:
             if bn is not None:
                 scale, shift = (t.to(dev) for t in fold_bn(bn))
             out_feat = torch.empty((out_lvl.cap, conv.out_channels), dtype=torch.float32, device=dev)
-            self.params.append((w, bias, scale, shift))
+            # wide layers run on the tcgen05 tile (weights packed once into the UMMA operand image)
+            packed = None
+            if self.algo != 1 and conv.in_channels >= 32 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
+                packed = ops.tc_pack_weight(w)
+            elif self.algo == 2 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
+                packed = ops.tc_pack_weight(w)
+            self.params.append((w, bias, scale, shift, packed))
             self.steps.append(_Step("conv", (cur_feat, nbr, w, bias, scale, shift, bn is not None, out_feat, out_lvl, K,
-                                             conv.in_channels, conv.out_channels)))
+                                             conv.in_channels, conv.out_channels, packed)))
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
         self.graph = None
@@ -186,16 +192,26 @@ class BackbonePlan:
                       "btc_rulebook_conv")
                 launches += 8
             else:
-                fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout = s.args
-                check(lib.btc_sparse_conv_fwd(_ptr(fin), _ptr(nbr), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift),
-                                              int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K, cin, cout, self.algo,
-                                              st), "btc_sparse_conv_fwd")
+                fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = s.args
+                self.launch_conv(s.args, st)
                 launches += 1
         # gather the live counts of every level into one small tensor (read back lazily by the caller)
         for i, l in enumerate(self.levels):
             self.dev_counts[i:i + 1].copy_(l.n_dev)
         self.launches_per_step = launches
         return launches
+
+    def launch_conv(self, args, st):
+        """One sparse-conv layer: tcgen05 tile when the weights were packed, fp32 FFMA tile otherwise."""
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = args
+        if packed is not None:
+            check(self.lib.btc_sparse_conv_fwd_tc(_ptr(fin), _ptr(nbr), _ptr(packed), _ptr(bias), _ptr(scale),
+                                                  _ptr(shift), int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K,
+                                                  cin, cout, st), "btc_sparse_conv_fwd_tc")
+        else:
+            check(self.lib.btc_sparse_conv_fwd(_ptr(fin), _ptr(nbr), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift),
+                                               int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K, cin, cout, 1, st),
+                  "btc_sparse_conv_fwd")
 
     def capture(self):
         """Warm up once on a side stream, then capture the step into a CUDA graph."""

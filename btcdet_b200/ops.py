@@ -226,6 +226,42 @@ def sparse_conv_fwd(features, nbr_out, weight, bias=None, scale=None, shift=None
     return out
 
 
+def tc_supported(K, c_in, c_out):
+    return bool(_lib.load().btc_sparse_conv_tc_supported(int(K), int(c_in), int(c_out)))
+
+
+def tc_pack_weight(weight):
+    """Pack [K,Cin,Cout] (or [*k,Cin,Cout]) fp32 weights into the tcgen05 operand image (hi/lo tf32 split,
+    K-major, 128-byte swizzle) consumed by sparse_conv_fwd_tc."""
+    lib = _lib.load()
+    _require_cuda(weight)
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    K = weight.numel() // (c_in * c_out)
+    nbytes = int(lib.btc_sparse_conv_tc_packed_bytes(K, c_in, c_out))
+    if nbytes < 0:
+        raise _lib.BtcError("tensor-core tile does not support K=%d Cin=%d Cout=%d" % (K, c_in, c_out))
+    weight = weight.detach().to(torch.float32).contiguous()
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    check(lib.btc_sparse_conv_tc_pack(_ptr(weight), K, c_in, c_out, _ptr(packed), _stream()), "btc_sparse_conv_tc_pack")
+    return packed
+
+
+def sparse_conv_fwd_tc(features, nbr_out, packed_weight, c_in, c_out, bias=None, scale=None, shift=None, relu=False,
+                       n_out_dev=None, out=None):
+    """tcgen05 3xTF32 gather-GEMM; same contract as sparse_conv_fwd with pre-packed weights."""
+    _require_cuda(features, nbr_out, packed_weight)
+    lib = _lib.load()
+    n_out, K = nbr_out.shape
+    features, nbr_out = features.contiguous(), nbr_out.contiguous()
+    assert features.dtype == torch.float32 and features.shape[1] == c_in
+    if out is None:
+        out = torch.empty((n_out, c_out), dtype=torch.float32, device=features.device)
+    check(lib.btc_sparse_conv_fwd_tc(_ptr(features), _ptr(nbr_out), _ptr(packed_weight), _ptr(bias), _ptr(scale),
+                                     _ptr(shift), int(bool(relu)), _ptr(out), n_out, _ptr(n_out_dev), K, int(c_in),
+                                     int(c_out), _stream()), "btc_sparse_conv_fwd_tc")
+    return out
+
+
 def sparse_conv_bwd_data(d_out, table, mirror, weight, n_in):
     lib = _lib.load()
     c_in, c_out = weight.shape[-2], weight.shape[-1]

@@ -202,14 +202,28 @@ int btc_rulebook_pairs(const int* table, int n_in_cap, const int* n_in_dev, int 
  *          (eval-mode BatchNorm1d folded: y = conv*scale + shift),
  * relu     != 0: fused ReLU after the affine,
  * feat_out [n_out_cap, c_out] f32.
- * algo: 0 = auto, 1 = fp32 FFMA tiles, 2 = tcgen05 3xTF32 tensor-core tiles
- *       (returns BTC_E_UNSUPPORTED when the shape does not qualify).
+ * algo: 0 / 1 = fp32 FFMA register tiles (exact fp32 products and sums).  The tcgen05
+ *       tensor-core tile takes pre-packed weights: see btc_sparse_conv_fwd_tc below.
  */
 int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out,
                         const float* weight, const float* bias,
                         const float* scale, const float* shift, int relu,
                         float* feat_out, int n_out_cap, const int* n_out_dev,
                         int K, int c_in, int c_out, int algo, void* stream);
+
+/*
+ * Tensor-core variant (tcgen05.mma kind::tf32 with the 3xTF32 split, accumulator in TMEM):
+ * same contract as btc_sparse_conv_fwd, for c_in >= 16, c_in % 4 == 0, 16 <= c_out <= 128,
+ * c_out % 4 == 0, K <= 64.  The weights are packed once per layer into the shared-memory image
+ * of the K-major, 128-byte-swizzled hi/lo operand tiles (btc_sparse_conv_tc_pack).
+ */
+int btc_sparse_conv_tc_supported(int K, int c_in, int c_out);
+int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
+int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
+int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,
+                           const float* bias, const float* scale, const float* shift, int relu,
+                           float* feat_out, int n_out_cap, const int* n_out_dev,
+                           int K, int c_in, int c_out, void* stream);
 
 /*
  * d feat_in [n_in_cap, c_in] = sum_k d_out[nbr_in[i][k]] @ W[k]^T.

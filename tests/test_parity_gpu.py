@@ -193,6 +193,40 @@ def test_sparse_conv_forward_within_tolerance(cuda, oracle, cin, cout, kind):
     assert rel_err(out2.cpu().numpy(), np.maximum(ref * scale + shift, 0)) < REL_TOL
 
 
+@pytest.mark.parametrize("cin,cout", [(32, 32), (16, 32), (32, 64), (64, 64), (64, 128), (128, 128), (256, 128),
+                                      (48, 40), (20, 16)])
+@pytest.mark.parametrize("kind", ["subm", "conv"])
+def test_tensor_core_conv_within_tolerance(cuda, oracle, cin, cout, kind):
+    """tcgen05 3xTF32 tile vs the oracle (and vs the fp32 FFMA tile): same 1e-4 bar."""
+    from btcdet_b200 import ops
+    if not ops.tc_supported(27, cin, cout):
+        pytest.skip("shape not covered by the tensor-core tile")
+    coords = _scene_coords(oracle, 31, n=9000)
+    rng = np.random.default_rng(cin * 1000 + cout + 7)
+    shape = [41, 1600, 1408]
+    if kind == "subm":
+        outids, pairs, pair_num, _ = oracle.get_indice_pairs(coords, 1, shape, 3, subm=True)
+        rb = ops.rulebook_subm(torch.from_numpy(coords).cuda(), 1, shape, 3)
+    else:
+        outids, pairs, pair_num, _ = oracle.get_indice_pairs(coords, 1, shape, 3, 2, 1)
+        rb = ops.rulebook_conv(torch.from_numpy(coords).cuda(), 1, shape, 3, 2, 1)
+    feat = rng.standard_normal((coords.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    scale, shift = rng.uniform(0.5, 1.5, cout).astype(np.float32), rng.standard_normal(cout).astype(np.float32)
+    ref = oracle.indice_conv(feat, w, pairs, pair_num, outids.shape[0], subm=(kind == "subm"), bias=bias)
+    wt = torch.from_numpy(w).cuda()
+    packed = ops.tc_pack_weight(wt)
+    f = torch.from_numpy(feat).cuda()
+    out = ops.sparse_conv_fwd_tc(f, rb.nbr_out, packed, cin, cout, torch.from_numpy(bias).cuda())
+    assert rel_err(out.cpu().numpy(), ref) < REL_TOL
+    out2 = ops.sparse_conv_fwd_tc(f, rb.nbr_out, packed, cin, cout, torch.from_numpy(bias).cuda(),
+                                  torch.from_numpy(scale).cuda(), torch.from_numpy(shift).cuda(), relu=True)
+    assert rel_err(out2.cpu().numpy(), np.maximum(ref * scale + shift, 0)) < REL_TOL
+    ffma = ops.sparse_conv_fwd(f, rb.nbr_out, wt, torch.from_numpy(bias).cuda(), algo=1)
+    assert rel_err(out.cpu().numpy(), ffma.cpu().numpy()) < 2e-5
+
+
 def test_config1_golden(cuda, oracle):
     """BASELINE.json configs[0]: 2k uniform points -> voxelize -> one SubMConv3d(16->16,k3); compared
     with the committed golden fixture (generated by tests/golden/make_golden.py from the oracle)."""
