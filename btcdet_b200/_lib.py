@@ -24,6 +24,9 @@ SIGNATURES = {
     "btc_index_workspace_bytes": (_i64, [_i64]),
     "btc_index_build": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _p, _p, _i64, _p]),
     "btc_index_clear": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p]),
+    "btc_hash_slots": (_i64, [_i]),
+    "btc_hash_build": (_i, [_p, _i, _p, _i, _p, _p, _p, _i64, _p]),
+    "btc_rulebook_subm_hash": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "btc_rulebook_subm": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "btc_rulebook_conv": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _i, _p, _p, _p, _p, _i64, _p]),
     "btc_rulebook_pairs_workspace_bytes": (_i64, [_i, _i]),

@@ -68,6 +68,27 @@ __device__ __forceinline__ int index_lookup(const uint2* __restrict__ index, int
     return (int)(e.y + __popc(e.x & (bit - 1u)));
 }
 
+// ---- coordinate hash (unsorted site sets: submanifold lookups) ---------------------------------------
+// Open addressing, linear probing; keys are flat cell keys (int64, -1 = empty), vals the site row.
+__device__ __forceinline__ uint32_t hash_key64(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
+__device__ __forceinline__ int hash_lookup(const long long* __restrict__ keys, const int* __restrict__ vals,
+                                           uint32_t hmask, int64_t key) {
+    uint32_t h = hash_key64((unsigned long long)key) & hmask;
+    while (true) {
+        long long kk = __ldg(keys + h);
+        if (kk == key) return __ldg(vals + h);
+        if (kk == -1LL) return -1;
+        h = (h + 1) & hmask;
+    }
+}
+
 // ---- warp / block scan helpers ------------------------------------------------
 __device__ __forceinline__ int warp_inclusive_scan(int v) {
     const int lane = threadIdx.x & 31;

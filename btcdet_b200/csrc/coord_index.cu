@@ -155,6 +155,27 @@ __global__ void index_clear_kernel(const int4* __restrict__ coords, int n_cap, c
     }
 }
 
+__global__ void hash_insert_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                                   Shape3 shape, int batch, long long* __restrict__ keys, int* __restrict__ vals,
+                                   uint32_t hmask) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = __ldg(coords + i);
+        if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)shape.d ||
+            (unsigned)c.z >= (unsigned)shape.h || (unsigned)c.w >= (unsigned)shape.w)
+            continue;
+        long long key = flat_key(c.x, c.y, c.z, c.w, shape);
+        uint32_t h = hash_key64((unsigned long long)key) & hmask;
+        while (true) {
+            long long old = (long long)atomicCAS((unsigned long long*)(keys + h), (unsigned long long)-1LL,
+                                                 (unsigned long long)key);
+            if (old == -1LL || old == key) break;
+            h = (h + 1) & hmask;
+        }
+        vals[h] = i;   // rows are unique: one writer per slot
+    }
+}
+
 }  // namespace btc
 
 using namespace btc;
@@ -200,6 +221,27 @@ int btc_index_build(const int* coords, int n_cap, const int* n_dev, int batch, c
                                                                 (const uint2*)index, perm);
         BTC_CHECK_LAUNCH("index_perm");
     }
+    return BTC_OK;
+}
+
+int64_t btc_hash_slots(int n_cap) {
+    int64_t h = 1024;
+    while (h < 2 * (int64_t)n_cap) h <<= 1;
+    return h;
+}
+
+int btc_hash_build(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, int64_t* keys,
+                   int* vals, int64_t n_slots, void* stream) {
+    if (!shape || !keys || !vals) return badarg("btc_hash_build: null argument");
+    if (n_slots < 2 * (int64_t)n_cap || (n_slots & (n_slots - 1))) return badarg("btc_hash_build: n_slots must be a power of two >= 2*n_cap");
+    cudaStream_t st = (cudaStream_t)stream;
+    BTC_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 8, st), "hash memset");
+    if (n_cap <= 0) return BTC_OK;
+    if (!coords) return badarg("btc_hash_build: null coordinates");
+    Shape3 s{shape[0], shape[1], shape[2]};
+    hash_insert_kernel<<<grid_for(n_cap, 256), 256, 0, st>>>((const int4*)coords, n_cap, n_dev, s, batch,
+                                                             (long long*)keys, vals, (uint32_t)(n_slots - 1));
+    BTC_CHECK_LAUNCH("hash_insert");
     return BTC_OK;
 }
 

@@ -67,6 +67,29 @@ __global__ void subm_table_kernel(const int4* __restrict__ coords, int n_cap, co
     }
 }
 
+// Same, probing a coordinate hash instead of the rank bitmap (unsorted inputs on huge grids: the
+// KITTI det level-1 grid is 92 M cells per scene for ~14 k sites — a 2N-slot hash is ~1 MB).
+__global__ void subm_table_hash_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                                       ConvGeom g, const long long* __restrict__ keys, const int* __restrict__ vals,
+                                       uint32_t hmask, int* __restrict__ nbr_out) {
+    const int n = live_count(n_cap, n_dev);
+    const int K = g.K;
+    const int64_t work = (int64_t)n * K;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
+        int4 c = __ldg(coords + i);
+        int kz, ky, kx;
+        offset_of(k, g.k, kz, ky, kx);
+        int z = c.y + (kz - g.k[0] / 2) * g.dil[0];
+        int y = c.z + (ky - g.k[1] / 2) * g.dil[1];
+        int x = c.w + (kx - g.k[2] / 2) * g.dil[2];
+        int j = -1;
+        if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w)
+            j = (k == K / 2) ? i : hash_lookup(keys, vals, hmask, flat_key(c.x, z, y, x, g.in));
+        nbr_out[t] = j;
+    }
+}
+
 // ---- strided / transposed -----------------------------------------------------------
 __global__ void conv_mark_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
                                  unsigned* __restrict__ out_index_words) {
@@ -254,6 +277,23 @@ int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch,
     subm_table_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, g,
                                                                             (const uint2*)index, perm, nbr_out);
     BTC_CHECK_LAUNCH("subm_table");
+    return BTC_OK;
+}
+
+int btc_rulebook_subm_hash(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape,
+                           const int* ksize, const int* dilation, const int64_t* keys, const int* vals,
+                           int64_t n_slots, int* nbr_out, void* stream) {
+    if (!shape || !ksize || !keys || !vals) return badarg("btc_rulebook_subm_hash: null argument");
+    if (n_slots <= 0 || (n_slots & (n_slots - 1))) return badarg("btc_rulebook_subm_hash: n_slots must be a power of two");
+    if (n_cap > 0 && (!coords || !nbr_out)) return badarg("btc_rulebook_subm_hash: null coordinates");
+    ConvGeom g;
+    int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+    if (make_geom(g, batch, shape, shape, ksize, one, zero, dilation, 0)) return badarg("btc_rulebook_subm_hash: bad geometry");
+    if (n_cap <= 0) return BTC_OK;
+    int64_t work = (int64_t)n_cap * g.K;
+    subm_table_hash_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const int4*)coords, n_cap, n_dev, g, (const long long*)keys, vals, (uint32_t)(n_slots - 1), nbr_out);
+    BTC_CHECK_LAUNCH("subm_table_hash");
     return BTC_OK;
 }
 

@@ -41,11 +41,11 @@ conv_fwd_ffma_kernel(const float* __restrict__ feat_in, const int* __restrict__ 
     __shared__ unsigned s_kmask[8];                                // K <= 256
 
     const int n = live_count(n_cap, n_dev);
-    const int row0 = blockIdx.x * BM;
-    if (row0 >= n) return;
     const int col0 = blockIdx.y * BN;
     const int tid = threadIdx.x;
-
+    // persistent over row tiles: the grid is sized by the SM count, not by the (capacity) row count
+    for (int row0 = blockIdx.x * BM; row0 < n; row0 += gridDim.x * BM) {
+    __syncthreads();   // previous tile's readers of nbr_s / klist / smem tiles are done
     if (tid < 8) s_kmask[tid] = 0u;
     __syncthreads();
     // neighbour tile (coalesced: the BM x K block is contiguous in the table)
@@ -203,6 +203,7 @@ conv_fwd_ffma_kernel(const float* __restrict__ feat_in, const int* __restrict__ 
             }
         }
     }
+    }  // row tiles
 }
 
 template <int BM, int BN, int TM, int TN>
@@ -211,7 +212,8 @@ static int launch_fwd(const float* feat_in, const int* table, int mirror, const 
                       int K, int c_in, int c_out, cudaStream_t st) {
     constexpr int NT = (BM / TM) * (BN / TN);
     size_t smem = (size_t)(2 * CK * (BM + 4) + 2 * CK * BN) * sizeof(float) + (size_t)(BM * K + K) * sizeof(int);
-    dim3 grid((n_cap + BM - 1) / BM, (c_out + BN - 1) / BN);
+    int tiles = (n_cap + BM - 1) / BM;
+    dim3 grid(tiles < 8 * kNumSM ? tiles : 8 * kNumSM, (c_out + BN - 1) / BN);
     const bool va = (c_in % 4 == 0) && (((uintptr_t)feat_in & 15) == 0);
     const bool vw = (c_out % 4 == 0) && (((uintptr_t)weight & 15) == 0) && (((uintptr_t)feat_out & 15) == 0);
 #define BTC_LAUNCH(VA, VW)                                                                                         \

@@ -24,7 +24,6 @@ namespace btc {
 
 constexpr int TC_BM = 128;      // output rows per CTA == UMMA M
 constexpr int TC_KC = 32;       // input channels per stage (32 tf32 = 128 B = one swizzle row)
-constexpr int TC_THREADS = 160; // 4 producer/epilogue warps + 1 MMA warp
 
 // ---- raw PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,8 +135,19 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
+// Persistent, warp-specialised: one CTA per SM loops over 128-row output tiles.
+//   warps 0-7  : two producer groups (4 warps each); group g fills the stages with (global stage index % 2 == g),
+//                prefetching the next stage's gather into registers before it stores the current one;
+//   warp  8    : MMA issuer (one elected lane);
+//   warps 9-12 : epilogue (TMEM lane quarter = warp % 4), overlapping the next tile's main loop through a
+//                double-buffered TMEM accumulator (2 x N columns).
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_MMA_WARP = 8;
+constexpr int TC_EPI_WARP0 = 9;
+constexpr int TC_PERSIST_THREADS = 13 * 32;
+
 template <int N, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_PERSIST_THREADS, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table, int mirror,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
@@ -146,171 +156,178 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     constexpr int A_BYTES = TC_BM * 128;          // one A tile (hi or lo)
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo)
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
+    constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;   // double-buffered accumulator
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
     extern __shared__ unsigned char smem_dyn[];
-    // 1024-byte alignment for the swizzled tiles
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    unsigned char* stages = smem;
-    int* nbr_s = (int*)(smem + STAGES * STAGE_BYTES);   // [TC_BM][K]
-    int* klist = nbr_s + TC_BM * K;                      // [K]
+    unsigned char* stages = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
 
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
-    __shared__ uint32_t s_tmem, s_nk;
-    __shared__ unsigned s_kmask[8];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t s_tmem;
 
     const int n = live_count(n_cap, n_dev);
-    const int row0 = blockIdx.x * TC_BM;
-    if (row0 >= n) return;                         // whole CTA exits together (before any barrier / alloc)
+    if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int num_tiles = (n + TC_BM - 1) / TC_BM;
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nchunk = (c_in + TC_KC - 1) / TC_KC;
+    const int T = K * nchunk;                      // stages per tile
+    const int total_stages = my_tiles * T;
 
-    if (tid < 8) s_kmask[tid] = 0u;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 128);          // 128 producer threads arrive; tx bytes from the bulk copy
+            mbar_init(&full_bar[s], 128);          // the 128 threads of one producer group (+ bulk-copy tx bytes)
             mbar_init(&empty_bar[s], 1);           // one tcgen05.commit
         }
-        mbar_init(&accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);           // one tcgen05.commit
+            mbar_init(&tmem_empty[b], 128);        // the 128 epilogue threads
+        }
         fence_mbar_init();
     }
-    __syncthreads();
-    if (warp == 4) tmem_alloc(&s_tmem, TMEM_COLS);
-    for (int e = tid; e < TC_BM * K; e += TC_THREADS) {
-        int r = e / K, k = e - r * K;
-        int v = -1;
-        if (row0 + r < n) v = __ldg(table + (int64_t)(row0 + r) * K + (mirror ? K - 1 - k : k));
-        nbr_s[e] = v;
-        if (v >= 0) atomicOr(&s_kmask[k >> 5], 1u << (k & 31));
-    }
+    if (warp == TC_MMA_WARP) tmem_alloc(&s_tmem, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
-        int nk = 0;
-        for (int k = 0; k < K; ++k)
-            if (s_kmask[k >> 5] & (1u << (k & 31))) klist[nk++] = k;
-        s_nk = nk;
-    }
-    __syncthreads();
     const uint32_t tmem_base = s_tmem;
-    const int nchunk = (c_in + TC_KC - 1) / TC_KC;
-    const int T = (int)s_nk * nchunk;
 
-    if (warp < 4) {
-        // ================= producers: gather + hi/lo split + swizzled store =================
-        const int sub = lane >> 3;       // row within the 4-row group handled per instruction
+    if (warp < TC_PRODUCER_WARPS) {
+        // ================= producers =================
+        const int group = warp >> 2, wg = warp & 3;
+        const int sub = lane >> 3;       // row within the 4-row group handled per load instruction
         const int q = lane & 7;          // 16-byte chunk within the 128-byte row
-        for (int it = 0; it < T; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);       // fresh barrier: parity-1 wait passes immediately
-            const int k = klist[it / nchunk];
-            const int cc = it % nchunk;
-            unsigned char* st = stages + s * STAGE_BYTES;
-            if (tid == 0) {
-                mbar_expect_tx(&full_bar[s], 2 * B_BYTES);
-                bulk_copy_g2s(st + 2 * A_BYTES, (const char*)packed_w + ((int64_t)k * nchunk + cc) * (2 * B_BYTES),
-                              2 * B_BYTES, &full_bar[s]);
-            }
+        float4 cur[8], nxt[8];
+        auto gather = [&](int gi, float4 (&v)[8]) {
+            const int tl = gi / T, j = gi - tl * T;
+            const int k = j / nchunk, cc = j - k * nchunk;
+            const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM;
             const int c = cc * TC_KC + q * 4;
-            float4 v[8];
+            const int kk = mirror ? K - 1 - k : k;
+            int src[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const int r = warp * 32 + g * 4 + sub;
-                const int src = nbr_s[r * K + k];
-                v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src >= 0 && c < c_in) v[g] = __ldg(reinterpret_cast<const float4*>(feat_in + (int64_t)src * c_in + c));
+                const int r = row0 + wg * 32 + g * 4 + sub;
+                src[g] = r < n ? __ldg(table + (int64_t)r * K + kk) : -1;
             }
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const int r = warp * 32 + g * 4 + sub;
+                v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src[g] >= 0 && c < c_in) v[g] = __ldg(reinterpret_cast<const float4*>(feat_in + (int64_t)src[g] * c_in + c));
+            }
+        };
+        int gi = group;
+        if (gi < total_stages) gather(gi, cur);
+        for (; gi < total_stages; gi += 2) {
+            if (gi + 2 < total_stages) gather(gi + 2, nxt);   // next stage's loads fly while this one is stored
+            const int s = gi % STAGES;
+            const uint32_t ph = (gi / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            unsigned char* st = stages + s * STAGE_BYTES;
+            if ((tid & 127) == 0) {
+                const int j = gi % T;
+                mbar_expect_tx(&full_bar[s], 2 * B_BYTES);
+                bulk_copy_g2s(st + 2 * A_BYTES, (const char*)packed_w + (int64_t)j * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int r = wg * 32 + g * 4 + sub;
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[g].x) & 0xFFFFE000u);
-                hi.y = __uint_as_float(__float_as_uint(v[g].y) & 0xFFFFE000u);
-                hi.z = __uint_as_float(__float_as_uint(v[g].z) & 0xFFFFE000u);
-                hi.w = __uint_as_float(__float_as_uint(v[g].w) & 0xFFFFE000u);
-                lo.x = v[g].x - hi.x;
-                lo.y = v[g].y - hi.y;
-                lo.z = v[g].z - hi.z;
-                lo.w = v[g].w - hi.w;
+                hi.x = __uint_as_float(__float_as_uint(cur[g].x) & 0xFFFFE000u);
+                hi.y = __uint_as_float(__float_as_uint(cur[g].y) & 0xFFFFE000u);
+                hi.z = __uint_as_float(__float_as_uint(cur[g].z) & 0xFFFFE000u);
+                hi.w = __uint_as_float(__float_as_uint(cur[g].w) & 0xFFFFE000u);
+                lo.x = cur[g].x - hi.x;
+                lo.y = cur[g].y - hi.y;
+                lo.z = cur[g].z - hi.z;
+                lo.w = cur[g].w - hi.w;
                 const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((q ^ (r & 7)) << 4);
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
             }
-            fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core
+            fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&full_bar[s]);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) cur[g] = nxt[g];
         }
-        // ================= epilogue: TMEM -> registers -> global =================
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const int row = row0 + warp * 32 + lane;
-        float* dst = feat_out + (int64_t)row * c_out;
-#pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 16) {
-            uint32_t acc[16];
-            if (T > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0u;
-            }
-            if (row < n) {
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    float o[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int col = c0 + j4 * 4 + jj;
-                        float x = __uint_as_float(acc[j4 * 4 + jj]);
-                        if (col < c_out) {
-                            if (bias) x += __ldg(bias + col);
-                            if (scale) x = x * __ldg(scale + col) + __ldg(shift + col);
-                            if (relu) x = fmaxf(x, 0.f);
-                        }
-                        o[jj] = x;
-                    }
-                    const int col = c0 + j4 * 4;
-                    if (col + 3 < c_out) {
-                        *reinterpret_cast<float4*>(dst + col) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            if (col + jj < c_out) dst[col + jj] = o[jj];
-                    }
-                }
-            }
-        }
-    } else {
-        // ================= MMA issuer (warp 4, one elected lane) =================
+    } else if (warp == TC_MMA_WARP) {
+        // ================= MMA issuer =================
         if (lane == 0) {
-            for (int it = 0; it < T; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            int gi = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int buf = tl & 1;
+                mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(stages + s * STAGE_BYTES);
-                const uint32_t a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                const uint32_t b_lo = b_hi + B_BYTES;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                for (int j = 0; j < T; ++j, ++gi) {
+                    const int s = gi % STAGES;
+                    const uint32_t ph = (gi / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(stages + s * STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                    const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
-                    const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32), da_lo = make_desc_sw128(a_lo + kk * 32);
-                    const uint64_t db_hi = make_desc_sw128(b_hi + kk * 32), db_lo = make_desc_sw128(b_lo + kk * 32);
-                    umma_tf32(tmem_base, da_lo, db_hi, IDESC, (it | kk) != 0);   // small terms first
-                    umma_tf32(tmem_base, da_hi, db_lo, IDESC, 1u);
-                    umma_tf32(tmem_base, da_hi, db_hi, IDESC, 1u);
+                    for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
+                        const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32), da_lo = make_desc_sw128(a_lo + kk * 32);
+                        const uint64_t db_hi = make_desc_sw128(b_hi + kk * 32), db_lo = make_desc_sw128(b_lo + kk * 32);
+                        umma_tf32(d_tmem, da_lo, db_hi, IDESC, (j | kk) != 0);   // small terms first
+                        umma_tf32(d_tmem, da_hi, db_lo, IDESC, 1u);
+                        umma_tf32(d_tmem, da_hi, db_hi, IDESC, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);      // frees the stage once the MMAs above retire
                 }
-                umma_commit(&empty_bar[s]);          // frees the stage once the MMAs above retire
+                umma_commit(&tmem_full[buf]);        // accumulator complete -> epilogue
             }
-            umma_commit(&accum_bar);                 // accumulator complete -> epilogue
         }
         __syncwarp();
+    } else {
+        // ================= epilogue =================
+        const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int buf = tl & 1;
+            mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+            tc_fence_after();
+            const int row = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM + quarter * 32 + lane;
+            float* dst = feat_out + (int64_t)row * c_out;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0), acc);
+                if (row < n && c0 < c_out) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float o[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int col = c0 + j4 * 4 + jj;
+                            float x = __uint_as_float(acc[j4 * 4 + jj]);
+                            if (col < c_out) {
+                                if (bias) x += __ldg(bias + col);
+                                if (scale) x = x * __ldg(scale + col) + __ldg(shift + col);
+                                if (relu) x = fmaxf(x, 0.f);
+                            }
+                            o[jj] = x;
+                        }
+                        const int col = c0 + j4 * 4;
+                        if (col + 3 < c_out) {
+                            *reinterpret_cast<float4*>(dst + col) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (col + jj < c_out) dst[col + jj] = o[jj];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);           // this accumulator buffer may be overwritten
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 template <int N, int STAGES>
@@ -318,16 +335,17 @@ static int launch_tc(const float* feat_in, const int* table, int mirror, const f
                      const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
                      int K, int c_in, int c_out, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * TC_BM * 128 + 2 * N * 128;
-    size_t smem = (size_t)STAGES * STAGE_BYTES + (size_t)(TC_BM * K + K) * sizeof(int) + 1024;
+    size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     auto kern = conv_fwd_tc_kernel<N, STAGES>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
         attr_set = smem;
     }
-    dim3 grid((n_cap + TC_BM - 1) / TC_BM);
-    kern<<<grid, TC_THREADS, smem, st>>>(feat_in, table, mirror, packed_w, bias, scale, shift, relu, feat_out, n_cap,
-                                         n_dev, K, c_in, c_out);
+    int tiles = (n_cap + TC_BM - 1) / TC_BM;
+    dim3 grid(tiles < kNumSM ? tiles : kNumSM);    // persistent: one CTA per SM
+    kern<<<grid, TC_PERSIST_THREADS, smem, st>>>(feat_in, table, mirror, packed_w, bias, scale, shift, relu, feat_out,
+                                                 n_cap, n_dev, K, c_in, c_out);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
@@ -380,8 +398,8 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
     cudaStream_t st = (cudaStream_t)stream;
     const float* pw = (const float*)packed_weight;
     switch (tc_padded_n(c_out)) {
-        case 32: return launch_tc<32, 3>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 64: return launch_tc<64, 3>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 32: return launch_tc<32, 4>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 64: return launch_tc<64, 4>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
         case 128: return launch_tc<128, 3>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
     }
     return BTC_E_UNSUPPORTED;

@@ -28,15 +28,6 @@ struct VoxGeom {
     int grid[3];  // x, y, z
 };
 
-__device__ __forceinline__ uint32_t hash64(unsigned long long k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdULL;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ULL;
-    k ^= k >> 33;
-    return (uint32_t)k;
-}
-
 __device__ __forceinline__ int scene_of(int i, const int* __restrict__ offs, int n_scenes) {
     int b = 0;
     while (b + 1 < n_scenes && i >= __ldg(offs + b + 1)) ++b;
@@ -71,7 +62,7 @@ __global__ void vox_hash_insert_kernel(const float* __restrict__ points, int n, 
         if (i < n_total && quantize(xyz, g, cx, cy, cz)) {
             int b = scene_of(i, scene_offsets, n_scenes);
             long long key = (((long long)b * g.grid[2] + cz) * g.grid[1] + cy) * (long long)g.grid[0] + cx;
-            unsigned h = hash64((unsigned long long)key) & hmask;
+            unsigned h = hash_key64((unsigned long long)key) & hmask;
             while (true) {
                 long long old = (long long)atomicCAS((unsigned long long*)(keys + h), (unsigned long long)kEmptyKey,
                                                      (unsigned long long)key);

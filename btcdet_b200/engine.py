@@ -31,13 +31,15 @@ class _Level:
     cap: int
     coords: torch.Tensor     # [cap, 4] i32
     n_dev: torch.Tensor      # [1] i32 view
-    index: Optional[torch.Tensor] = None   # rank bitmap (int64 entries)
+    index: Optional[torch.Tensor] = None   # rank bitmap (int64 entries) — sorted levels
     perm: Optional[torch.Tensor] = None
+    hash_keys: Optional[torch.Tensor] = None   # coordinate hash — the unsorted voxeliser level
+    hash_vals: Optional[torch.Tensor] = None
 
 
 @dataclass
 class _Step:
-    kind: str            # "index_build" | "subm_rb" | "conv_rb" | "conv"
+    kind: str            # "hash_build" | "subm_rb" | "conv_rb" | "conv"
     args: tuple
 
 
@@ -96,7 +98,7 @@ class BackbonePlan:
             rb = self.rulebooks.get(key) if key is not None else None
             if rb is None:
                 if conv.subm:
-                    if cur_lvl.index is None:
+                    if cur_lvl.index is None and cur_lvl.hash_keys is None:
                         self._add_index(cur_lvl)
                     nbr = torch.empty((cur_lvl.cap, K), dtype=torch.int32, device=dev)
                     self.steps.append(_Step("subm_rb", (cur_lvl, conv.kernel_size, conv.dilation, nbr)))
@@ -143,9 +145,11 @@ class BackbonePlan:
 
     # ------------------------------------------------------------------------------------
     def _add_index(self, lvl: _Level):
-        lvl.index = torch.zeros(ops.index_entries(self.batch, lvl.shape), dtype=torch.int64, device=self.device)
-        lvl.perm = torch.empty(lvl.cap, dtype=torch.int32, device=self.device)
-        self.steps.append(_Step("index_build", (lvl,)))
+        """Unsorted level (voxeliser order): coordinate hash instead of a 92 M-cell bitmap."""
+        n_slots = int(self.lib.btc_hash_slots(lvl.cap))
+        lvl.hash_keys = torch.empty(n_slots, dtype=torch.int64, device=self.device)
+        lvl.hash_vals = torch.empty(n_slots, dtype=torch.int32, device=self.device)
+        self.steps.append(_Step("hash_build", (lvl,)))
 
     def _workspace(self, nbytes):
         ws = self._ws.get("ws")
@@ -167,19 +171,22 @@ class BackbonePlan:
                                self.vox_ws.numel(), st), "btc_voxelize")
         launches += 9
         for s in self.steps:
-            if s.kind == "index_build":
+            if s.kind == "hash_build":
                 (lvl,) = s.args
-                lvl.index.zero_()
-                ws = self._workspace(lib.btc_index_workspace_bytes(lvl.index.numel()))
-                check(lib.btc_index_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                          _ptr(lvl.index), lvl.index.numel(), _ptr(lvl.perm), None, _ptr(ws),
-                                          ws.numel(), st), "btc_index_build")
-                launches += 6
+                check(lib.btc_hash_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                         _ptr(lvl.hash_keys), _ptr(lvl.hash_vals), lvl.hash_keys.numel(), st),
+                      "btc_hash_build")
+                launches += 1
             elif s.kind == "subm_rb":
                 lvl, ksize, dil, nbr = s.args
-                check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape), int3(ksize),
-                                            int3(dil), _ptr(lvl.index), lvl.index.numel(), _ptr(lvl.perm), _ptr(nbr),
-                                            st), "btc_rulebook_subm")
+                if lvl.hash_keys is not None:
+                    check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                                     int3(ksize), int3(dil), _ptr(lvl.hash_keys), _ptr(lvl.hash_vals),
+                                                     lvl.hash_keys.numel(), _ptr(nbr), st), "btc_rulebook_subm_hash")
+                else:
+                    check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                                int3(ksize), int3(dil), _ptr(lvl.index), lvl.index.numel(),
+                                                _ptr(lvl.perm), _ptr(nbr), st), "btc_rulebook_subm")
                 launches += 1
             elif s.kind == "conv_rb":
                 lin, lout, ksize, stride, pad, dil, nbr = s.args

@@ -51,11 +51,18 @@ def deconv_output_shape(in_shape, ksize, stride, padding, dilation, output_paddi
 # ------------------------------------------------------------------------------------------
 @dataclass
 class CoordIndex:
-    """Rank bitmap over batch x spatial_shape (+ rank->row permutation when rows are unsorted)."""
-    entries: torch.Tensor  # int64 [n_entries]  ({bits, rank} packed)
-    perm: Optional[torch.Tensor]  # int32 [N] or None when rows are in ascending key order
+    """Coordinate -> row lookup of one site set.
+
+    Sorted site sets (outputs of strided / transposed convs) carry the rank bitmap that produced
+    them (`entries`, rows == ranks).  Unsorted site sets (voxeliser order, user tensors) carry a
+    coordinate hash (`hash_keys`/`hash_vals`) — far cheaper than a bitmap on a 92 M-cell grid.
+    """
+    entries: Optional[torch.Tensor]  # int64 [n_entries]  ({bits, rank} packed) or None
+    perm: Optional[torch.Tensor]  # int32 [N] rank->row, only for bitmaps over unsorted rows
     batch: int
     shape: Sequence[int]
+    hash_keys: Optional[torch.Tensor] = None  # int64 [n_slots]
+    hash_vals: Optional[torch.Tensor] = None  # int32 [n_slots]
 
 
 def index_entries(batch, shape):
@@ -75,6 +82,20 @@ def build_index(coords: torch.Tensor, batch: int, shape, need_perm=True, n_dev=N
     check(lib.btc_index_build(_ptr(coords), n, _ptr(n_dev), int(batch), int3(shape), _ptr(entries), n_entries,
                               _ptr(perm), None, _ptr(ws), ws_bytes, _stream()), "btc_index_build")
     return CoordIndex(entries, perm, int(batch), list(shape))
+
+
+def build_hash(coords: torch.Tensor, batch: int, shape, n_dev=None) -> CoordIndex:
+    """Coordinate hash of an (unsorted) site set."""
+    _require_cuda(coords)
+    lib = _lib.load()
+    assert coords.dtype == torch.int32 and coords.dim() == 2 and coords.shape[1] == 4 and coords.is_contiguous()
+    n = coords.shape[0]
+    n_slots = int(lib.btc_hash_slots(n))
+    keys = torch.empty(n_slots, dtype=torch.int64, device=coords.device)
+    vals = torch.empty(n_slots, dtype=torch.int32, device=coords.device)
+    check(lib.btc_hash_build(_ptr(coords), n, _ptr(n_dev), int(batch), int3(shape), _ptr(keys), _ptr(vals), n_slots,
+                             _stream()), "btc_hash_build")
+    return CoordIndex(None, None, int(batch), list(shape), keys, vals)
 
 
 # ------------------------------------------------------------------------------------------
@@ -134,11 +155,16 @@ def rulebook_subm(coords: torch.Tensor, batch: int, shape, ksize, dilation=1,
     n = coords.shape[0]
     K = ksize[0] * ksize[1] * ksize[2]
     if index is None:
-        index = build_index(coords, batch, shape, need_perm=True)
+        index = build_hash(coords, batch, shape)
     nbr = torch.empty((n, K), dtype=torch.int32, device=coords.device)
-    check(lib.btc_rulebook_subm(_ptr(coords), n, None, int(batch), int3(shape), int3(ksize), int3(dilation),
-                                _ptr(index.entries), index.entries.numel(), _ptr(index.perm), _ptr(nbr), _stream()),
-          "btc_rulebook_subm")
+    if index.hash_keys is not None:
+        check(lib.btc_rulebook_subm_hash(_ptr(coords), n, None, int(batch), int3(shape), int3(ksize), int3(dilation),
+                                         _ptr(index.hash_keys), _ptr(index.hash_vals), index.hash_keys.numel(),
+                                         _ptr(nbr), _stream()), "btc_rulebook_subm_hash")
+    else:
+        check(lib.btc_rulebook_subm(_ptr(coords), n, None, int(batch), int3(shape), int3(ksize), int3(dilation),
+                                    _ptr(index.entries), index.entries.numel(), _ptr(index.perm), _ptr(nbr), _stream()),
+              "btc_rulebook_subm")
     return Rulebook(nbr, None, coords, n, n, K, True, list(shape), list(shape), ksize, [1, 1, 1],
                     [k // 2 for k in ksize], dilation, False, index)
 

@@ -128,6 +128,16 @@ int btc_index_clear(const int* coords, int n_cap, const int* n_dev,
                     int batch, const int* shape, uint64_t* index, int64_t n_entries,
                     void* stream);
 
+/*
+ * Coordinate hash: the lookup structure for UNSORTED site sets on huge grids (the voxeliser's
+ * first-come rows on the 92 M-cell KITTI det grid), where a dense bitmap would cost more
+ * traffic than the whole rulebook.  Open addressing over flat (b,z,y,x) keys; `keys` int64
+ * [n_slots] (zeroed to -1 inside), `vals` int32 [n_slots]; n_slots = btc_hash_slots(n_cap).
+ */
+int64_t btc_hash_slots(int n_cap);
+int btc_hash_build(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape,
+                   int64_t* keys, int* vals, int64_t n_slots, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Rulebooks ("indice pairs")                                                  */
 /* Replace spconv.ops.get_indice_pairs (spconv 1.2.1 src/spconv/indice.cu:    */
@@ -147,6 +157,12 @@ int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev,
                       int batch, const int* shape, const int* ksize, const int* dilation,
                       const uint64_t* index, int64_t n_entries, const int* perm,
                       int* nbr_out, void* stream);
+
+/* Same table, probing a coordinate hash built with btc_hash_build over `coords`. */
+int btc_rulebook_subm_hash(const int* coords, int n_cap, const int* n_dev,
+                           int batch, const int* shape, const int* ksize, const int* dilation,
+                           const int64_t* keys, const int* vals, int64_t n_slots,
+                           int* nbr_out, void* stream);
 
 /*
  * Regular (strided) or transposed sparse convolution / pooling rulebook.

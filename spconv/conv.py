@@ -128,7 +128,7 @@ class SparseConvolution(SparseModule):
                 d3 = _pad3(self.dilation, nd, 1)
                 if self.subm:
                     if input._index is None:
-                        input._index = _ops.build_index(coords4, batch_size, shape3, need_perm=True)
+                        input._index = _ops.build_hash(coords4, batch_size, shape3)
                     rulebook = _ops.rulebook_subm(coords4, batch_size, shape3, k3, d3, index=input._index)
                     out_indices, out_spatial_shape = indices, spatial_shape
                     out_index = input._index

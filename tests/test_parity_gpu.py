@@ -122,8 +122,10 @@ def test_rulebooks_det_pyramid_bit_exact(cuda, oracle, batch, uniform):
     levels = [(3, 2, 1), (3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0)]
     for ksize, stride, pad in levels:
         c = torch.from_numpy(coords).cuda()
-        rb = ops.rulebook_subm(c, batch, shape, 3)
+        rb = ops.rulebook_subm(c, batch, shape, 3)   # coordinate-hash lookup (unsorted rows)
         _check_rulebook(oracle, rb, coords, batch, shape, 3, 1, 1, True, False)
+        rb_bitmap = ops.rulebook_subm(c, batch, shape, 3, index=ops.build_index(c, batch, shape, need_perm=True))
+        assert torch.equal(rb_bitmap.nbr_out, rb.nbr_out)   # rank-bitmap + permutation lookup agrees
         rb = ops.rulebook_conv(c, batch, shape, ksize, stride, pad)
         coords = _check_rulebook(oracle, rb, coords, batch, shape, ksize, stride, pad, False, False)
         # the output index of a strided conv doubles as the (sorted) index of the next subm layer
