@@ -136,34 +136,86 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 // Persistent, warp-specialised: one CTA per SM loops over 128-row output tiles.
-//   warps 0-7  : two producer groups (4 warps each); group g fills the stages with (global stage index % 2 == g),
-//                prefetching the next stage's gather into registers before it stores the current one;
+//   warps 0-7  : two producer groups (4 warps each, thread == output row); group g feeds the stages with
+//                (global stage index % 2 == g): gather the neighbour row chunk with 16-byte loads (next stage
+//                prefetched in registers), split hi/lo and write the A operand STRAIGHT INTO TENSOR MEMORY with
+//                tcgen05.st — the MMA then reads A from TMEM (".ts" form), so shared memory only carries the
+//                weight tiles.  (An SS-form 3xTF32 step reads 18 KB of smem per 8-deep k-step and is smem-
+//                bandwidth bound at ~70 cycles per MMA; with A in TMEM the same step is compute bound.)
 //   warp  8    : MMA issuer (one elected lane);
 //   warps 9-12 : epilogue (TMEM lane quarter = warp % 4), overlapping the next tile's main loop through a
-//                double-buffered TMEM accumulator (2 x N columns).
+//                double-buffered TMEM accumulator;
+//   warp  13   : index loader — TMA-stages each tile's [128 x K] block of the neighbour table into shared
+//                memory with one cp.async.bulk, one tile ahead.
+// TMEM map (512 columns): [0, 2N) two accumulators | [2N + 64*s, +32) A_hi of stage s | [+32, +64) A_lo.
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_MMA_WARP = 8;
 constexpr int TC_EPI_WARP0 = 9;
-constexpr int TC_PERSIST_THREADS = 13 * 32;
+constexpr int TC_IDX_WARP = 13;
+constexpr int TC_PERSIST_THREADS = 14 * 32;
+constexpr int TC_STAGES = 4;
+template <int N> struct TcDepth { static constexpr int value = N > 64 ? 2 : 3; };   // cp.async gather stages in flight per producer warp (smem budget)
 
-template <int N, int STAGES>
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory"); }
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+// warp-converged election of one lane (all 32 lanes must execute this)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int N>
 __global__ void __launch_bounds__(TC_PERSIST_THREADS, 1)
-conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table, int mirror,
+conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, int n_cap, const int* __restrict__ n_dev, int K, int c_in,
                    int c_out) {
-    constexpr int A_BYTES = TC_BM * 128;          // one A tile (hi or lo)
-    constexpr int B_BYTES = N * 128;              // one B tile (hi or lo)
-    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;   // double-buffered accumulator
+    constexpr int STAGES = TC_STAGES;
+    constexpr int TC_DEPTH = TcDepth<N>::value;
+    constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
+    constexpr int STAGE_BYTES = 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t A_COL0 = 2 * N;            // first A-operand column
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    static_assert(2 * N + 64 * STAGES <= 512, "TMEM budget");
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* stages = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
+    unsigned char* a_stage = stages + STAGES * STAGE_BYTES;                 // [8 warps][TC_DEPTH][32 rows x 128 B]
+    int* nbr_s = (int*)(a_stage + TC_PRODUCER_WARPS * TC_DEPTH * 4096);     // [2][TC_BM * K]
 
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], nbr_full[2], nbr_empty[2];
     __shared__ uint32_t s_tmem;
 
     const int n = live_count(n_cap, n_dev);
@@ -183,6 +235,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);           // one tcgen05.commit
             mbar_init(&tmem_empty[b], 128);        // the 128 epilogue threads
+            mbar_init(&nbr_full[b], 1);            // the index loader (+ tx bytes)
+            mbar_init(&nbr_empty[b], 256);         // every producer thread
         }
         fence_mbar_init();
     }
@@ -194,91 +248,155 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 
     if (warp < TC_PRODUCER_WARPS) {
         // ================= producers =================
-        const int group = warp >> 2, wg = warp & 3;
-        const int sub = lane >> 3;       // row within the 4-row group handled per load instruction
-        const int q = lane & 7;          // 16-byte chunk within the 128-byte row
-        float4 cur[8], nxt[8];
-        auto gather = [&](int gi, float4 (&v)[8]) {
-            const int tl = gi / T, j = gi - tl * T;
-            const int k = j / nchunk, cc = j - k * nchunk;
-            const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM;
-            const int c = cc * TC_KC + q * 4;
-            const int kk = mirror ? K - 1 - k : k;
-            int src[8];
+        // Each warp owns 32 output rows of the tile end to end.  Global -> shared: cp.async, 8 lanes per row so a
+        // warp request touches 4 cache lines (a row-per-thread gather would touch 32 and serialise in L1);
+        // invalid neighbours are zero-filled by the copy itself.  Shared -> registers: one row per thread (the
+        // layout tcgen05.st wants), conflict-free through a 16-byte-chunk XOR swizzle.  TC_DEPTH stages in flight.
+        const int group = warp >> 2, quarter = warp & 3;
+        const int sub = lane >> 3, q = lane & 7;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t abuf = smem_u32(a_stage + warp * (TC_DEPTH * 4096));
+        // Lane constants (the issue path is instruction-bound: keep the per-copy address math to a few ops).
+        // Row r = g*4 + sub of the warp's 32 rows goes to r*128 + ((q ^ (r & 7)) << 4); (r & 7) = (g & 1)*4 + sub.
+        const uint32_t dst_even = sub * 128 + ((q ^ sub) << 4);
+        const uint32_t dst_odd = sub * 128 + ((q ^ (4 + sub)) << 4);
+        const uint32_t rowbytes = (uint32_t)c_in * 4u;
+        const int strideK4 = 4 * K;                 // index-tile stride between rows r and r + 4
+        const char* fbase = reinterpret_cast<const char*>(feat_in);
+        // position of the next stage to ISSUE (tile, offset k, chunk cc), advanced by two global stages per step
+        int i_tl = 0, i_k = group / nchunk, i_cc = group - i_k * nchunk;
+        if (i_k >= K) { i_k -= K; i_tl = 1; }      // only when T == 1
+        int cur_tile = -1;                          // tile whose index block this thread currently reads
+        int rows_left = 0;
+        auto issue = [&](int slot) {
+            if (i_tl != cur_tile) {                 // moved on to the next tile's index block
+                if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);
+                cur_tile = i_tl;
+                mbar_wait(&nbr_full[i_tl & 1], (i_tl >> 1) & 1);
+                rows_left = n - (((int)blockIdx.x + i_tl * (int)gridDim.x) * TC_BM + quarter * 32);
+            }
+            const int col = i_cc * TC_KC + q * 4;
+            const bool col_ok = col < c_in;
+            const uint32_t colbytes = (uint32_t)col * 4u;
+            const int* nb = nbr_s + (i_tl & 1) * TC_BM * K + (quarter * 32 + sub) * K + i_k;
+            const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const int r = row0 + wg * 32 + g * 4 + sub;
-                src[g] = r < n ? __ldg(table + (int64_t)r * K + kk) : -1;
+                const int src = nb[g * strideK4];
+                const bool ok = col_ok && (g * 4 + sub) < rows_left && src >= 0;
+                const uint32_t off = ok ? (uint32_t)src * rowbytes + colbytes : 0u;
+                const uint32_t dst = dbase + (uint32_t)(g * 512) + ((g & 1) ? dst_odd : dst_even);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
             }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src[g] >= 0 && c < c_in) v[g] = __ldg(reinterpret_cast<const float4*>(feat_in + (int64_t)src[g] * c_in + c));
-            }
+            cp_async_commit();
+            // advance two global stages
+            i_cc += 2;
+            if (i_cc >= nchunk) { i_cc -= nchunk; ++i_k; if (i_cc >= nchunk) { i_cc -= nchunk; ++i_k; } }
+            if (i_k >= K) { i_k -= K; ++i_tl; }
         };
-        int gi = group;
-        if (gi < total_stages) gather(gi, cur);
-        for (; gi < total_stages; gi += 2) {
-            if (gi + 2 < total_stages) gather(gi + 2, nxt);   // next stage's loads fly while this one is stored
-            const int s = gi % STAGES;
-            const uint32_t ph = (gi / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            unsigned char* st = stages + s * STAGE_BYTES;
+        // this warp's stages: gi = group, group + 2, ...; local counter li
+        const int my_count = (total_stages - group + 1) / 2;
+        for (int li = 0; li < TC_DEPTH - 1 && li < my_count; ++li) issue(li % TC_DEPTH);
+        const uint32_t rd_base = abuf + (uint32_t)lane * 128u;
+        const uint32_t x7 = (uint32_t)(lane & 7);
+        int s = group % STAGES, ph = 0, jpos = group % T, slot = 0;   // consume-side stage slot / phase / weight chunk
+        for (int li = 0; li < my_count; ++li) {
+            if (li + TC_DEPTH - 1 < my_count) issue((li + TC_DEPTH - 1) % TC_DEPTH);
+            else cp_async_commit();                // keep the group count uniform for wait_group
+            cp_async_wait<TC_DEPTH - 1>();
+            __syncwarp();
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t a = rd_base + (uint32_t)slot * 4096u + (((uint32_t)i ^ x7) << 4);
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(a));
+            }
+            __syncwarp();                          // everyone has read the slot before it is refilled
+            mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
+            tc_fence_after();
             if ((tid & 127) == 0) {
-                const int j = gi % T;
+                unsigned char* st = stages + s * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], 2 * B_BYTES);
-                bulk_copy_g2s(st + 2 * A_BYTES, (const char*)packed_w + (int64_t)j * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
+                bulk_copy_g2s(st, (const char*)packed_w + (int64_t)jpos * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
             }
+            uint32_t w[32];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const int r = wg * 32 + g * 4 + sub;
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(cur[g].x) & 0xFFFFE000u);
-                hi.y = __uint_as_float(__float_as_uint(cur[g].y) & 0xFFFFE000u);
-                hi.z = __uint_as_float(__float_as_uint(cur[g].z) & 0xFFFFE000u);
-                hi.w = __uint_as_float(__float_as_uint(cur[g].w) & 0xFFFFE000u);
-                lo.x = cur[g].x - hi.x;
-                lo.y = cur[g].y - hi.y;
-                lo.z = cur[g].z - hi.z;
-                lo.w = cur[g].w - hi.w;
-                const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((q ^ (r & 7)) << 4);
-                *reinterpret_cast<float4*>(st + off) = hi;
-                *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+            for (int i = 0; i < 8; ++i) {          // hi: low 13 mantissa bits cleared -> exact tf32
+                w[4 * i + 0] = __float_as_uint(v[i].x) & 0xFFFFE000u;
+                w[4 * i + 1] = __float_as_uint(v[i].y) & 0xFFFFE000u;
+                w[4 * i + 2] = __float_as_uint(v[i].z) & 0xFFFFE000u;
+                w[4 * i + 3] = __float_as_uint(v[i].w) & 0xFFFFE000u;
             }
-            fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+            tmem_st32(lane_base + A_COL0 + (uint32_t)(s * 64), w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {          // lo: exact fp32 remainder
+                w[4 * i + 0] = __float_as_uint(v[i].x - __uint_as_float(w[4 * i + 0]));
+                w[4 * i + 1] = __float_as_uint(v[i].y - __uint_as_float(w[4 * i + 1]));
+                w[4 * i + 2] = __float_as_uint(v[i].z - __uint_as_float(w[4 * i + 2]));
+                w[4 * i + 3] = __float_as_uint(v[i].w - __uint_as_float(w[4 * i + 3]));
+            }
+            tmem_st32(lane_base + A_COL0 + (uint32_t)(s * 64 + 32), w);
+            tmem_wait_st();
+            tc_fence_before();
             mbar_arrive(&full_bar[s]);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) cur[g] = nxt[g];
+            // advance the consume-side counters by two global stages
+            s += 2; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+            jpos += 2; if (jpos >= T) jpos -= T;
+            if (++slot == TC_DEPTH) slot = 0;
         }
+        if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);
     } else if (warp == TC_MMA_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            int gi = 0;
-            for (int tl = 0; tl < my_tiles; ++tl) {
-                const int buf = tl & 1;
-                mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator
+        // The whole warp runs the loop in warp-uniform control flow and one ELECTed lane issues: a divergent
+        // `if (lane == 0)` makes the compiler wrap every UTCHMMA in a serialisation loop (~100 cycles per MMA
+        // instead of the 32-cycle M*N/256 floor measured with tools/mma_rate.cu).
+        int gi = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int buf = tl & 1;
+            mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+            for (int j = 0; j < T; ++j, ++gi) {
+                const int s = gi % STAGES;
+                const uint32_t ph = (gi / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-                for (int j = 0; j < T; ++j, ++gi) {
-                    const int s = gi % STAGES;
-                    const uint32_t ph = (gi / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(stages + s * STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
-                    const uint32_t b_lo = b_hi + B_BYTES;
+                const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(s * 64);
+                const uint32_t a_lo = a_hi + 32;
+                const uint32_t b_hi = smem_u32(stages + s * STAGE_BYTES);
+                const uint32_t b_lo = b_hi + B_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
-                        const uint64_t da_hi = make_desc_sw128(a_hi + kk * 32), da_lo = make_desc_sw128(a_lo + kk * 32);
+                    for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
                         const uint64_t db_hi = make_desc_sw128(b_hi + kk * 32), db_lo = make_desc_sw128(b_lo + kk * 32);
-                        umma_tf32(d_tmem, da_lo, db_hi, IDESC, (j | kk) != 0);   // small terms first
-                        umma_tf32(d_tmem, da_hi, db_lo, IDESC, 1u);
-                        umma_tf32(d_tmem, da_hi, db_hi, IDESC, 1u);
+                        umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, (j | kk) != 0);   // small terms first
+                        umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
+                        umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
                     }
                     umma_commit(&empty_bar[s]);      // frees the stage once the MMAs above retire
                 }
-                umma_commit(&tmem_full[buf]);        // accumulator complete -> epilogue
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
+            __syncwarp();
+        }
+    } else if (warp == TC_IDX_WARP) {
+        // ================= index loader: TMA-stage each tile's neighbour block =================
+        if (lane == 0) {
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int buf = tl & 1;
+                mbar_wait(&nbr_empty[buf], ((tl >> 1) & 1) ^ 1);
+                const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM;
+                const int rows = n_cap - row0 < TC_BM ? n_cap - row0 : TC_BM;
+                const uint32_t bytes = (uint32_t)rows * K * 4, bulk = bytes & ~15u;
+                int* dst = nbr_s + buf * TC_BM * K;
+                const int* src = table + (int64_t)row0 * K;
+                if (bulk) {
+                    mbar_expect_tx(&nbr_full[buf], bulk);
+                    bulk_copy_g2s(dst, src, bulk, &nbr_full[buf]);
+                }
+                for (uint32_t e = bulk / 4; e < bytes / 4; ++e) dst[e] = __ldg(src + e);   // < 16-byte tail
+                mbar_arrive(&nbr_full[buf]);
             }
         }
         __syncwarp();
@@ -330,13 +448,14 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int N, int STAGES>
-static int launch_tc(const float* feat_in, const int* table, int mirror, const float* packed_w, const float* bias,
+template <int N>
+static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                      const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
                      int K, int c_in, int c_out, cudaStream_t st) {
-    constexpr int STAGE_BYTES = 2 * TC_BM * 128 + 2 * N * 128;
-    size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-    auto kern = conv_fwd_tc_kernel<N, STAGES>;
+    constexpr int STAGE_BYTES = 2 * N * 128;
+    size_t smem = (size_t)TC_STAGES * STAGE_BYTES + (size_t)TC_PRODUCER_WARPS * TcDepth<N>::value * 4096 +
+                  (size_t)2 * TC_BM * K * sizeof(int) + 1024 + 16;
+    auto kern = conv_fwd_tc_kernel<N>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
@@ -344,8 +463,8 @@ static int launch_tc(const float* feat_in, const int* table, int mirror, const f
     }
     int tiles = (n_cap + TC_BM - 1) / TC_BM;
     dim3 grid(tiles < kNumSM ? tiles : kNumSM);    // persistent: one CTA per SM
-    kern<<<grid, TC_PERSIST_THREADS, smem, st>>>(feat_in, table, mirror, packed_w, bias, scale, shift, relu, feat_out,
-                                                 n_cap, n_dev, K, c_in, c_out);
+    kern<<<grid, TC_PERSIST_THREADS, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap,
+                                                 n_dev, K, c_in, c_out);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
@@ -398,9 +517,9 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
     cudaStream_t st = (cudaStream_t)stream;
     const float* pw = (const float*)packed_weight;
     switch (tc_padded_n(c_out)) {
-        case 32: return launch_tc<32, 4>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 64: return launch_tc<64, 4>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 128: return launch_tc<128, 3>(feat_in, nbr_out, 0, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 32: return launch_tc<32>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 64: return launch_tc<64>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 128: return launch_tc<128>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
     }
     return BTC_E_UNSUPPORTED;
 }

@@ -1,0 +1,135 @@
+// Micro-benchmark: issue-to-retire cost of tcgen05.mma (kind::tf32 / kind::f16) on sm_100a as a
+// function of N and of the accumulator dependency pattern.  One CTA, one issuing thread.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu && ./mma_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t a) {
+    uint64_t d = 0;
+    d |= (uint64_t)((a >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+template <int KIND>  // 0 tf32, 1 f16(bf16)
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (KIND == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (KIND == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+// mode: 0 = SS one accumulator, 1 = SS two accumulators alternating, 2 = TS one accumulator, 3 = TS two accumulators
+template <int KIND>
+__global__ void __launch_bounds__(128) bench(int N, int mode, int iters, long long* out) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((float*)smem)[i] = 0.001f * (i % 7);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tm = s_tmem;
+    if (mode == 5) {
+        // warp-uniform issue loop: the whole warp runs the loop, one ELECTed lane issues (CUTLASS style)
+        if (threadIdx.x < 32) {
+            uint32_t fmt = KIND == 0 ? 2u : 1u;
+            uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint64_t db = make_desc_sw128(smem_u32(smem + 16384));
+            long long t0 = clock64();
+            for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint32_t pred = 0;
+                    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+                    if (pred) mma_ts<KIND>(tm, tm + 384 + (u & 3) * 8, db + (u & 3) * 2, idesc, 1u);
+                }
+            }
+            uint32_t pred = 0;
+            asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+            if (pred) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+            } while (!done);
+            long long t1 = clock64();
+            if (threadIdx.x == 0) out[0] = t1 - t0;
+        }
+    } else
+    if (threadIdx.x == 0) {
+        uint32_t fmt = KIND == 0 ? 2u : 1u;  // tf32 / bf16
+        uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        uint64_t da = make_desc_sw128(smem_u32(smem)), db = make_desc_sw128(smem_u32(smem + 16384));
+        long long t0 = clock64();
+        if (mode < 4) {
+        for (int i = 0; i < iters; ++i) {
+            uint32_t d = tm + ((mode & 1) ? (uint32_t)((i & 1) * 256) : 0u);
+            uint32_t kk = (i & 3) * 2;   // walk the 4 k-steps of a 128-byte row
+            if (mode < 2) mma_ss<KIND>(d, da + kk, db + kk, idesc, 1u);
+            else mma_ts<KIND>(d, tm + 384 + (i & 3) * 8, db + kk, idesc, 1u);
+        }
+        } else {   // mode 4: TS, fully unrolled x8, constant operands (pure issue-rate probe)
+        for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mma_ts<KIND>(tm, tm + 384 + (u & 3) * 8, db + (u & 3) * 2, idesc, 1u);
+        }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        } while (!done);
+        long long t1 = clock64();
+        out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+}
+
+int main() {
+    long long* d_out;
+    cudaMalloc(&d_out, 8);
+    size_t smem = 16384 + 32768 + 1024;
+    cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int iters = 4096;
+    const char* names[6] = {"SS 1acc", "SS 2acc", "TS 1acc", "TS 2acc", "TS unrolled", "TS elect-uniform"};
+    for (int kind = 0; kind < 2; ++kind)
+        for (int N : {64, 128, 192, 256})
+            for (int mode = 4; mode < 6; ++mode) {
+                long long h = 0;
+                for (int rep = 0; rep < 2; ++rep) {
+                    if (kind == 0) bench<0><<<1, 128, smem>>>(N, mode, iters, d_out);
+                    else bench<1><<<1, 128, smem>>>(N, mode, iters, d_out);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                    cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+                }
+                double cyc = (double)h / iters;
+                int K = kind == 0 ? 8 : 16;
+                printf("%s M=128 N=%3d K=%2d %s: %7.1f cycles/MMA  -> %7.0f MAC/clk\n", kind == 0 ? "tf32" : "bf16", N, K, names[mode], cyc, 128.0 * N * K / cyc);
+            }
+    return 0;
+}
