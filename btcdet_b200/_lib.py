@@ -43,6 +43,8 @@ SIGNATURES = {
     "btc_maxpool_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _p]),
     "btc_to_dense": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
     "btc_from_dense": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "btc_occ_targets_workspace_bytes": (_i64, [_i, _p, _p]),
+    "btc_occ_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_revoxelize_workspace_bytes": (_i64, [_i, _i64]),
     "btc_revoxelize": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_revoxelize_fill": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _i, _p]),

@@ -1,0 +1,295 @@
+// Occupancy / occlusion mask generation — SURVEY §8 rows a5-a8 and the mask algebra of a12.
+// Replaces, with a handful of fused kernels and no host synchronisation, the torch index-op chain of
+//   btcdet/models/occ_pnt/occ_training_targets/occ_targets_template.py
+//     get_valid / get_voxelwise_mask :194-202, create_predict_area3d :432-447 (225x index blow-up),
+//     occ_from_cylin_ocp :136-155 + point2coords_inrange :82-90 + occ_from_sphere_ocp :110-134 +
+//     get_empty_mask :186-191 (nonzero / cumsum over a promoted int64 volume), filter_occ :249-255,
+//     prepare_cls_loss_map :333 (general_cls_loss_mask).
+//
+// Bit-exactness: torch eager evaluates every *, +, -, / as its own fp32 kernel — no FMA contraction.
+// All arithmetic that feeds a floor/trunc below therefore uses __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn
+// and the same CUDA libm entry points torch uses (sqrtf, atan2f, sinf, cosf); every mask write is an
+// idempotent "store 1", so the result is independent of thread order.
+#include "common.cuh"
+
+namespace btc {
+
+struct OccGeom {
+    float vs[3], lo[3], hi[3];        // occ grid (rho, phi, z): voxel size, range min / max
+    float svs[3], slo[3], shi[3];     // support sphere grid (r, az, el)
+    float empt_thresh, det_zmin, det_zmax;
+    int g[3];                         // nx, ny, nz
+    int sg[3];                        // snx, sny, snz
+    int kern[3];                      // dist kern (z, y, x)
+    int concede_x, use_empty;
+    int batch;
+};
+
+__device__ __forceinline__ float deg2rad_like_torch(float deg) {
+    // coords_utils.py: `x * np.pi / 180.`  ->  (x * fp32(pi)) / 180
+    return __fdiv_rn(__fmul_rn(deg, 3.14159274101257324f), 180.0f);
+}
+constexpr float kRad2Deg = 57.2957801818847656f;   // fp32(180. / np.pi)
+
+// point2coords_inrange (:82-90): inclusive range test, trunc((p - origin) / vs), clamp into the grid
+__device__ __forceinline__ bool quantize_inrange(const float p[3], const float lo[3], const float hi[3],
+                                                 const float vs[3], const int n[3], int c[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!(p[a] >= lo[a] && p[a] <= hi[a])) return false;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        long long q = (long long)__fdiv_rn(__fsub_rn(p[a], lo[a]), vs[a]);
+        q = q < (long long)(n[a] - 1) ? q : (long long)(n[a] - 1);
+        q = q > 0 ? q : 0;
+        c[a] = (int)q;
+    }
+    return true;
+}
+
+// a5 + the sphere scatter of a7: one thread per (voxel, slot)
+__global__ void occ_points_kernel(const float* __restrict__ voxels, int P, int C, const int4* __restrict__ coords,
+                                  const int* __restrict__ num_points, int m_cap, const int* __restrict__ m_dev,
+                                  const float* __restrict__ rot_z, OccGeom g, unsigned char* __restrict__ voxelwise,
+                                  unsigned char* __restrict__ sphere_map) {
+    const int m_live = live_count(m_cap, m_dev);
+    const int64_t work = (int64_t)m_live * P;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(t / P), p = (int)(t - (int64_t)m * P);
+        if (p >= __ldg(num_points + m)) continue;
+        const int4 c = __ldg(coords + m);      // (b, z, y, x)
+        if ((unsigned)c.x >= (unsigned)g.batch) continue;
+        if (p == 0 && (unsigned)c.y < (unsigned)g.g[2] && (unsigned)c.z < (unsigned)g.g[1] && (unsigned)c.w < (unsigned)g.g[0])
+            voxelwise[(((int64_t)c.x * g.g[2] + c.y) * g.g[1] + c.z) * g.g[0] + c.w] = 1;
+        const float* v = voxels + ((int64_t)m * P + p) * C;
+        const float rho = __ldg(v), phi = __ldg(v + 1), z = __ldg(v + 2);
+        // cylinder_uvd2absxyz (coords_utils.py:198-204)
+        const float u = deg2rad_like_torch(phi);
+        const float x = __fmul_rn(rho, cosf(u));
+        const float y = __fmul_rn(-rho, sinf(u));
+        // cartesian_sphere_coords (coords_utils.py:216-226) on (p + sphere_offset), sphere_offset = 0
+        const float xo = __fadd_rn(x, 0.0f), yo = __fadd_rn(y, 0.0f), zo = __fadd_rn(z, 0.0f);
+        const float sx = __fmul_rn(xo, xo), sy = __fmul_rn(yo, yo), sz = __fmul_rn(zo, zo);
+        const float sxy = __fadd_rn(sx, sy);
+        float sp[3];
+        sp[0] = sqrtf(__fadd_rn(sxy, sz));
+        sp[1] = __fmul_rn(atan2f(-yo, xo), kRad2Deg);
+        sp[2] = __fmul_rn(atan2f(zo, sqrtf(sxy)), kRad2Deg);
+        if (rot_z) sp[1] = __fadd_rn(sp[1], __ldg(rot_z + c.x));
+        int sc[3];
+        if (quantize_inrange(sp, g.slo, g.shi, g.svs, g.sg, sc))
+            sphere_map[(((int64_t)c.x * g.sg[2] + sc[2]) * g.sg[1] + sc[1]) * g.sg[0] + sc[0]] = 1;
+    }
+}
+
+// a6 create_predict_area3d: one thread per (voxel, window cell); out-of-grid cells clamp ONTO the border
+__global__ void occ_dilate_kernel(const int4* __restrict__ coords, const int* __restrict__ num_points, int m_cap,
+                                  const int* __restrict__ m_dev, OccGeom g, unsigned char* __restrict__ vcc) {
+    const int m_live = live_count(m_cap, m_dev);
+    const int win = g.kern[0] * g.kern[1] * g.kern[2];
+    const int64_t work = (int64_t)m_live * win;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(t / win), w = (int)(t - (int64_t)m * win);
+        if (__ldg(num_points + m) <= 0) continue;
+        const int4 c = __ldg(coords + m);
+        const int dx = w % g.kern[2], dy = (w / g.kern[2]) % g.kern[1], dz = w / (g.kern[2] * g.kern[1]);
+        int b = min(max(c.x, 0), g.batch - 1);
+        int z = min(max(c.y + dz - g.kern[0] / 2, 0), g.g[2] - 1);
+        int y = min(max(c.z + dy - g.kern[1] / 2, 0), g.g[1] - 1);
+        int x = min(max(c.w + dx - g.kern[2] / 2 + g.concede_x, 0), g.g[0] - 1);
+        vcc[(((int64_t)b * g.g[2] + z) * g.g[1] + y) * g.g[0] + x] = 1;
+    }
+}
+
+// per (b, el, az) column of the sphere map: number of returns and first return at range bin >= 1
+__global__ void sphere_columns_kernel(const unsigned char* __restrict__ sphere_map, OccGeom g, int* __restrict__ counts,
+                                      int* __restrict__ first1) {
+    const int64_t cols = (int64_t)g.batch * g.sg[2] * g.sg[1];
+    for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < cols; col += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char* p = sphere_map + col * g.sg[0];
+        int cnt = 0, first = g.sg[0];
+        for (int r = 0; r < g.sg[0]; ++r) {
+            int v = p[r] != 0;
+            cnt += v;
+            if (v && r >= 1 && first == g.sg[0]) first = r;
+        }
+        counts[col] = cnt;
+        first1[col] = p[0] ? -(first + 1) : first;   // sign bit: range bin 0 holds a return of its own
+    }
+}
+
+// occ_from_sphere_ocp + back-projection: one thread per sphere cell (b, el, az, r)
+__global__ void sphere_occlusion_kernel(const int* __restrict__ counts, const int* __restrict__ first1, OccGeom g,
+                                        unsigned char* __restrict__ occ_raw) {
+    const int snx = g.sg[0], sny = g.sg[1], snz = g.sg[2];
+    const int64_t cells = (int64_t)g.batch * snz * sny * snx;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < cells; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t % snx);
+        const int64_t col = t / snx;
+        const int az = (int)(col % sny);
+        const int el = (int)((col / sny) % snz);
+        const int b = (int)(col / ((int64_t)sny * snz));
+        int first = __ldg(first1 + col);
+        const bool own_bin0 = first < 0;
+        if (own_bin0) first = -first - 1;
+        if (g.use_empty) {
+            // range bin 0 <- empty column whose 3x3 (el, az) neighbourhood holds > thresh returns (get_empty_mask)
+            bool bin0 = false;
+            if (__ldg(counts + col) == 0) {
+                float s = 0.f;   // fixed all-ones 3x3 conv over float counts, zero padded (exact small integers)
+                for (int de = -1; de <= 1; ++de)
+                    for (int da = -1; da <= 1; ++da) {
+                        int e2 = el + de, a2 = az + da;
+                        if (e2 >= 0 && e2 < snz && a2 >= 0 && a2 < sny)
+                            s += (float)__ldg(counts + ((int64_t)b * snz + e2) * sny + a2);
+                    }
+                bin0 = s > g.empt_thresh;
+            }
+            if (bin0) first = 0;
+        } else if (own_bin0) {
+            first = 0;   // EMPT_SUR_THRESH >= 9: bin 0 is not overwritten and keeps its own return
+        }
+        if (r < first) continue;   // cumsum(dim=r) > 0.9: at or behind the first return
+        // bin lower corner -> Cartesian -> cylinder (occ_targets_template.py:147-149)
+        const float sr = __fadd_rn(__fmul_rn((float)r, g.svs[0]), g.slo[0]);
+        const float sa = __fadd_rn(__fmul_rn((float)az, g.svs[1]), g.slo[1]);
+        const float se = __fadd_rn(__fmul_rn((float)el, g.svs[2]), g.slo[2]);
+        const float te = deg2rad_like_torch(se), ta = deg2rad_like_torch(sa);
+        const float xyd = __fmul_rn(sr, cosf(te));
+        const float x = __fmul_rn(xyd, cosf(ta));
+        const float y = __fmul_rn(-xyd, sinf(ta));
+        const float z = __fmul_rn(sr, sinf(te));
+        const float xo = __fsub_rn(x, 0.0f), yo = __fsub_rn(y, 0.0f), zo = __fsub_rn(z, 0.0f);
+        float cp[3];
+        cp[0] = sqrtf(__fadd_rn(__fmul_rn(xo, xo), __fmul_rn(yo, yo)));
+        cp[1] = __fmul_rn(atan2f(-yo, xo), kRad2Deg);
+        cp[2] = zo;
+        int cc[3];
+        if (quantize_inrange(cp, g.lo, g.hi, g.vs, g.g, cc))
+            occ_raw[(((int64_t)b * g.g[2] + cc[2]) * g.g[1] + cc[1]) * g.g[0] + cc[0]] = 1;
+    }
+}
+
+// filter_occ part 1: per (b, x) the minimum over (z, y) of (1 - occupied) * 100 + z_centre
+__global__ void occ_floor_kernel(const unsigned char* __restrict__ voxelwise, OccGeom g, float* __restrict__ floor_z) {
+    const int nx = g.g[0], ny = g.g[1], nz = g.g[2];
+    const int64_t n = (int64_t)g.batch * nx;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx), b = (int)(t / nx);
+        float m = 3.4e38f;
+        for (int z = 0; z < nz; ++z) {
+            const float zc = __fadd_rn(__fmul_rn(__fadd_rn(0.5f, (float)z), g.vs[2]), g.lo[2]);
+            const float free_v = __fadd_rn(100.0f, zc);
+            const unsigned char* row = voxelwise + (((int64_t)b * nz + z) * ny) * nx + x;
+            bool any_occ = false, any_free = false;
+            for (int y = 0; y < ny; ++y) {
+                if (row[(int64_t)y * nx]) any_occ = true; else any_free = true;
+            }
+            if (any_occ) m = fminf(m, zc);
+            if (any_free) m = fminf(m, free_v);
+        }
+        if (m > 20.0f) m = __fsub_rn(m, 200.0f);
+        floor_z[t] = fmaxf(m, g.det_zmin);
+    }
+}
+
+// filter_occ part 2 + general_cls_loss_mask
+__global__ void occ_filter_kernel(const unsigned char* __restrict__ occ_raw, const unsigned char* __restrict__ vcc,
+                                  const float* __restrict__ floor_z, OccGeom g, unsigned char* __restrict__ occ_mask,
+                                  unsigned char* __restrict__ general_mask) {
+    const int nx = g.g[0], ny = g.g[1], nz = g.g[2];
+    const int64_t cells = (int64_t)g.batch * nz * ny * nx;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < cells; t += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int z = (int)((t / ((int64_t)nx * ny)) % nz);
+        const int b = (int)(t / ((int64_t)nx * ny * nz));
+        const float zc = __fadd_rn(__fmul_rn(__fadd_rn(0.5f, (float)z), g.vs[2]), g.lo[2]);
+        const unsigned char o = (occ_raw[t] && zc > floor_z[(int64_t)b * nx + x] && zc < g.det_zmax) ? 1 : 0;
+        occ_mask[t] = o;
+        if (general_mask) general_mask[t] = o & vcc[t];
+    }
+}
+
+static int64_t occ_ws(const OccGeom& g, int64_t* o_sphere, int64_t* o_counts, int64_t* o_first, int64_t* o_floor,
+                      int64_t* o_raw) {
+    int64_t off = 0;
+    int64_t sph = (int64_t)g.batch * g.sg[0] * g.sg[1] * g.sg[2];
+    int64_t cols = (int64_t)g.batch * g.sg[1] * g.sg[2];
+    int64_t cells = (int64_t)g.batch * g.g[0] * g.g[1] * g.g[2];
+    *o_sphere = off; off += align_up(sph, 256);
+    *o_raw = off; off += align_up(cells, 256);
+    *o_counts = off; off += align_up(cols * 4, 256);
+    *o_first = off; off += align_up(cols * 4, 256);
+    *o_floor = off; off += align_up((int64_t)g.batch * g.g[0] * 4, 256);
+    return off;
+}
+
+static int parse_geom(OccGeom& g, int batch, const float* gf, const int* gi) {
+    if (!gf || !gi || batch < 1) return BTC_E_BADARG;
+    for (int a = 0; a < 3; ++a) {
+        g.vs[a] = gf[a]; g.lo[a] = gf[3 + a]; g.hi[a] = gf[6 + a];
+        g.svs[a] = gf[9 + a]; g.slo[a] = gf[12 + a]; g.shi[a] = gf[15 + a];
+        g.g[a] = gi[a]; g.sg[a] = gi[3 + a]; g.kern[a] = gi[6 + a];
+        if (g.g[a] < 1 || g.sg[a] < 1 || g.kern[a] < 1) return BTC_E_BADARG;
+    }
+    g.empt_thresh = gf[18]; g.det_zmin = gf[19]; g.det_zmax = gf[20];
+    g.concede_x = gi[9]; g.use_empty = gi[10];
+    g.batch = batch;
+    return BTC_OK;
+}
+
+}  // namespace btc
+
+using namespace btc;
+
+extern "C" {
+
+int64_t btc_occ_targets_workspace_bytes(int batch, const float* geom_f, const int* geom_i) {
+    OccGeom g;
+    if (parse_geom(g, batch, geom_f, geom_i)) return BTC_E_BADARG;
+    int64_t a, b, c, d, e;
+    return occ_ws(g, &a, &b, &c, &d, &e);
+}
+
+int btc_occ_targets(const float* voxels, int P, int C, const int* voxel_coords, const int* num_points, int m_cap,
+                    const int* m_dev, int batch, const float* rot_z, const float* geom_f, const int* geom_i,
+                    uint8_t* voxelwise_mask, uint8_t* vcc_mask, uint8_t* occ_mask, uint8_t* general_mask,
+                    uint8_t* sphere_map_out, void* workspace, int64_t workspace_bytes, void* stream) {
+    OccGeom g;
+    if (parse_geom(g, batch, geom_f, geom_i)) return badarg("btc_occ_targets: bad geometry");
+    if (!voxelwise_mask || !vcc_mask || !occ_mask || !workspace) return badarg("btc_occ_targets: null argument");
+    if (m_cap > 0 && (!voxels || !voxel_coords || !num_points)) return badarg("btc_occ_targets: null inputs");
+    if (P < 1 || C < 3) return badarg("btc_occ_targets: bad voxel layout");
+    int64_t o_sphere, o_counts, o_first, o_floor, o_raw;
+    if (workspace_bytes < occ_ws(g, &o_sphere, &o_counts, &o_first, &o_floor, &o_raw)) return badarg("btc_occ_targets: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    unsigned char* sphere = (unsigned char*)(ws + o_sphere);
+    unsigned char* raw = (unsigned char*)(ws + o_raw);
+    int* counts = (int*)(ws + o_counts);
+    int* first1 = (int*)(ws + o_first);
+    float* floor_z = (float*)(ws + o_floor);
+    const int64_t cells = (int64_t)batch * g.g[0] * g.g[1] * g.g[2];
+    const int64_t sph = (int64_t)batch * g.sg[0] * g.sg[1] * g.sg[2];
+    BTC_CUDA(cudaMemsetAsync(voxelwise_mask, 0, cells, st), "occ memset");
+    BTC_CUDA(cudaMemsetAsync(vcc_mask, 0, cells, st), "occ memset");
+    BTC_CUDA(cudaMemsetAsync(sphere, 0, align_up(sph, 256) + align_up(cells, 256), st), "occ memset");   // sphere + raw
+    const int T = 256;
+    if (m_cap > 0) {
+        occ_points_kernel<<<grid_for((int64_t)m_cap * P, T), T, 0, st>>>(voxels, P, C, (const int4*)voxel_coords, num_points,
+                                                                         m_cap, m_dev, rot_z, g, voxelwise_mask, sphere);
+        int win = g.kern[0] * g.kern[1] * g.kern[2];
+        occ_dilate_kernel<<<grid_for((int64_t)m_cap * win, T), T, 0, st>>>((const int4*)voxel_coords, num_points, m_cap, m_dev,
+                                                                           g, vcc_mask);
+    }
+    sphere_columns_kernel<<<grid_for((int64_t)batch * g.sg[1] * g.sg[2], T), T, 0, st>>>(sphere, g, counts, first1);
+    sphere_occlusion_kernel<<<grid_for(sph, T), T, 0, st>>>(counts, first1, g, raw);
+    occ_floor_kernel<<<grid_for((int64_t)batch * g.g[0], 64), 64, 0, st>>>(voxelwise_mask, g, floor_z);
+    occ_filter_kernel<<<grid_for(cells, T), T, 0, st>>>(raw, vcc_mask, floor_z, g, occ_mask, general_mask);
+    if (sphere_map_out) BTC_CUDA(cudaMemcpyAsync(sphere_map_out, sphere, sph, cudaMemcpyDeviceToDevice, st), "occ copy");
+    BTC_CHECK_LAUNCH("occ_targets");
+    return BTC_OK;
+}
+
+}  // extern "C"

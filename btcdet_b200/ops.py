@@ -471,3 +471,51 @@ def revoxelize_sorted(pt_coords: torch.Tensor, pt_feat: torch.Tensor, batch: int
     check(lib.btc_revoxelize_fill(_ptr(pt_feat), _ptr(pt_voxel), _ptr(slots), n, None, c, pmax, _ptr(voxels), m,
                                   _stream()), "btc_revoxelize_fill")
     return voxels, vox_count[:m].to(torch.int64), vox_coords[:m].to(torch.int64)
+
+
+# ------------------------------------------------------------------------------------------
+# occupancy / occlusion masks
+# ------------------------------------------------------------------------------------------
+def occ_geometry_arrays(voxel_size, point_cloud_range, support_sphere_range, dist_kern, half_x, empt_sur_thresh,
+                        det_point_cloud_range):
+    """Pack DATA_CONFIG.OCC geometry (btcdet_kitti_car.yaml:72-92) into the geom_f / geom_i arrays of btc_occ_targets."""
+    import numpy as np
+    r, v = np.array(point_cloud_range, dtype=np.float64), np.array(voxel_size, dtype=np.float64)
+    grid = np.round((r[3:6] - r[0:3]) / v).astype(np.int64)                       # data_processor.py:119-120
+    sr = np.asarray(support_sphere_range, dtype=np.float64)
+    svs = np.array([voxel_size[0], voxel_size[1], sr[6]], dtype=np.float64)        # occ_targets_template.py:48
+    sgrid = ((sr[3:6] - sr[:3]) / svs).astype(int)                                 # :51 (truncation)
+    use_empty = empt_sur_thresh != "None" and float(empt_sur_thresh) < 9
+    gf = list(voxel_size) + list(r[:3]) + list(r[3:6]) + list(svs) + list(sr[:3]) + list(sr[3:6]) + \
+        [float(empt_sur_thresh) if use_empty else 0.0, float(det_point_cloud_range[2]), float(det_point_cloud_range[5])]
+    gi = [int(g) for g in grid] + [int(g) for g in sgrid] + [int(k) for k in dist_kern] + \
+        [int(dist_kern[-1] // 2 if half_x else 0), int(use_empty)]
+    return gf, gi
+
+
+def occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom_i, rot_z=None, want_sphere=False):
+    """Fused GPU occupancy / occlusion masks.  Returns a dict of uint8 [B,nz,ny,nx] tensors."""
+    _require_cuda(voxels, voxel_coords, voxel_num_points)
+    lib = _lib.load()
+    dev = voxels.device
+    voxels = voxels.to(torch.float32).contiguous()
+    coords = voxel_coords.to(torch.int32).contiguous()
+    nump = voxel_num_points.to(torch.int32).contiguous()
+    m, P, C = voxels.shape
+    B = int(batch_size)
+    gf, gi = float_array(geom_f), (ctypes.c_int * len(geom_i))(*[int(v) for v in geom_i])
+    nx, ny, nz = geom_i[0:3]
+    shape = (B, nz, ny, nx)
+    out = {k: torch.empty(shape, dtype=torch.uint8, device=dev)
+           for k in ("voxelwise_mask", "vcc_mask", "occ_voxelwise_mask", "general_cls_loss_mask")}
+    sphere = torch.empty((B, geom_i[5], geom_i[4], geom_i[3]), dtype=torch.uint8, device=dev) if want_sphere else None
+    ws_bytes = int(lib.btc_occ_targets_workspace_bytes(B, gf, gi))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rz = None if rot_z is None else rot_z.to(torch.float32).contiguous()
+    check(lib.btc_occ_targets(_ptr(voxels), P, C, _ptr(coords), _ptr(nump), m, None, B, _ptr(rz), gf, gi,
+                              _ptr(out["voxelwise_mask"]), _ptr(out["vcc_mask"]), _ptr(out["occ_voxelwise_mask"]),
+                              _ptr(out["general_cls_loss_mask"]), _ptr(sphere), _ptr(ws), ws_bytes, _stream()),
+          "btc_occ_targets")
+    if want_sphere:
+        out["sphere_map"] = sphere
+    return out

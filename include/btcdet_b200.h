@@ -313,6 +313,34 @@ int btc_revoxelize_fill(const float* pt_feat, const int* pt_voxel, const int* sl
                         int n_cap, const int* n_dev, int c, int p_max,
                         float* voxels, int vox_rows, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Occupancy / occlusion masks (SURVEY §8 rows a5-a8 + the mask algebra of a12) */
+/* Replaces, in one sync-free call, the torch index-op chain of               */
+/* btcdet/models/occ_pnt/occ_training_targets/occ_targets_template.py:        */
+/* get_valid/get_voxelwise_mask :194-202, create_predict_area3d :432-447,      */
+/* occ_from_cylin_ocp :136-155 (+ :82-90, :110-134, :186-191), filter_occ      */
+/* :249-255 and general_cls_loss_mask :333.  Bit-exact with that code run on   */
+/* the same device (fp32 op order and CUDA libm calls reproduced, no FMA).     */
+/*                                                                            */
+/* voxels [m, P, C>=3] f32 cylindrical (rho, phi deg, z, ...); voxel_coords    */
+/* [m, 4] i32 (b, z, y, x); num_points [m] i32; rot_z [batch] f32 or NULL.     */
+/* geom_f[21]: voxel_size[3], range_min[3], range_max[3] of the occ grid       */
+/*   (rho, phi, z order), sphere voxel_size[3], sphere_min[3], sphere_max[3]   */
+/*   (r, az, el order), EMPT_SUR_THRESH, det z min, det z max.                 */
+/* geom_i[11]: grid nx,ny,nz; sphere grid nx,ny,nz; DIST_KERN z,y,x;           */
+/*   concede_x; use_empty_surround (EMPT_SUR_THRESH < 9).                      */
+/* Outputs u8 [batch, nz, ny, nx]: voxelwise_mask, vcc_mask,                   */
+/*   occ_voxelwise_mask (after filter_occ), general_cls_loss_mask (or NULL);   */
+/*   sphere_map_out u8 [batch, snz, sny, snx] or NULL (before the empty-       */
+/*   surround rewrite of range bin 0).                                         */
+/* ------------------------------------------------------------------------- */
+int64_t btc_occ_targets_workspace_bytes(int batch, const float* geom_f, const int* geom_i);
+int btc_occ_targets(const float* voxels, int P, int C, const int* voxel_coords, const int* num_points,
+                    int m_cap, const int* m_dev, int batch, const float* rot_z,
+                    const float* geom_f, const int* geom_i,
+                    uint8_t* voxelwise_mask, uint8_t* vcc_mask, uint8_t* occ_mask, uint8_t* general_mask,
+                    uint8_t* sphere_map_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

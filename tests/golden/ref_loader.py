@@ -1,0 +1,126 @@
+"""Loads pieces of the reference (/root/reference, read-only) in THIS container so that their outputs
+can pin the oracle and generate golden fixtures (the GPU box has no reference checkout).
+
+The reference's model code cannot be imported as a package here: `btcdet/models/__init__.py` pulls in
+detectors that need compiled CUDA extensions (THC-era, unbuildable — SURVEY §8c), and the mask code
+hard-codes device="cuda".  This loader
+  * registers empty namespace packages for `btcdet`, `btcdet.utils`, `btcdet.models`, ... and executes
+    only the requested source files under their real dotted names (relative imports then resolve);
+  * stubs `btcdet.ops.roiaware_pool3d.roiaware_pool3d_utils` (imported, never called on these paths);
+  * while the reference code runs, rewrites device="cuda" to "cpu" in torch factory calls.
+Nothing is copied: the files are executed where they lie.
+"""
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "btcdet"))
+
+
+def _ns(name, path):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    m.__package__ = name
+    sys.modules[name] = m
+    return m
+
+
+def _load(name, relpath):
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None):
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    parent, _, leaf = name.rpartition(".")
+    if parent in sys.modules:
+        setattr(sys.modules[parent], leaf, mod)
+    return mod
+
+
+def load_reference_modules():
+    """Returns a dict of the reference modules on the mask / re-voxelisation path."""
+    assert available(), "reference checkout not present"
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if root not in sys.path:
+        sys.path.insert(0, root)   # the drop-in `spconv` shim
+    if not hasattr(np, "int"):
+        np.int = int               # removed numpy alias used at occ_targets_template.py:51
+    _ns("btcdet", os.path.join(REF, "btcdet"))
+    _ns("btcdet.utils", os.path.join(REF, "btcdet/utils"))
+    _ns("btcdet.ops", os.path.join(REF, "btcdet/ops"))
+    _ns("btcdet.ops.roiaware_pool3d", os.path.join(REF, "btcdet/ops/roiaware_pool3d"))
+    stub = types.ModuleType("btcdet.ops.roiaware_pool3d.roiaware_pool3d_utils")
+    sys.modules[stub.__name__] = stub
+    sys.modules["btcdet.ops.roiaware_pool3d"].roiaware_pool3d_utils = stub
+    _ns("btcdet.models", os.path.join(REF, "btcdet/models"))
+    _ns("btcdet.models.backbones_3d", os.path.join(REF, "btcdet/models/backbones_3d"))
+    _ns("btcdet.models.occ_pnt", os.path.join(REF, "btcdet/models/occ_pnt"))
+    _ns("btcdet.models.occ_pnt.occ_training_targets", os.path.join(REF, "btcdet/models/occ_pnt/occ_training_targets"))
+    mods = {}
+    mods["common_utils"] = _load("btcdet.utils.common_utils", "btcdet/utils/common_utils.py")
+    mods["coords_utils"] = _load("btcdet.utils.coords_utils", "btcdet/utils/coords_utils.py")
+    mods["point_box_utils"] = _load("btcdet.utils.point_box_utils", "btcdet/utils/point_box_utils.py")
+    with cuda_as_cpu():
+        mods["spconv_backbone"] = _load("btcdet.models.backbones_3d.spconv_backbone",
+                                        "btcdet/models/backbones_3d/spconv_backbone.py")
+        mods["occ_targets_template"] = _load("btcdet.models.occ_pnt.occ_training_targets.occ_targets_template",
+                                             "btcdet/models/occ_pnt/occ_training_targets/occ_targets_template.py")
+        mods["occ_targets_3d"] = _load("btcdet.models.occ_pnt.occ_training_targets.occ_targets_3d",
+                                       "btcdet/models/occ_pnt/occ_training_targets/occ_targets_3d.py")
+    return mods
+
+
+_FACTORIES = ["zeros", "ones", "empty", "full", "tensor", "as_tensor", "arange", "zeros_like", "ones_like", "rand",
+              "randint", "linspace", "eye", "meshgrid"]
+
+
+@contextlib.contextmanager
+def cuda_as_cpu():
+    """Rewrite device="cuda" to "cpu" in torch factory calls while reference code executes."""
+    saved = {}
+
+    def wrap(fn):
+        def inner(*a, **kw):
+            dev = kw.get("device")
+            if dev is not None and str(dev).startswith("cuda"):
+                kw["device"] = "cpu"
+            return fn(*a, **kw)
+        return inner
+
+    for name in _FACTORIES:
+        saved[name] = getattr(torch, name)
+        setattr(torch, name, wrap(saved[name]))
+    try:
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(torch, name, fn)
+
+
+class Cfg(dict):
+    """easydict.EasyDict stand-in (not installed here)."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError:
+            raise AttributeError(k)
+        return v
+
+    @staticmethod
+    def wrap(d):
+        if isinstance(d, dict):
+            return Cfg({k: Cfg.wrap(v) for k, v in d.items()})
+        return d
