@@ -26,8 +26,11 @@ struct OccGeom {
 };
 
 __device__ __forceinline__ float deg2rad_like_torch(float deg) {
-    // coords_utils.py: `x * np.pi / 180.`  ->  (x * fp32(pi)) / 180
-    return __fdiv_rn(__fmul_rn(deg, 3.14159274101257324f), 180.0f);
+    // coords_utils.py: `x * np.pi / 180.`.  On CUDA, torch evaluates tensor / python_scalar as a multiplication by
+    // the reciprocal computed once on the host in fp32 (ATen BinaryDivTrueKernel.cu, "is_cpu_scalar" fast path):
+    // (x * fp32(pi)) * fp32(1/180) — NOT an IEEE division.  The reference only runs on CUDA, so that is the
+    // behaviour to reproduce (a CPU run of the same code divides, and differs at bin edges).
+    return __fmul_rn(__fmul_rn(deg, 3.14159274101257324f), 1.0f / 180.0f);
 }
 constexpr float kRad2Deg = 57.2957801818847656f;   // fp32(180. / np.pi)
 

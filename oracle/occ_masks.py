@@ -75,18 +75,33 @@ def all_voxel_centers_z(geo: OccGeometry, device):
     return zc.view(nz, 1, 1).expand(nz, ny, nx).contiguous()
 
 
+# `tensor / python_scalar` is device dependent in torch: the CPU kernel divides, the CUDA kernel multiplies by the
+# fp32 reciprocal computed on the host (ATen BinaryDivTrueKernel.cu, is_cpu_scalar fast path).  The mask code
+# back-projects sphere-bin LOWER CORNERS, which land exactly on cylinder-bin edges, so this one-ulp difference
+# moves ~10 % of the occluded cells (measured: 20 623 of 204 511 on the fixture scene).  The reference only runs
+# on CUDA; `CUDA_SCALAR_DIV` = True makes CPU tensors follow the CUDA rule (CUDA tensors always do).
+CUDA_SCALAR_DIV = False
+
+
+def _deg2rad(x):
+    """`x * np.pi / 180.` (coords_utils.py:181-185,200-202) under the active scalar-division rule."""
+    if CUDA_SCALAR_DIV and not x.is_cuda:
+        return (x * np.pi) * float(np.float32(1.0) / np.float32(180.0))
+    return x * np.pi / 180.
+
+
 def cylinder_uvd2absxyz(rho, phi, z):
     """coords_utils.py:198-204: u = (phi*pi)/180 ; x = rho*cos(u) ; y = (-rho)*sin(u)."""
-    u = phi * np.pi / 180.
+    u = _deg2rad(phi)
     return torch.stack([rho * torch.cos(u), -rho * torch.sin(u), z], dim=-1)
 
 
 def sphere_uvd2absxyz(r, az, el):
     """coords_utils.py:180-186."""
-    xydist = r * torch.cos(el * np.pi / 180.)
-    x = xydist * torch.cos(az * np.pi / 180.)
-    y = -xydist * torch.sin(az * np.pi / 180.)
-    z = r * torch.sin(el * np.pi / 180.)
+    xydist = r * torch.cos(_deg2rad(el))
+    x = xydist * torch.cos(_deg2rad(az))
+    y = -xydist * torch.sin(_deg2rad(az))
+    z = r * torch.sin(_deg2rad(el))
     return torch.stack([x, y, z], dim=-1)
 
 

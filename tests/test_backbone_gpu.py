@@ -98,3 +98,72 @@ def test_planned_engine_reports_capacity_overflow(cuda):
     plan.forward(torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda())
     with pytest.raises(_lib.BtcError):
         plan.read_counts()
+
+
+def _randomize(model, seed):
+    from btcdet_b200 import backbones
+    torch.manual_seed(seed)
+    for m in model.modules():
+        if hasattr(m, "reset_parameters") and not isinstance(m, torch.nn.BatchNorm1d):
+            m.reset_parameters()
+    return backbones.randomize_bn_(model, seed).eval()
+
+
+def test_reference_det_backbone_topology_matches_oracle(cuda, oracle):
+    """VoxelBackBone8xOcc dataflow (spconv_backbone.py:936-1019): SubM/SparseConv/SparseMaxPool3d, sparse_cat across
+    tensors built by different ops, cached 'spconv3'/'spconv4' rulebooks reused by down2/down3, dense() + gather."""
+    import spconv
+    from btcdet_b200 import synthetic as S
+    from tests import models_mirror, oracle_net
+    batch = 2
+    model = _randomize(models_mirror.DetBackboneMirror(6, 4), 3)
+    scenes = [S.lidar_like(12000, seed=300 + b) for b in range(batch)]
+    v, coords, npts = oracle.voxelize_batch(scenes, S.DET_VOXEL_SIZE, S.KITTI_RANGE, 5, 16000)
+    rng = np.random.default_rng(0)
+    feats = np.concatenate([(v.sum(1) / np.maximum(npts, 1)[:, None]), rng.uniform(0, 1, (v.shape[0], 2))], 1).astype(np.float32)
+    occ_feats = np.abs(rng.standard_normal((v.shape[0], 2))).astype(np.float32)
+    ref = model.run(models_mirror.OracleBackend(), oracle_net.to_oracle_tensor(feats, coords, model.sparse_shape, batch),
+                    occ_feats)
+    model = model.cuda()
+    with torch.no_grad():
+        x = spconv.SparseConvTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda(), model.sparse_shape, batch)
+        got = model.run(models_mirror.ShimBackend(), x, torch.from_numpy(occ_feats).cuda())
+    for name in ("x_conv2", "x_conv3", "out", "x_combine"):
+        np.testing.assert_array_equal(got[name].indices.cpu().numpy(), ref[name].indices, err_msg=name)
+        assert rel_err(got[name].features.cpu().numpy(), ref[name].features) < REL_TOL, name
+    assert got["x_combine"].features.shape[1] == 128 and list(got["out"].spatial_shape) == [2, 200, 176]
+
+
+def test_reference_occ_backbone_topology_matches_oracle(cuda, oracle):
+    """VoxelBackBoneDeconv + OccHead3D convs (spconv_backbone.py:138-203, occ_head_3D.py:41-52): dilating
+    SparseConv3d, two SparseConvTranspose3d, SubM heads with/without bias, dense() of the head outputs."""
+    import spconv
+    from btcdet_b200 import synthetic as S
+    from tests import models_mirror, oracle_net
+    from oracle.occ_masks import OccGeometry
+    geo = OccGeometry()
+    batch = 2
+    model = _randomize(models_mirror.OccBackboneMirror(4), 5)
+    gen = oracle.VoxelGeneratorV2(geo.voxel_size, geo.point_cloud_range, S.OCC_MAX_POINTS, S.OCC_MAX_VOXELS["train"])
+    fs, cs = [], []
+    for b in range(batch):
+        pts = S.lidar_like(6000, seed=400 + b)
+        cyl = np.stack([np.linalg.norm(pts[:, :2], axis=1), np.arctan2(-pts[:, 1], pts[:, 0]) * 180. / np.pi, pts[:, 2],
+                        pts[:, 3]], -1).astype(np.float32)
+        r = gen.generate(cyl)
+        fs.append(r["voxels"].sum(1) / np.maximum(r["num_points_per_voxel"], 1)[:, None])
+        cs.append(np.pad(r["coordinates"], ((0, 0), (1, 0)), constant_values=b))
+    feats, coords = np.concatenate(fs).astype(np.float32), np.concatenate(cs).astype(np.int32)
+    feats = feats / np.array([70.0, 40.0, 3.0, 1.0], np.float32)      # keep activations O(1)
+    ref = model.run(models_mirror.OracleBackend(), oracle_net.to_oracle_tensor(feats, coords, model.sparse_shape, batch))
+    model = model.cuda()
+    with torch.no_grad():
+        x = spconv.SparseConvTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda(), model.sparse_shape, batch)
+        got = model.run(models_mirror.ShimBackend(), x)
+        dense_cls = got["cls"].dense()
+    for name in ("encoded", "cls", "res"):
+        np.testing.assert_array_equal(got[name].indices.cpu().numpy(), ref[name].indices, err_msg=name)
+        assert rel_err(got[name].features.cpu().numpy(), ref[name].features) < REL_TOL, name
+    assert list(got["encoded"].spatial_shape) == [9, 157, 209] and got["encoded"].indices.shape[0] > 5 * coords.shape[0]
+    np.testing.assert_array_equal(dense_cls.cpu().numpy(), oracle.dense(got["cls"].features.cpu().numpy(),
+                                                                         ref["cls"].indices, [9, 157, 209], batch))

@@ -51,3 +51,26 @@ def test_reference_backbones_build_on_the_shim():
     assert float(fix.weight.min()) == float(fix.weight.max()) == pytest.approx(1.0 / 27)
     block = sb.SparseBasicBlock(16, 16, norm_fn=lambda c: __import__("torch").nn.BatchNorm1d(c), indice_key="r")
     assert isinstance(block, spconv.SparseModule)
+
+
+def test_mirrors_have_the_reference_state_dict_layout():
+    """tests/models_mirror.py (used by the -m gpu tests, where no reference exists) is checked here against the
+    real classes: identical parameter / buffer names and shapes."""
+    import numpy as np
+    from tests import models_mirror
+    sb = _load("ref_spconv_backbone", "btcdet/models/backbones_3d/spconv_backbone.py")
+    ref_occ = sb.VoxelBackBoneDeconv(_Cfg(), input_channels=4, grid_size=[209, 157, 9])
+    mir_occ = models_mirror.OccBackboneMirror(4, (209, 157, 9))
+    ref_sd = {k: tuple(v.shape) for k, v in ref_occ.state_dict().items()}
+    mir_sd = {k: tuple(v.shape) for k, v in mir_occ.state_dict().items() if not k.startswith(("conv_cls", "conv_res"))}
+    assert ref_sd == mir_sd and mir_occ.sparse_shape == ref_occ.sparse_shape
+    cfg = _Cfg(OCC_CONV_TYPE=['identity', 'maxpool'], OCC_CONV_EXECUTE=[False, True],
+               OUT_FEAT_TYPE=['None', 'None', 'None', 'None', 'big_bev_combine'])
+    ref_det = sb.VoxelBackBone8xOcc(cfg, input_channels=6, grid_size=np.array([1408, 1600, 40]),
+                                    original_num_rawpoint_features=4)
+    mir_det = models_mirror.DetBackboneMirror(6, 4, (1408, 1600, 40))
+    assert {k: tuple(v.shape) for k, v in ref_det.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in mir_det.state_dict().items()}
+    assert list(ref_det.sparse_shape) == mir_det.sparse_shape
+    # the real classes' parameters load into the mirror unchanged (same names, same layouts)
+    mir_det.load_state_dict(ref_det.state_dict())
