@@ -112,23 +112,24 @@ __host__ __device__ __forceinline__ int sw128_offset(int r, int j) {
 }
 
 // ---- weight pre-pack ------------------------------------------------------------------------------
-// packed[k][chunk] = { B_hi image [N x 128 B] , B_lo image [N x 128 B] }, B = W[k]^T (N x Cin, K-major)
+// The reduction axis is the flattened (offset k, input channel ci) index e = k*c_in + ci, cut into chunks of 32:
+// thin layers pack several offsets into one MMA stage (c_in = 4: eight offsets per stage, 4 stages per tile).
+// packed[chunk] = { B_hi image [N x 128 B] , B_lo image [N x 128 B] },  B[n][j] = W[e/c_in][e%c_in][n], e = 32*chunk + j
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_in, int c_out, int N,
                                       float* __restrict__ packed) {
-    const int nchunk = (c_in + TC_KC - 1) / TC_KC;
-    const int64_t total = (int64_t)K * nchunk * N * TC_KC;
+    const int E = K * c_in;
+    const int nchunk = (E + TC_KC - 1) / TC_KC;
+    const int64_t total = (int64_t)nchunk * N * TC_KC;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int j = (int)(t % TC_KC);
         int64_t r = t / TC_KC;
         int n = (int)(r % N);
-        r /= N;
-        int cc = (int)(r % nchunk);
-        int k = (int)(r / nchunk);
-        int ci = cc * TC_KC + j;
-        float v = (ci < c_in && n < c_out) ? w[((int64_t)k * c_in + ci) * c_out + n] : 0.f;
+        int cc = (int)(r / N);
+        int e = cc * TC_KC + j;
+        float v = (e < E && n < c_out) ? w[(int64_t)e * c_out + n] : 0.f;   // w[k][ci][n] is e-major already
         float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         float lo = v - hi;
-        char* base = (char*)packed + ((int64_t)k * nchunk + cc) * (2 * N * 128);
+        char* base = (char*)packed + (int64_t)cc * (2 * N * 128);
         *(float*)(base + sw128_offset(n, j)) = hi;
         *(float*)(base + N * 128 + sw128_offset(n, j)) = lo;
     }
@@ -223,8 +224,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (n + TC_BM - 1) / TC_BM;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int nchunk = (c_in + TC_KC - 1) / TC_KC;
-    const int T = K * nchunk;                      // stages per tile
+    const int E = K * c_in;                         // flattened (offset, channel) reduction length
+    const int T = (E + TC_KC - 1) / TC_KC;          // stages per tile: 32 reduction elements each
     const int total_stages = my_tiles * T;
 
     if (tid == 0) {
@@ -263,9 +264,12 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         const uint32_t rowbytes = (uint32_t)c_in * 4u;
         const int strideK4 = 4 * K;                 // index-tile stride between rows r and r + 4
         const char* fbase = reinterpret_cast<const char*>(feat_in);
-        // position of the next stage to ISSUE (tile, offset k, chunk cc), advanced by two global stages per step
-        int i_tl = 0, i_k = group / nchunk, i_cc = group - i_k * nchunk;
-        if (i_k >= K) { i_k -= K; i_tl = 1; }      // only when T == 1
+        // position of the next stage to ISSUE: tile i_tl, stage i_j within the tile; this lane's 4-float piece of the
+        // stage covers flattened elements e = 32*i_j + 4*q .. +3  ->  offset i_k = e / c_in, channel i_ch = e % c_in
+        // (c_in % 4 == 0, so a piece never straddles two offsets).  Advanced by two global stages per step.
+        const int step_k = 64 / c_in, step_ch = 64 - step_k * c_in;
+        int i_tl = group / T, i_j = group - i_tl * T;
+        int i_k = (i_j * TC_KC + q * 4) / c_in, i_ch = (i_j * TC_KC + q * 4) - i_k * c_in;
         int cur_tile = -1;                          // tile whose index block this thread currently reads
         int rows_left = 0;
         auto issue = [&](int slot) {
@@ -275,10 +279,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 mbar_wait(&nbr_full[i_tl & 1], (i_tl >> 1) & 1);
                 rows_left = n - (((int)blockIdx.x + i_tl * (int)gridDim.x) * TC_BM + quarter * 32);
             }
-            const int col = i_cc * TC_KC + q * 4;
-            const bool col_ok = col < c_in;
-            const uint32_t colbytes = (uint32_t)col * 4u;
-            const int* nb = nbr_s + (i_tl & 1) * TC_BM * K + (quarter * 32 + sub) * K + i_k;
+            const bool col_ok = i_k < K;            // beyond the end of the reduction axis: zero fill
+            const uint32_t colbytes = (uint32_t)i_ch * 4u;
+            const int* nb = nbr_s + (i_tl & 1) * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0);
             const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -289,10 +292,17 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
             }
             cp_async_commit();
-            // advance two global stages
-            i_cc += 2;
-            if (i_cc >= nchunk) { i_cc -= nchunk; ++i_k; if (i_cc >= nchunk) { i_cc -= nchunk; ++i_k; } }
-            if (i_k >= K) { i_k -= K; ++i_tl; }
+            // advance two global stages (64 reduction elements)
+            i_j += 2;
+            if (i_j >= T) {                         // next tile(s): restart the reduction axis
+                do { i_j -= T; ++i_tl; } while (i_j >= T);
+                i_k = (i_j * TC_KC + q * 4) / c_in;
+                i_ch = (i_j * TC_KC + q * 4) - i_k * c_in;
+            } else {
+                i_k += step_k;
+                i_ch += step_ch;
+                if (i_ch >= c_in) { i_ch -= c_in; ++i_k; }
+            }
         };
         // this warp's stages: gi = group, group + 2, ...; local counter li
         const int my_count = (total_stages - group + 1) / 2;
@@ -483,22 +493,23 @@ using namespace btc;
 extern "C" {
 
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out) {
-    return (K >= 1 && K <= 64 && c_in >= 16 && c_in % 4 == 0 && c_out >= 16 && c_out % 4 == 0 && tc_padded_n(c_out) != 0) ? 1 : 0;
+    return (K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 4 && c_out % 4 == 0 && tc_padded_n(c_out) != 0 &&
+            (int64_t)K * c_in >= 32) ? 1 : 0;
 }
 
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out) {
     if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return BTC_E_UNSUPPORTED;
     int N = tc_padded_n(c_out);
-    int nchunk = (c_in + TC_KC - 1) / TC_KC;
-    return (int64_t)K * nchunk * 2 * N * 128;
+    int nchunk = (K * c_in + TC_KC - 1) / TC_KC;
+    return (int64_t)nchunk * 2 * N * 128;
 }
 
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream) {
     if (!weight || !packed) return badarg("btc_sparse_conv_tc_pack: null argument");
     if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_tc_pack: shape not supported", cudaSuccess);
     int N = tc_padded_n(c_out);
-    int nchunk = (c_in + TC_KC - 1) / TC_KC;
-    int64_t total = (int64_t)K * nchunk * N * TC_KC;
+    int nchunk = (K * c_in + TC_KC - 1) / TC_KC;
+    int64_t total = (int64_t)nchunk * N * TC_KC;
     tc_pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, c_in, c_out, N, (float*)packed);
     BTC_CHECK_LAUNCH("tc_pack_weight");
     return BTC_OK;

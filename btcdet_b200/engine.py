@@ -129,9 +129,7 @@ class BackbonePlan:
             out_feat = torch.empty((out_lvl.cap, conv.out_channels), dtype=torch.float32, device=dev)
             # wide layers run on the tcgen05 tile (weights packed once into the UMMA operand image)
             packed = None
-            if self.algo != 1 and conv.in_channels >= 32 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
-                packed = ops.tc_pack_weight(w)
-            elif self.algo == 2 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
+            if self.algo != 1 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
                 packed = ops.tc_pack_weight(w)
             self.params.append((w, bias, scale, shift, packed))
             self.steps.append(_Step("conv", (cur_feat, nbr, w, bias, scale, shift, bn is not None, out_feat, out_lvl, K,

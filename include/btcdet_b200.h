@@ -229,9 +229,11 @@ int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out,
 
 /*
  * Tensor-core variant (tcgen05.mma kind::tf32 with the 3xTF32 split, accumulator in TMEM):
- * same contract as btc_sparse_conv_fwd, for c_in >= 16, c_in % 4 == 0, 16 <= c_out <= 128,
- * c_out % 4 == 0, K <= 64.  The weights are packed once per layer into the shared-memory image
- * of the K-major, 128-byte-swizzled hi/lo operand tiles (btc_sparse_conv_tc_pack).
+ * same contract as btc_sparse_conv_fwd, for c_in % 4 == 0, c_out % 4 == 0, c_out <= 128, K <= 64,
+ * K * c_in >= 32.  The reduction runs over the flattened (offset, input channel) axis in chunks
+ * of 32, so thin layers (c_in = 4, 16) pack several offsets into one MMA stage.  The weights are
+ * packed once per layer into the shared-memory image of the K-major, 128-byte-swizzled hi/lo
+ * operand tiles (btc_sparse_conv_tc_pack).
  */
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);

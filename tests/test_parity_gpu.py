@@ -196,7 +196,7 @@ def test_sparse_conv_forward_within_tolerance(cuda, oracle, cin, cout, kind):
 
 
 @pytest.mark.parametrize("cin,cout", [(32, 32), (16, 32), (32, 64), (64, 64), (64, 128), (128, 128), (256, 128),
-                                      (48, 40), (20, 16)])
+                                      (48, 40), (20, 16), (4, 16), (16, 16), (8, 4), (6, 16)])
 @pytest.mark.parametrize("kind", ["subm", "conv"])
 def test_tensor_core_conv_within_tolerance(cuda, oracle, cin, cout, kind):
     """tcgen05 3xTF32 tile vs the oracle (and vs the fp32 FFMA tile): same 1e-4 bar."""
