@@ -137,6 +137,7 @@ class BackbonePlan:
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
         self.graph = None
+        self._side_stream = torch.cuda.Stream(device=dev)
         self.launches_per_step = 0
         self.host_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32).pin_memory()
         self.dev_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32, device=dev)
@@ -157,49 +158,76 @@ class BackbonePlan:
         return ws
 
     def _run(self):
-        """Enqueue the whole step on the current stream (no host synchronisation anywhere)."""
+        """Enqueue the whole step (no host synchronisation anywhere).
+
+        Two streams: the rulebook chain (voxelise -> hash -> neighbour tables of every level) depends only on
+        coordinates, the convolution chain only needs rulebook l before layer l.  Running them on separate
+        streams (parallel branches of the captured graph) hides the ~50 small latency-bound indexing kernels
+        behind the tensor-core layers, whose persistent CTAs (448 threads, one per SM) leave room on every SM.
+        """
         lib, B = self.lib, self.batch
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        main = torch.cuda.current_stream()
+        side = self._side_stream
         launches = 0
         lvl0 = self.levels[0]
-        check(lib.btc_voxelize(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
-                               float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
-                               self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
-                               _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
-                               self.vox_ws.numel(), st), "btc_voxelize")
+        side.wait_stream(main)
+        last_rb_event = None
+        with torch.cuda.stream(side):
+            st = ctypes.c_void_p(side.cuda_stream)
+            check(lib.btc_voxelize(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
+                                   float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
+                                   self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
+                                   _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
+                                   self.vox_ws.numel(), st), "btc_voxelize")
+            last_rb_event = torch.cuda.Event()
+            last_rb_event.record(side)
         launches += 9
+        # pass 1: the whole rulebook chain on the side stream, one event per step
+        conv_deps = []
         for s in self.steps:
-            if s.kind == "hash_build":
-                (lvl,) = s.args
-                check(lib.btc_hash_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                         _ptr(lvl.hash_keys), _ptr(lvl.hash_vals), lvl.hash_keys.numel(), st),
-                      "btc_hash_build")
-                launches += 1
-            elif s.kind == "subm_rb":
-                lvl, ksize, dil, nbr = s.args
-                if lvl.hash_keys is not None:
-                    check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                                     int3(ksize), int3(dil), _ptr(lvl.hash_keys), _ptr(lvl.hash_vals),
-                                                     lvl.hash_keys.numel(), _ptr(nbr), st), "btc_rulebook_subm_hash")
-                else:
-                    check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                                int3(ksize), int3(dil), _ptr(lvl.index), lvl.index.numel(),
-                                                _ptr(lvl.perm), _ptr(nbr), st), "btc_rulebook_subm")
-                launches += 1
-            elif s.kind == "conv_rb":
-                lin, lout, ksize, stride, pad, dil, nbr = s.args
-                lout.index.zero_()
-                ws = self._workspace(lib.btc_index_workspace_bytes(lout.index.numel()))
-                check(lib.btc_rulebook_conv(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
-                                            int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
-                                            _ptr(lout.index), lout.index.numel(), _ptr(lout.coords), lout.cap,
-                                            _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
-                      "btc_rulebook_conv")
-                launches += 8
-            else:
-                fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = s.args
-                self.launch_conv(s.args, st)
-                launches += 1
+            if s.kind == "conv":
+                conv_deps.append((s, last_rb_event))   # needs every rulebook step enqueued before it
+                continue
+            with torch.cuda.stream(side):
+                st = ctypes.c_void_p(side.cuda_stream)
+                if s.kind == "hash_build":
+                    (lvl,) = s.args
+                    check(lib.btc_hash_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                             _ptr(lvl.hash_keys), _ptr(lvl.hash_vals), lvl.hash_keys.numel(), st),
+                          "btc_hash_build")
+                    launches += 1
+                elif s.kind == "subm_rb":
+                    lvl, ksize, dil, nbr = s.args
+                    if lvl.hash_keys is not None:
+                        check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                                         int3(ksize), int3(dil), _ptr(lvl.hash_keys), _ptr(lvl.hash_vals),
+                                                         lvl.hash_keys.numel(), _ptr(nbr), st), "btc_rulebook_subm_hash")
+                    else:
+                        check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                                    int3(ksize), int3(dil), _ptr(lvl.index), lvl.index.numel(),
+                                                    _ptr(lvl.perm), _ptr(nbr), st), "btc_rulebook_subm")
+                    launches += 1
+                elif s.kind == "conv_rb":
+                    lin, lout, ksize, stride, pad, dil, nbr = s.args
+                    lout.index.zero_()
+                    ws = self._workspace(lib.btc_index_workspace_bytes(lout.index.numel()))
+                    check(lib.btc_rulebook_conv(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
+                                                int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
+                                                _ptr(lout.index), lout.index.numel(), _ptr(lout.coords), lout.cap,
+                                                _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
+                          "btc_rulebook_conv")
+                    launches += 8
+                last_rb_event = torch.cuda.Event()
+                last_rb_event.record(side)
+        # pass 2: the convolution chain on the main stream, each layer behind its rulebook's event
+        waited = None
+        for s, ev in conv_deps:
+            if ev is not waited:
+                main.wait_event(ev)
+                waited = ev
+            self.launch_conv(s.args, ctypes.c_void_p(main.cuda_stream))
+            launches += 1
+        main.wait_stream(side)
         # gather the live counts of every level into one small tensor (read back lazily by the caller)
         for i, l in enumerate(self.levels):
             self.dev_counts[i:i + 1].copy_(l.n_dev)
