@@ -173,6 +173,29 @@ def run_ours(args, rank, world):
             ms = float(t.item())
         return ms
 
+    def timed_pipelined(run_step, drain_fn, steps, warmup):
+        """Whole-region timing for the pipelined host-facing call: CUDA events bracket `steps` submits plus the
+        drain of the last results (copy stream included through the final D2H event); inputs/outputs exceed L2
+        per step (fresh pinned-host batches, 15 MB of results) so no flush is interleaved."""
+        for i in range(warmup):
+            run_step(i)
+        drain_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run_step(i)
+        drain_fn()
+        torch.cuda.current_stream().wait_stream(plan._pl["copy_stream"])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     # ---- value: inputs resident in HBM ---------------------------------------------------------
     def step_dev(i):
         p, o = dev_batches[i % len(dev_batches)]
@@ -186,20 +209,33 @@ def run_ours(args, rank, world):
     counts = plan.read_counts()
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region -----------------------------------
-    out_host = torch.empty((plan.out_lvl.cap, plan.out_feat.shape[1]), dtype=torch.float32).pin_memory()
-    n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    # The host-facing call is a 2-deep software pipeline (engine.submit / retrieve): while batch i computes, the
+    # exact-size result of batch i-1 leaves over a copy stream.  Every batch's points are copied from pinned host
+    # memory and every batch's result rows (features + coordinates) land in pinned host memory inside the region.
+    plan.enable_pipeline()
     d2h_bytes = [0]
+    outstanding = [0]
+    last_ev = [None]
 
     def step_e2e(i):
         p, o = host_batches[i % len(host_batches)]
-        feat, coords, n_dev = plan.forward(p, o)          # pinned H2D + graph replay
-        n_host.copy_(n_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the user needs the row count to size the result
-        n = int(n_host[0])
-        out_host[:n].copy_(feat[:n], non_blocking=True)   # device -> host read of the step's result
-        d2h_bytes[0] = n * feat.shape[1] * 4 + 4
+        plan.submit(p, o)
+        outstanding[0] += 1
+        if outstanding[0] > 1:
+            feat, coords, ev = plan.retrieve()
+            outstanding[0] -= 1
+            last_ev[0] = ev
+            d2h_bytes[0] = feat.numel() * 4 + coords.numel() * 4 + 4
 
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    def drain():
+        while outstanding[0] > 0:
+            feat, coords, ev = plan.retrieve()
+            outstanding[0] -= 1
+            last_ev[0] = ev
+        if last_ev[0] is not None:
+            last_ev[0].synchronize()
+
+    ms_e2e = timed_pipelined(step_e2e, drain, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     h2d_bytes = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
 
@@ -252,7 +288,8 @@ def run_ours(args, rank, world):
         "config": {"workload": "configs[1]: VoxelBackBone8x forward (voxelize+MeanVFE+rulebooks+12 sparse convs) on "
                                "lidar_like 20k-pt KITTI-range clouds, voxel [0.05,0.05,0.1], C_in=4",
                    "scenes_per_step_per_gpu": B, "points_per_scene": N_POINTS, "parallelism": "dp%d" % world,
-                   "l2": "256 MB buffer written between timed steps (untimed); %d distinct scenes cycled" % N_SCENE_POOL,
+                   "l2": "value: 256 MB buffer written between timed steps (untimed), %d distinct scenes cycled; e2e: pipelined "
+                         "region timed whole, fresh pinned-host batch in and ~15 MB of results out per step" % N_SCENE_POOL,
                    "cuda_graph": not args.no_graph, "conv_algo": args.algo,
                    "level_sites": counts},
         "e2e": {"value": round(scenes_total / (ms_e2e * 1e-3), 2), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,

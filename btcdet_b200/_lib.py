@@ -41,6 +41,7 @@ SIGNATURES = {
     "btc_sparse_conv_bwd_weight": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "btc_maxpool_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _p]),
     "btc_maxpool_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _p]),
+    "btc_copy_rows": (_i, [_p, _p, _i, _p, _i, _p]),
     "btc_to_dense": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
     "btc_from_dense": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
     "btc_occ_targets_workspace_bytes": (_i64, [_i, _p, _p]),

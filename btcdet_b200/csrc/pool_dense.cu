@@ -193,6 +193,15 @@ __global__ void revox_fill_kernel(const float* __restrict__ pt_feat, const int* 
     }
 }
 
+// dst[0 : n*row_words] = src[...] for the live rows only (n read on the device): stages a capacity-sized result
+// buffer into a compact one without a host round-trip.
+__global__ void copy_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_cap,
+                                 const int* __restrict__ n_dev, int row_vec4) {
+    const int64_t work = (int64_t)live_count(n_cap, n_dev) * row_vec4;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x)
+        dst[t] = __ldg(src + t);
+}
+
 }  // namespace btc
 
 using namespace btc;
@@ -219,6 +228,17 @@ int btc_maxpool_bwd(const float* feat_in, const float* feat_out, const float* d_
     maxpool_bwd_kernel<<<grid_for((int64_t)n_out_cap * c, 256), 256, 0, st>>>(feat_in, feat_out, d_out, nbr_out, d_in,
                                                                              n_out_cap, n_out_dev, K, c);
     BTC_CHECK_LAUNCH("maxpool_bwd");
+    return BTC_OK;
+}
+
+int btc_copy_rows(const void* src, void* dst, int n_cap, const int* n_dev, int row_bytes, void* stream) {
+    if (!src || !dst) return badarg("btc_copy_rows: null argument");
+    if (row_bytes <= 0 || row_bytes % 16 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15))
+        return badarg("btc_copy_rows: rows must be 16-byte multiples and 16-byte aligned");
+    if (n_cap <= 0) return BTC_OK;
+    copy_rows_kernel<<<grid_for((int64_t)n_cap * (row_bytes / 16), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)src, (uint4*)dst, n_cap, n_dev, row_bytes / 16);
+    BTC_CHECK_LAUNCH("copy_rows");
     return BTC_OK;
 }
 

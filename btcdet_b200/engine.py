@@ -280,6 +280,68 @@ class BackbonePlan:
         self.step()
         return self.out_feat, self.out_lvl.coords, self.out_lvl.n_dev
 
+    # ---- pipelined host-facing call: H2D, graph replay and D2H of consecutive batches overlap ------------
+    def enable_pipeline(self, result_rows=None, slots=2):
+        """Allocate the staging needed by submit()/retrieve(): per slot a compact device copy of the result rows
+        (so the next replay may overwrite the static output buffer) and a pinned host buffer."""
+        dev, C = self.device, self.out_feat.shape[1]
+        rows = int(result_rows or min(self.out_lvl.cap, self.batch * 16384))
+        self._pl = {
+            "rows": rows, "slots": slots, "k": 0, "pending": [],
+            "stage_feat": [torch.empty((rows, C), dtype=torch.float32, device=dev) for _ in range(slots)],
+            "stage_coords": [torch.empty((rows, 4), dtype=torch.int32, device=dev) for _ in range(slots)],
+            "stage_n": [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(slots)],
+            "host_feat": [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(slots)],
+            "host_coords": [torch.empty((rows, 4), dtype=torch.int32).pin_memory() for _ in range(slots)],
+            "host_n": [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(slots)],
+            "count_ready": [torch.cuda.Event() for _ in range(slots)],
+            "d2h_done": [None] * slots,
+            "copy_stream": torch.cuda.Stream(device=dev),
+        }
+        return self
+
+    def submit(self, points, scene_offsets):
+        """Enqueue one batch (pinned host or device tensors): H2D, the graph, staging of the live result rows and
+        the tiny count read-back.  Returns immediately; call retrieve() for results in submission order."""
+        pl = self._pl
+        slot = pl["k"] % pl["slots"]
+        main = torch.cuda.current_stream()
+        if pl["d2h_done"][slot] is not None:
+            main.wait_event(pl["d2h_done"][slot])      # the previous occupant of this slot has left the device
+        self.load_points(points, scene_offsets)
+        self.step()
+        st = ctypes.c_void_p(main.cuda_stream)
+        C = self.out_feat.shape[1]
+        check(self.lib.btc_copy_rows(_ptr(self.out_feat), _ptr(pl["stage_feat"][slot]), min(self.out_lvl.cap, pl["rows"]),
+                                     _ptr(self.out_lvl.n_dev), C * 4, st), "btc_copy_rows")
+        check(self.lib.btc_copy_rows(_ptr(self.out_lvl.coords), _ptr(pl["stage_coords"][slot]),
+                                     min(self.out_lvl.cap, pl["rows"]), _ptr(self.out_lvl.n_dev), 16, st), "btc_copy_rows")
+        pl["stage_n"][slot].copy_(self.out_lvl.n_dev, non_blocking=True)
+        pl["host_n"][slot].copy_(pl["stage_n"][slot], non_blocking=True)
+        pl["count_ready"][slot].record(main)
+        pl["pending"].append(slot)
+        pl["k"] += 1
+
+    def retrieve(self):
+        """Result of the oldest submitted batch: (features [n,C], coords [n,4]) as views of pinned host buffers,
+        valid until two further submits.  Only this call waits, and only for that batch."""
+        pl = self._pl
+        slot = pl["pending"].pop(0)
+        pl["count_ready"][slot].synchronize()          # the row count of that batch (the GPU is already busy with the next)
+        n = int(pl["host_n"][slot][0])
+        if n > pl["rows"]:
+            raise _lib.BtcError("result of %d rows exceeds the pipeline staging capacity %d" % (n, pl["rows"]))
+        cs = pl["copy_stream"]
+        cs.wait_event(pl["count_ready"][slot])
+        with torch.cuda.stream(cs):
+            pl["host_feat"][slot][:n].copy_(pl["stage_feat"][slot][:n], non_blocking=True)
+            pl["host_coords"][slot][:n].copy_(pl["stage_coords"][slot][:n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        pl["d2h_done"][slot] = ev
+        pl.setdefault("last_d2h", []).append(ev)
+        return pl["host_feat"][slot][:n], pl["host_coords"][slot][:n], ev
+
     def read_counts(self):
         """One small D2H copy of every level's live count; raises if a capacity overflowed."""
         self.host_counts[:len(self.levels)].copy_(self.dev_counts[:len(self.levels)], non_blocking=False)

@@ -284,6 +284,9 @@ int btc_maxpool_bwd(const float* feat_in, const float* feat_out, const float* d_
 /* ------------------------------------------------------------------------- */
 int btc_to_dense(const float* feat, const int* coords, int n_cap, const int* n_dev,
                  int c, int batch, const int* shape, float* out, void* stream);
+/* Compact copy of the live rows (count read on the device) of a capacity-sized row buffer;
+ * row_bytes % 16 == 0.  Used to stage results for an asynchronous device->host copy. */
+int btc_copy_rows(const void* src, void* dst, int n_cap, const int* n_dev, int row_bytes, void* stream);
 /* Backward of dense(): d_feat[i][ch] = d_out[b, ch, z, y, x]. */
 int btc_from_dense(const float* d_out, const int* coords, int n_cap, const int* n_dev,
                    int c, int batch, const int* shape, float* d_feat, void* stream);

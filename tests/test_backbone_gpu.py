@@ -167,3 +167,35 @@ def test_reference_occ_backbone_topology_matches_oracle(cuda, oracle):
     assert list(got["encoded"].spatial_shape) == [9, 157, 209] and got["encoded"].indices.shape[0] > 5 * coords.shape[0]
     np.testing.assert_array_equal(dense_cls.cpu().numpy(), oracle.dense(got["cls"].features.cpu().numpy(),
                                                                          ref["cls"].indices, [9, 157, 209], batch))
+
+
+def test_pipelined_submit_retrieve_matches_forward(cuda, oracle):
+    """engine.submit/retrieve (2-deep pipeline, results staged compactly and copied out on a side stream) returns
+    exactly what the synchronous forward computes, in submission order."""
+    from btcdet_b200 import backbones, engine, synthetic as S
+    torch.manual_seed(0)
+    model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+    plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, 2, 2 * 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                               max_points=5, max_voxels=16000).capture().enable_pipeline()
+    batches = []
+    for i in range(4):
+        pts, offs = S.batch_points([S.lidar_like(20000, seed=500 + 2 * i), S.lidar_like(15000, seed=501 + 2 * i)])
+        batches.append((torch.from_numpy(pts).pin_memory(), torch.from_numpy(offs).pin_memory()))
+    want = []
+    for p, o in batches:
+        feat, coords, n_dev = plan.forward(p, o)
+        n = int(n_dev.item())
+        want.append((feat[:n].cpu().clone(), coords[:n].cpu().clone()))
+    got = []
+    for i, (p, o) in enumerate(batches):
+        plan.submit(p, o)
+        if i >= 1:
+            f, c, ev = plan.retrieve()
+            ev.synchronize()
+            got.append((f.clone(), c.clone()))
+    f, c, ev = plan.retrieve()
+    ev.synchronize()
+    got.append((f.clone(), c.clone()))
+    assert len(got) == len(want)
+    for (gf, gc), (wf, wc) in zip(got, want):
+        assert torch.equal(gc, wc) and torch.equal(gf, wf)
