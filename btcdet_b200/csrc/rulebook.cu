@@ -43,72 +43,88 @@ __device__ __forceinline__ bool out_coord(int in, int kk, int s, int p, int d, i
 }
 
 // ---- submanifold ----------------------------------------------------------------
-// One thread per (site, tap); the 27 probes of a site hit 9 index words that sit in L1/L2.
-__global__ void subm_table_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
-                                  ConvGeom g, const uint2* __restrict__ index, const int* __restrict__ perm,
-                                  int* __restrict__ nbr_out) {
-    const int n = live_count(n_cap, n_dev);
-    const int K = g.K;
-    const int64_t work = (int64_t)n * K;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
-        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
-        int4 c = __ldg(coords + i);
+// Block = 32 tap lanes x 8 sites (the 27 probes of a site hit ~9 index words that sit in L1/L2); the tap ->
+// (kz,ky,kx) decomposition comes from a per-block table, so there is no integer division on the hot path.
+// HASH = probe a coordinate hash (unsorted rows on huge grids: the KITTI det level-1 grid is 92 M cells per scene
+// for ~14 k sites, a 2N-slot hash is ~1 MB) instead of the rank bitmap.
+constexpr int kSubmSites = 8;
+
+__device__ __forceinline__ void fill_tap_table(const ConvGeom& g, int* s_tap /*[K]*/) {
+    for (int k = threadIdx.y * 32 + threadIdx.x; k < g.K; k += 32 * kSubmSites) {
         int kz, ky, kx;
         offset_of(k, g.k, kz, ky, kx);
-        int z = c.y + (kz - g.k[0] / 2) * g.dil[0];
-        int y = c.z + (ky - g.k[1] / 2) * g.dil[1];
-        int x = c.w + (kx - g.k[2] / 2) * g.dil[2];
-        int j = -1;
-        if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w) {
-            int r = index_lookup(index, flat_key(c.x, z, y, x, g.in));
-            if (r >= 0) j = perm ? __ldg(perm + r) : r;
-        }
-        nbr_out[t] = j;
+        s_tap[k] = ((kz - g.k[0] / 2) * g.dil[0] + 64) | (((ky - g.k[1] / 2) * g.dil[1] + 64) << 8) |
+                   (((kx - g.k[2] / 2) * g.dil[2] + 64) << 16);
     }
+    __syncthreads();
 }
 
-// Same, probing a coordinate hash instead of the rank bitmap (unsorted inputs on huge grids: the
-// KITTI det level-1 grid is 92 M cells per scene for ~14 k sites — a 2N-slot hash is ~1 MB).
-__global__ void subm_table_hash_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
-                                       ConvGeom g, const long long* __restrict__ keys, const int* __restrict__ vals,
-                                       uint32_t hmask, int* __restrict__ nbr_out) {
+template <bool HASH>
+__global__ void __launch_bounds__(32 * kSubmSites)
+subm_table_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
+                  const uint2* __restrict__ index, const int* __restrict__ perm, const long long* __restrict__ keys,
+                  const int* __restrict__ vals, uint32_t hmask, int* __restrict__ nbr_out) {
+    __shared__ int s_tap[256];
+    fill_tap_table(g, s_tap);
     const int n = live_count(n_cap, n_dev);
     const int K = g.K;
-    const int64_t work = (int64_t)n * K;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
-        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
-        int4 c = __ldg(coords + i);
-        int kz, ky, kx;
-        offset_of(k, g.k, kz, ky, kx);
-        int z = c.y + (kz - g.k[0] / 2) * g.dil[0];
-        int y = c.z + (ky - g.k[1] / 2) * g.dil[1];
-        int x = c.w + (kx - g.k[2] / 2) * g.dil[2];
-        int j = -1;
-        if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w)
-            j = (k == K / 2) ? i : hash_lookup(keys, vals, hmask, flat_key(c.x, z, y, x, g.in));
-        nbr_out[t] = j;
+    for (int i = blockIdx.x * kSubmSites + threadIdx.y; i < n; i += gridDim.x * kSubmSites) {
+        const int4 c = __ldg(coords + i);
+        for (int k = threadIdx.x; k < K; k += 32) {
+            const int tap = s_tap[k];
+            const int z = c.y + (tap & 255) - 64, y = c.z + ((tap >> 8) & 255) - 64, x = c.w + ((tap >> 16) & 255) - 64;
+            int j = -1;
+            if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w) {
+                const int64_t key = flat_key(c.x, z, y, x, g.in);
+                if (HASH) {
+                    j = (k == K / 2) ? i : hash_lookup(keys, vals, hmask, key);
+                } else {
+                    int r = index_lookup(index, key);
+                    if (r >= 0) j = perm ? __ldg(perm + r) : r;
+                }
+            }
+            nbr_out[(int64_t)i * K + k] = j;
+        }
     }
 }
 
 // ---- strided / transposed -----------------------------------------------------------
+// Valid taps of one axis for input coordinate `in`: regular conv -> those kk with (in + p - kk*d) divisible by s
+// (k=3, s=2: one or two of the three), transposed -> every kk landing inside the output.  At most 8 per axis.
+constexpr int kMaxAxisTaps = 8;
+__device__ __forceinline__ int axis_taps(int in, int k, int s, int p, int d, int out_dim, int transposed,
+                                         int (&kk_l)[kMaxAxisTaps], int (&o_l)[kMaxAxisTaps]) {
+    int cnt = 0;
+    for (int kk = 0; kk < k && cnt < kMaxAxisTaps; ++kk) {
+        int o;
+        if (out_coord(in, kk, s, p, d, out_dim, transposed, o)) {
+            kk_l[cnt] = kk;
+            o_l[cnt] = o;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
+// One thread per input site; it enumerates only its valid (kz,ky,kx) taps (3.4 of 27 on average for k3 s2).
 __global__ void conv_mark_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
                                  unsigned* __restrict__ out_index_words) {
     const int n = live_count(n_cap, n_dev);
-    const int K = g.K;
-    const int64_t work = (int64_t)n * K;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
-        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
-        int4 c = __ldg(coords + i);
-        int kz, ky, kx, oz, oy, ox;
-        offset_of(k, g.k, kz, ky, kx);
-        if (!out_coord(c.y, kz, g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, oz)) continue;
-        if (!out_coord(c.z, ky, g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, oy)) continue;
-        if (!out_coord(c.w, kx, g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, ox)) continue;
-        int64_t key = flat_key(c.x, oz, oy, ox, g.out);
-        unsigned bit = 1u << (unsigned)(key & 31);
-        unsigned* wptr = out_index_words + 2 * (key >> 5);
-        // most taps of neighbouring inputs hit an already-set bit: test before the atomic
-        if (!(*(volatile unsigned*)wptr & bit)) atomicOr(wptr, bit);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        int kz_l[kMaxAxisTaps], oz_l[kMaxAxisTaps], ky_l[kMaxAxisTaps], oy_l[kMaxAxisTaps], kx_l[kMaxAxisTaps], ox_l[kMaxAxisTaps];
+        const int nz = axis_taps(c.y, g.k[0], g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, kz_l, oz_l);
+        const int ny = axis_taps(c.z, g.k[1], g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, ky_l, oy_l);
+        const int nx = axis_taps(c.w, g.k[2], g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, kx_l, ox_l);
+        for (int a = 0; a < nz; ++a)
+            for (int b = 0; b < ny; ++b)
+                for (int d = 0; d < nx; ++d) {
+                    const int64_t key = flat_key(c.x, oz_l[a], oy_l[b], ox_l[d], g.out);
+                    const unsigned bit = 1u << (unsigned)(key & 31);
+                    unsigned* wptr = out_index_words + 2 * (key >> 5);
+                    // most taps of neighbouring inputs hit an already-set bit: test before the atomic
+                    if (!(*(volatile unsigned*)wptr & bit)) atomicOr(wptr, bit);
+                }
     }
 }
 
@@ -131,6 +147,8 @@ __global__ void conv_emit_kernel(const uint2* __restrict__ out_index, int64_t n_
                 int z = (int)(t % out.d);
                 int b = (int)(t / out.d);
                 out_coords[row] = make_int4(b, z, y, x);
+                if (nbr_out)   // initialise this output row of the neighbour table (conv_tables fills the taps)
+                    for (int k = 0; k < K; ++k) nbr_out[(int64_t)row * K + k] = -1;
             }
             ++row;
         }
@@ -148,21 +166,23 @@ __global__ void conv_tables_kernel(const int4* __restrict__ coords, int n_cap, c
                                    int* __restrict__ nbr_in) {
     const int n = live_count(n_cap, n_dev);
     const int K = g.K;
-    const int64_t work = (int64_t)n * K;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
-        int i = (int)(t / K), k = (int)(t - (int64_t)i * K);
-        int4 c = __ldg(coords + i);
-        int kz, ky, kx, oz, oy, ox;
-        offset_of(k, g.k, kz, ky, kx);
-        int o = -1;
-        if (out_coord(c.y, kz, g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, oz) &&
-            out_coord(c.z, ky, g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, oy) &&
-            out_coord(c.w, kx, g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, ox)) {
-            o = index_lookup(out_index, flat_key(c.x, oz, oy, ox, g.out));
-            if (o >= out_cap) o = -1;
-        }
-        if (nbr_in) nbr_in[t] = o;
-        if (nbr_out && o >= 0) nbr_out[(int64_t)o * K + k] = i;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        if (nbr_in)
+            for (int k = 0; k < K; ++k) nbr_in[(int64_t)i * K + k] = -1;
+        int kz_l[kMaxAxisTaps], oz_l[kMaxAxisTaps], ky_l[kMaxAxisTaps], oy_l[kMaxAxisTaps], kx_l[kMaxAxisTaps], ox_l[kMaxAxisTaps];
+        const int nz = axis_taps(c.y, g.k[0], g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, kz_l, oz_l);
+        const int ny = axis_taps(c.z, g.k[1], g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, ky_l, oy_l);
+        const int nx = axis_taps(c.w, g.k[2], g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, kx_l, ox_l);
+        for (int a = 0; a < nz; ++a)
+            for (int b = 0; b < ny; ++b)
+                for (int d = 0; d < nx; ++d) {
+                    const int k = (kz_l[a] * g.k[1] + ky_l[b]) * g.k[2] + kx_l[d];
+                    int o = index_lookup(out_index, flat_key(c.x, oz_l[a], oy_l[b], ox_l[d], g.out));
+                    if (o >= out_cap) o = -1;
+                    if (nbr_in) nbr_in[(int64_t)i * K + k] = o;
+                    if (nbr_out && o >= 0) nbr_out[(int64_t)o * K + k] = i;
+                }
     }
 }
 
@@ -273,9 +293,11 @@ int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch,
     int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
     if (make_geom(g, batch, shape, shape, ksize, one, zero, dilation, 0)) return badarg("btc_rulebook_subm: bad geometry");
     if (n_cap <= 0) return BTC_OK;
-    int64_t work = (int64_t)n_cap * g.K;
-    subm_table_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, g,
-                                                                            (const uint2*)index, perm, nbr_out);
+    if (g.K > 256 || g.k[0] * g.dil[0] > 120 || g.k[1] * g.dil[1] > 120 || g.k[2] * g.dil[2] > 120)
+        return badarg("btc_rulebook_subm: kernel too large");
+    dim3 blk(32, kSubmSites);
+    subm_table_kernel<false><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, (cudaStream_t)stream>>>(
+        (const int4*)coords, n_cap, n_dev, g, (const uint2*)index, perm, nullptr, nullptr, 0u, nbr_out);
     BTC_CHECK_LAUNCH("subm_table");
     return BTC_OK;
 }
@@ -290,9 +312,11 @@ int btc_rulebook_subm_hash(const int* coords, int n_cap, const int* n_dev, int b
     int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
     if (make_geom(g, batch, shape, shape, ksize, one, zero, dilation, 0)) return badarg("btc_rulebook_subm_hash: bad geometry");
     if (n_cap <= 0) return BTC_OK;
-    int64_t work = (int64_t)n_cap * g.K;
-    subm_table_hash_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const int4*)coords, n_cap, n_dev, g, (const long long*)keys, vals, (uint32_t)(n_slots - 1), nbr_out);
+    if (g.K > 256 || g.k[0] * g.dil[0] > 120 || g.k[1] * g.dil[1] > 120 || g.k[2] * g.dil[2] > 120)
+        return badarg("btc_rulebook_subm_hash: kernel too large");
+    dim3 blk(32, kSubmSites);
+    subm_table_kernel<true><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, (cudaStream_t)stream>>>(
+        (const int4*)coords, n_cap, n_dev, g, nullptr, nullptr, (const long long*)keys, vals, (uint32_t)(n_slots - 1), nbr_out);
     BTC_CHECK_LAUNCH("subm_table_hash");
     return BTC_OK;
 }
@@ -312,9 +336,11 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, i
         return badarg("btc_rulebook_conv: bad geometry");
     cudaStream_t st = (cudaStream_t)stream;
     const int T = 256;
-    int64_t work = (int64_t)(n_in_cap > 0 ? n_in_cap : 1) * g.K;
+    if (g.k[0] > kMaxAxisTaps || g.k[1] > kMaxAxisTaps || g.k[2] > kMaxAxisTaps)
+        return badarg("btc_rulebook_conv: kernel extent above 8 per axis");
+    int64_t work = (int64_t)(n_in_cap > 0 ? n_in_cap : 1);   // one thread per input site
     if (n_in_cap > 0) {
-        conv_mark_kernel<<<grid_for(work, T), T, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+        conv_mark_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
                                                           (unsigned*)out_index);
         BTC_CHECK_LAUNCH("conv_mark");
     }
@@ -323,10 +349,8 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, i
     if (out_cap > 0 && out_coords)
         conv_emit_kernel<<<grid_for(out_entries, T), T, 0, st>>>((const uint2*)out_index, out_entries, g.out, out_cap, g.K,
                                                                 (int4*)out_coords, nbr_out);
-    if (nbr_out && out_cap > 0)
-        fill_table_kernel<<<grid_for((int64_t)out_cap * g.K, T), T, 0, st>>>(nbr_out, out_cap, n_out, g.K);
     if (n_in_cap > 0 && (nbr_out || nbr_in))
-        conv_tables_kernel<<<grid_for(work, T), T, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+        conv_tables_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
                                                             (const uint2*)out_index, out_cap, nbr_out, nbr_in);
     BTC_CHECK_LAUNCH("conv rulebook");
     return BTC_OK;
