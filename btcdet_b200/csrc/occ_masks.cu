@@ -242,6 +242,113 @@ static int parse_geom(OccGeom& g, int batch, const float* gf, const int* gi) {
     return BTC_OK;
 }
 
+// ---- occupancy-point injection: threshold -> ordered compaction -> pseudo points -----------
+// Replaces AddOccTemplate.filter_occ_points (nonzero + per-scene python loop, add_occ_template.py:94-128, without
+// the top-k branch), occ_coords2absxyz (:131-146), trans_voxel_grid (:78-88) and assemble_occ_points (:149-165).
+struct InjectGeom {
+    float ovs[3], oorg[3];     // occ grid voxel size / origin (rho, phi, z)
+    float dvs[3], dmin[3];     // det grid voxel size / range min (x, y, z)
+    int g[3];                  // occ grid nx, ny, nz
+    int dg[3];                 // det grid nx, ny, nz
+    float thresh, inten;
+    int batch;
+};
+
+__global__ void occ_flag_kernel(const float* __restrict__ probs, int64_t cells, float thresh, int* __restrict__ flags) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < cells; t += (int64_t)gridDim.x * blockDim.x)
+        flags[t] = __ldg(probs + t) > thresh ? 1 : 0;
+}
+
+__global__ void occ_emit_kernel(const float* __restrict__ probs, const float* __restrict__ residuals,
+                                const int* __restrict__ flags, const int* __restrict__ rank,
+                                const int* __restrict__ total, const float* __restrict__ rot_z, InjectGeom g, int cap,
+                                int4* __restrict__ occ_coords, float* __restrict__ occ_probs, float* __restrict__ occ_xyz,
+                                int4* __restrict__ det_coords, float* __restrict__ occ_points, int* __restrict__ counts) {
+    const int nx = g.g[0], ny = g.g[1], nz = g.g[2];
+    const int64_t per_scene = (int64_t)nz * ny * nx;
+    const int64_t cells = per_scene * g.batch;
+    if (blockIdx.x == 0 && threadIdx.x <= g.batch) {      // per-scene counts + total
+        int b = threadIdx.x;
+        int r1 = b < g.batch ? __ldg(rank + (int64_t)b * per_scene) : 0;
+        if (b == g.batch) counts[b] = *total;
+        else counts[b] = ((b + 1 < g.batch) ? __ldg(rank + (int64_t)(b + 1) * per_scene) : *total) - r1;
+    }
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < cells; t += (int64_t)gridDim.x * blockDim.x) {
+        if (!flags[t]) continue;
+        const int row = rank[t];
+        if (row >= cap) continue;
+        const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)((t / ((int64_t)nx * ny)) % nz);
+        const int b = (int)(t / per_scene);
+        const float p = __ldg(probs + t);
+        // voxel centre in cylinder coordinates: origin + (idx + 0.5) * vs   (python-float scalars -> fp32)
+        float rho = __fadd_rn(g.oorg[0], __fmul_rn(__fadd_rn((float)x, 0.5f), g.ovs[0]));
+        float phi = __fadd_rn(g.oorg[1], __fmul_rn(__fadd_rn((float)y, 0.5f), g.ovs[1]));
+        float zc = __fadd_rn(g.oorg[2], __fmul_rn(__fadd_rn((float)z, 0.5f), g.ovs[2]));
+        if (rot_z) phi = __fsub_rn(phi, __ldg(rot_z + b));
+        const float u = deg2rad_like_torch(phi);
+        float px = __fmul_rn(rho, cosf(u));
+        float py = __fmul_rn(-rho, sinf(u));
+        float pz = zc;
+        if (residuals) {
+            const float* r = residuals + (int64_t)b * 3 * per_scene + (t - (int64_t)b * per_scene);
+            px = __fadd_rn(px, __ldg(r));
+            py = __fadd_rn(py, __ldg(r + per_scene));
+            pz = __fadd_rn(pz, __ldg(r + 2 * per_scene));
+        }
+        // trans_voxel_grid: floor((p - min) / vs) clamped into the det grid
+        const float q[3] = {px, py, pz};
+        int dc[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float f = floorf(__fdiv_rn(__fsub_rn(q[a], g.dmin[a]), g.dvs[a]));
+            f = fminf(fmaxf(f, 0.0f), (float)(g.dg[a] - 1));
+            dc[a] = (int)f;
+        }
+        occ_coords[row] = make_int4(b, z, y, x);
+        occ_probs[row] = p;
+        occ_xyz[row * 3 + 0] = px; occ_xyz[row * 3 + 1] = py; occ_xyz[row * 3 + 2] = pz;
+        det_coords[row] = make_int4(b, dc[2], dc[1], dc[0]);
+        float* o = occ_points + (int64_t)row * 6;
+        o[0] = px; o[1] = py; o[2] = pz; o[3] = g.inten; o[4] = p; o[5] = 1.0f;
+    }
+}
+
+// OccVFE (occ_vfe.py:24-55): slots with code < 0.05 are raw points, the others injected occupancy points.
+__global__ void occ_vfe_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points, int m_cap,
+                               const int* __restrict__ m_dev, int P, int C, int n_raw, float* __restrict__ feats,
+                               float* __restrict__ occ_feats) {
+    const int m = live_count(m_cap, m_dev);
+    const int n_code = C - n_raw;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < m; v += gridDim.x * blockDim.x) {
+        const float* vox = voxels + (int64_t)v * P * C;
+        const int np = __ldg(num_points + v);
+        int raw_n = 0, occ_n = 0;
+        for (int p = 0; p < P && p < np; ++p) {
+            if (__ldg(vox + p * C + C - 1) < 0.05f) ++raw_n; else ++occ_n;
+        }
+        const bool occ_only = occ_n > 0 && raw_n == 0;
+        const float raw_d = (float)max(raw_n, 1), occ_d = (float)max(occ_n, 1);
+        for (int c = 0; c < n_raw; ++c) {
+            float sr = 0.f, so = 0.f;
+            for (int p = 0; p < P; ++p) {
+                const bool valid = p < np;
+                const float val = __ldg(vox + p * C + c);
+                const bool is_raw = __ldg(vox + p * C + C - 1) < 0.05f;
+                sr = __fadd_rn(sr, (valid && is_raw) ? val : 0.0f);
+                so = __fadd_rn(so, (valid && !is_raw) ? val : 0.0f);
+            }
+            const float fr = __fdiv_rn(sr, raw_d), fo = __fdiv_rn(so, occ_d);
+            feats[(int64_t)v * C + c] = __fadd_rn(fr, occ_only ? fo : 0.0f);
+        }
+        for (int c = 0; c < n_code; ++c) {   // max over ALL slots, zero padding included (as the reference)
+            float mx = __ldg(vox + n_raw + c);
+            for (int p = 1; p < P; ++p) mx = fmaxf(mx, __ldg(vox + p * C + n_raw + c));
+            feats[(int64_t)v * C + n_raw + c] = mx;
+            if (occ_feats) occ_feats[(int64_t)v * n_code + c] = mx;
+        }
+    }
+}
+
 }  // namespace btc
 
 using namespace btc;
@@ -292,6 +399,54 @@ int btc_occ_targets(const float* voxels, int P, int C, const int* voxel_coords, 
     occ_filter_kernel<<<grid_for(cells, T), T, 0, st>>>(raw, vcc_mask, floor_z, g, occ_mask, general_mask);
     if (sphere_map_out) BTC_CUDA(cudaMemcpyAsync(sphere_map_out, sphere, sph, cudaMemcpyDeviceToDevice, st), "occ copy");
     BTC_CHECK_LAUNCH("occ_targets");
+    return BTC_OK;
+}
+
+int64_t btc_occ_select_workspace_bytes(int batch, const int* grid) {
+    if (!grid || batch < 1) return BTC_E_BADARG;
+    int64_t cells = (int64_t)batch * grid[0] * grid[1] * grid[2];
+    return align_up(cells * 4, 256) * 2 + align_up((int64_t)(scan_num_blocks(cells) + 2) * 4, 256) + 256;
+}
+
+int btc_occ_select(const float* probs, const float* residuals, int batch, const int* grid, float thresh,
+                   const float* rot_z, const float* geom_f, const int* det_grid, float inten, int cap, int* occ_coords,
+                   float* occ_probs, float* occ_xyz, int* det_coords, float* occ_points, int* counts, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
+    if (!probs || !grid || !geom_f || !det_grid || !counts || !workspace) return badarg("btc_occ_select: null argument");
+    if (cap > 0 && (!occ_coords || !occ_probs || !occ_xyz || !det_coords || !occ_points)) return badarg("btc_occ_select: null outputs");
+    if (workspace_bytes < btc_occ_select_workspace_bytes(batch, grid)) return badarg("btc_occ_select: workspace too small");
+    InjectGeom g;
+    for (int a = 0; a < 3; ++a) {
+        g.ovs[a] = geom_f[a]; g.oorg[a] = geom_f[3 + a]; g.dvs[a] = geom_f[6 + a]; g.dmin[a] = geom_f[9 + a];
+        g.g[a] = grid[a]; g.dg[a] = det_grid[a];
+    }
+    g.thresh = thresh; g.inten = inten; g.batch = batch;
+    const int64_t cells = (int64_t)batch * grid[0] * grid[1] * grid[2];
+    if (cells > 0x7fffffff) return badarg("btc_occ_select: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    int* flags = (int*)ws;
+    int* rank = (int*)(ws + align_up(cells * 4, 256));
+    int* block_sums = (int*)(ws + 2 * align_up(cells * 4, 256));
+    int* total = (int*)(ws + 2 * align_up(cells * 4, 256) + align_up((int64_t)(scan_num_blocks(cells) + 2) * 4, 256));
+    occ_flag_kernel<<<grid_for(cells, 256), 256, 0, st>>>(probs, cells, thresh, flags);
+    int rc = launch_flag_scan(flags, rank, (int)cells, block_sums, total, st);
+    if (rc) return rc;
+    occ_emit_kernel<<<grid_for(cells, 256), 256, 0, st>>>(probs, residuals, flags, rank, total, rot_z, g, cap, (int4*)occ_coords,
+                                                         occ_probs, occ_xyz, (int4*)det_coords, occ_points, counts);
+    BTC_CHECK_LAUNCH("occ_select");
+    return BTC_OK;
+}
+
+int btc_occ_vfe(const float* voxels, const int* num_points, int m_cap, const int* m_dev, int P, int C, int num_raw,
+                float* feats, float* occ_feats, void* stream) {
+    if (!feats) return badarg("btc_occ_vfe: null argument");
+    if (P < 1 || C < 2 || num_raw < 1 || num_raw >= C) return badarg("btc_occ_vfe: bad layout");
+    if (m_cap <= 0) return BTC_OK;
+    if (!voxels || !num_points) return badarg("btc_occ_vfe: null inputs");
+    occ_vfe_kernel<<<grid_for(m_cap, 128), 128, 0, (cudaStream_t)stream>>>(voxels, num_points, m_cap, m_dev, P, C, num_raw, feats,
+                                                                          occ_feats);
+    BTC_CHECK_LAUNCH("occ_vfe");
     return BTC_OK;
 }
 

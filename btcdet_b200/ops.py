@@ -519,3 +519,95 @@ def occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom
     if want_sphere:
         out["sphere_map"] = sphere
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# occupancy-point injection (PassOccVox) and OccVFE
+# ------------------------------------------------------------------------------------------
+def occ_select(probs, residuals, thresh, max_points, occ_voxel_size, occ_origin, det_voxel_size, det_range, det_grid,
+               rot_z=None, inten=0.0):
+    """filter_occ_points + occ_coords2absxyz + trans_voxel_grid + assemble_occ_points on the GPU
+    (btcdet/models/occ_pnt/add_occ_template.py:78-165).  One host read (the counts) for exact shapes; the rare
+    top-k branch (more than `max_points` cells above threshold in a scene) is applied with torch.topk on the
+    compacted probabilities.  Returns a dict of tensors or None when no cell passes."""
+    _require_cuda(probs)
+    lib = _lib.load()
+    dev = probs.device
+    probs = probs.to(torch.float32).contiguous()
+    res = None if residuals is None else residuals.to(torch.float32).contiguous()
+    B, nz, ny, nx = probs.shape
+    grid = int3([nx, ny, nz])
+    n_above = B * nz * ny * nx
+    cap = min(n_above, max(1024, B * max(int(max_points), 1) * 4))
+    ws_bytes = int(lib.btc_occ_select_workspace_bytes(B, grid))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    gf = float_array(list(occ_voxel_size) + list(occ_origin) + list(det_voxel_size) + list(det_range[:3]))
+    rz = None if rot_z is None else rot_z.to(torch.float32).contiguous()
+    while True:
+        out = {"occ_coords": torch.empty((cap, 4), dtype=torch.int32, device=dev),
+               "occ_probs": torch.empty(cap, dtype=torch.float32, device=dev),
+               "occ_xyz": torch.empty((cap, 3), dtype=torch.float32, device=dev),
+               "det_coords": torch.empty((cap, 4), dtype=torch.int32, device=dev),
+               "occ_points": torch.empty((cap, 6), dtype=torch.float32, device=dev)}
+        counts = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        check(lib.btc_occ_select(_ptr(probs), _ptr(res), B, grid, ctypes.c_float(thresh), _ptr(rz), gf, int3(det_grid),
+                                 ctypes.c_float(inten), cap, _ptr(out["occ_coords"]), _ptr(out["occ_probs"]),
+                                 _ptr(out["occ_xyz"]), _ptr(out["det_coords"]), _ptr(out["occ_points"]), _ptr(counts),
+                                 _ptr(ws), ws_bytes, _stream()), "btc_occ_select")
+        c = counts.tolist()
+        if c[B] <= cap:
+            break
+        cap = c[B]                      # capacity guess too small: rerun once with the exact size
+    total = c[B]
+    if total == 0:
+        return None
+    out = {k: v[:total] for k, v in out.items()}
+    if max(c[:B]) > max_points:         # top-k branch of the reference (order unspecified there: sorted=False)
+        keep, start = [], 0
+        for b in range(B):
+            n_b = c[b]
+            if n_b > max_points:
+                _, top = torch.topk(out["occ_probs"][start:start + n_b], int(max_points), largest=True, sorted=False)
+                keep.append(top + start)
+            elif n_b > 0:
+                keep.append(torch.arange(start, start + n_b, device=dev))
+            start += n_b
+        keep = torch.cat(keep)
+        out = {k: v[keep] for k, v in out.items()}
+    out["counts"] = c
+    return out
+
+
+def occ_vfe(voxels, voxel_num_points, num_raw_features=4):
+    """OccVFE.forward (btcdet/models/backbones_3d/vfe/occ_vfe.py:24-55): returns (voxel_features [M,C], occ_voxel_features)."""
+    _require_cuda(voxels, voxel_num_points)
+    lib = _lib.load()
+    voxels = voxels.to(torch.float32).contiguous()
+    nump = voxel_num_points.to(torch.int32).contiguous()
+    m, P, C = voxels.shape
+    feats = torch.empty((m, C), dtype=torch.float32, device=voxels.device)
+    occ = torch.empty((m, C - num_raw_features), dtype=torch.float32, device=voxels.device)
+    check(lib.btc_occ_vfe(_ptr(voxels), _ptr(nump), m, None, P, C, int(num_raw_features), _ptr(feats), _ptr(occ), _stream()),
+          "btc_occ_vfe")
+    return feats, occ
+
+
+def pass_occ_vox(probs, residuals, det_voxels, det_voxel_num_points, det_voxel_coords, batch_size, thresh, max_points,
+                 occ_voxel_size, occ_origin, det_voxel_size, det_range, det_grid, rot_z=None, inten=0.0):
+    """PassOccVox.forward (btcdet/models/occ_pnt/pass_occ_vox.py:10-59) for the cylinder / REG configuration:
+    select occupancy cells, build pseudo points, append the raw det-voxel points (two zero code channels) and
+    re-voxelise everything sorted on the det grid.  Returns (voxels [M',Pmax,6], num_points, coords, selection)."""
+    sel = occ_select(probs, residuals, thresh, max_points, occ_voxel_size, occ_origin, det_voxel_size, det_range, det_grid,
+                     rot_z=rot_z, inten=inten)
+    M, P, C = det_voxels.shape
+    mask = torch.arange(P, device=det_voxels.device).view(1, -1) < det_voxel_num_points.view(-1, 1)
+    gt_points = det_voxels[mask]
+    gt_coords = det_voxel_coords.to(torch.int32)[mask.nonzero()[:, 0]]
+    gt_points = torch.cat([gt_points, torch.zeros((gt_points.shape[0], 2), dtype=gt_points.dtype, device=gt_points.device)], dim=1)
+    if sel is None:
+        return None
+    points = torch.cat([gt_points, sel["occ_points"]], dim=0)
+    coords = torch.cat([gt_coords, sel["det_coords"]], dim=0)
+    shape = [int(det_grid[2]), int(det_grid[1]), int(det_grid[0])]
+    voxels, counts, vox_coords = revoxelize_sorted(coords, points, batch_size, shape)
+    return voxels, counts, vox_coords, sel

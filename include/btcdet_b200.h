@@ -346,6 +346,29 @@ int btc_occ_targets(const float* voxels, int P, int C, const int* voxel_coords, 
                     uint8_t* voxelwise_mask, uint8_t* vcc_mask, uint8_t* occ_mask, uint8_t* general_mask,
                     uint8_t* sphere_map_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Occupancy-point injection                         */
+/* btc_occ_select replaces AddOccTemplate.filter_occ_points (without top-k),  */
+/* occ_coords2absxyz, trans_voxel_grid and assemble_occ_points                */
+/* (btcdet/models/occ_pnt/add_occ_template.py:78-165): cells with             */
+/* prob > thresh, compacted in row-major (torch.nonzero) order per scene,     */
+/* turned into pseudo points [x,y,z,inten,prob,1] and det-grid coordinates.   */
+/* probs [batch,nz,ny,nx] f32, residuals [batch,3,nz,ny,nx] f32 or NULL,      */
+/* grid (nx,ny,nz), geom_f[12] = occ voxel size[3], occ origin[3] (rho,phi,z), */
+/* det voxel size[3], det range min[3] (x,y,z); det_grid (nx,ny,nz).          */
+/* Outputs (capacity `cap` rows): occ_coords [cap,4] (b,z,y,x), occ_probs,    */
+/* occ_xyz [cap,3], det_coords [cap,4], occ_points [cap,6];                   */
+/* counts [batch+1] i32 device: per scene, then the total.                    */
+/* btc_occ_vfe replaces OccVFE.forward (backbones_3d/vfe/occ_vfe.py:24-55).   */
+/* ------------------------------------------------------------------------- */
+int64_t btc_occ_select_workspace_bytes(int batch, const int* grid);
+int btc_occ_select(const float* probs, const float* residuals, int batch, const int* grid, float thresh,
+                   const float* rot_z, const float* geom_f, const int* det_grid, float inten, int cap,
+                   int* occ_coords, float* occ_probs, float* occ_xyz, int* det_coords, float* occ_points,
+                   int* counts, void* workspace, int64_t workspace_bytes, void* stream);
+int btc_occ_vfe(const float* voxels, const int* num_points, int m_cap, const int* m_dev, int P, int C,
+                int num_raw, float* feats, float* occ_feats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

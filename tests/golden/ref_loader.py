@@ -68,6 +68,10 @@ def load_reference_modules():
     _ns("btcdet.models.backbones_3d", os.path.join(REF, "btcdet/models/backbones_3d"))
     _ns("btcdet.models.occ_pnt", os.path.join(REF, "btcdet/models/occ_pnt"))
     _ns("btcdet.models.occ_pnt.occ_training_targets", os.path.join(REF, "btcdet/models/occ_pnt/occ_training_targets"))
+    vis = types.ModuleType("btcdet.utils.vis_occ_utils")      # skimage-based drawing helpers: imported, never called here
+    sys.modules[vis.__name__] = vis
+    sys.modules["btcdet.utils"].vis_occ_utils = vis
+    _ns("btcdet.models.backbones_3d.vfe", os.path.join(REF, "btcdet/models/backbones_3d/vfe"))
     mods = {}
     mods["common_utils"] = _load("btcdet.utils.common_utils", "btcdet/utils/common_utils.py")
     mods["coords_utils"] = _load("btcdet.utils.coords_utils", "btcdet/utils/coords_utils.py")
@@ -79,6 +83,10 @@ def load_reference_modules():
                                              "btcdet/models/occ_pnt/occ_training_targets/occ_targets_template.py")
         mods["occ_targets_3d"] = _load("btcdet.models.occ_pnt.occ_training_targets.occ_targets_3d",
                                        "btcdet/models/occ_pnt/occ_training_targets/occ_targets_3d.py")
+        mods["add_occ_template"] = _load("btcdet.models.occ_pnt.add_occ_template", "btcdet/models/occ_pnt/add_occ_template.py")
+        mods["pass_occ_vox"] = _load("btcdet.models.occ_pnt.pass_occ_vox", "btcdet/models/occ_pnt/pass_occ_vox.py")
+        mods["vfe_template"] = _load("btcdet.models.backbones_3d.vfe.vfe_template", "btcdet/models/backbones_3d/vfe/vfe_template.py")
+        mods["occ_vfe"] = _load("btcdet.models.backbones_3d.vfe.occ_vfe", "btcdet/models/backbones_3d/vfe/occ_vfe.py")
     return mods
 
 
