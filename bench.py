@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="scenes per step per GPU")
     ap.add_argument("--algo", type=int, default=0, help="conv tile: 0 auto, 1 FFMA, 2 tcgen05")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
