@@ -18,6 +18,7 @@
 //     instruction), apply bias / folded-BN affine / ReLU and write the output rows.
 //
 // Shared memory per stage: A_hi + A_lo (2 x 16 KB) + B_hi + B_lo (2 x N x 128 B).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace btc {
@@ -149,13 +150,17 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
 //   warp  13   : index loader — TMA-stages each tile's [128 x K] block of the neighbour table into shared
 //                memory with one cp.async.bulk, one tile ahead.
 // TMEM map (512 columns): [0, 2N) two accumulators | [2N + 64*s, +32) A_hi of stage s | [+32, +64) A_lo.
-constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_MMA_WARP = 8;
-constexpr int TC_EPI_WARP0 = 9;
-constexpr int TC_IDX_WARP = 13;
-constexpr int TC_PERSIST_THREADS = 14 * 32;
+// Warp roles for NPW producer warps (8 or 16): [0, NPW) producers in NPW/4 groups, NPW = MMA issuer, NPW+1..NPW+4
+// epilogue (TMEM lane quarter = warp % 4 covers 1,2,3,0), NPW+5 = index loader, the rest (to a multiple of four warps,
+// so that setmaxnreg acts on whole warpgroups) idle until the final barrier.
+template <int NPW> struct TcRoles {
+    static constexpr int kGroups = NPW / 4;
+    static constexpr int kMma = NPW, kEpi0 = NPW + 1, kIdx = NPW + 5;
+    static constexpr int kWarps = ((NPW + 6 + 3) / 4) * 4;
+    static constexpr int kThreads = kWarps * 32;
+};
 constexpr int TC_STAGES = 4;
-template <int N> struct TcDepth { static constexpr int value = N > 64 ? 2 : 3; };   // cp.async gather stages in flight per producer warp (smem budget)
+template <int N, int NPW> struct TcDepth { static constexpr int value = (N > 64 || NPW > 8) ? 2 : 4; };   // cp.async gather stages in flight per producer warp (smem budget)
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
@@ -192,17 +197,31 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int N>
-__global__ void __launch_bounds__(TC_PERSIST_THREADS, 1)
+template <int N, int NPW>
+__global__ void __launch_bounds__(TcRoles<NPW>::kThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, int n_cap, const int* __restrict__ n_dev, int K, int c_in,
                    int c_out) {
     constexpr int STAGES = TC_STAGES;
-    constexpr int TC_DEPTH = TcDepth<N>::value;
+    constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
+    using Roles = TcRoles<NPW>;
+    constexpr int G = Roles::kGroups;               // producer groups; group g feeds the stages with gi % G == g
+    constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx;
+    static_assert(TC_STAGES % G == 0 || G % TC_STAGES == 0, "stage ring / group count");
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = 512;
@@ -237,7 +256,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             mbar_init(&tmem_full[b], 1);           // one tcgen05.commit
             mbar_init(&tmem_empty[b], 128);        // the 128 epilogue threads
             mbar_init(&nbr_full[b], 1);            // the index loader (+ tx bytes)
-            mbar_init(&nbr_empty[b], 256);         // every producer thread
+            mbar_init(&nbr_empty[b], NPW * 32);    // every producer thread
         }
         fence_mbar_init();
     }
@@ -267,7 +286,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // position of the next stage to ISSUE: tile i_tl, stage i_j within the tile; this lane's 4-float piece of the
         // stage covers flattened elements e = 32*i_j + 4*q .. +3  ->  offset i_k = e / c_in, channel i_ch = e % c_in
         // (c_in % 4 == 0, so a piece never straddles two offsets).  Advanced by two global stages per step.
-        const int step_k = 64 / c_in, step_ch = 64 - step_k * c_in;
+        const int step_k = (32 * G) / c_in, step_ch = 32 * G - step_k * c_in;   // G stages per step
         int i_tl = group / T, i_j = group - i_tl * T;
         int i_k = (i_j * TC_KC + q * 4) / c_in, i_ch = (i_j * TC_KC + q * 4) - i_k * c_in;
         int cur_tile = -1;                          // tile whose index block this thread currently reads
@@ -292,8 +311,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
             }
             cp_async_commit();
-            // advance two global stages (64 reduction elements)
-            i_j += 2;
+            // advance G global stages (32*G reduction elements)
+            i_j += G;
             if (i_j >= T) {                         // next tile(s): restart the reduction axis
                 do { i_j -= T; ++i_tl; } while (i_j >= T);
                 i_k = (i_j * TC_KC + q * 4) / c_in;
@@ -305,7 +324,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
         };
         // this warp's stages: gi = group, group + 2, ...; local counter li
-        const int my_count = (total_stages - group + 1) / 2;
+        const int my_count = (total_stages - group + G - 1) / G;
         for (int li = 0; li < TC_DEPTH - 1 && li < my_count; ++li) issue(li % TC_DEPTH);
         const uint32_t rd_base = abuf + (uint32_t)lane * 128u;
         const uint32_t x7 = (uint32_t)(lane & 7);
@@ -329,29 +348,34 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 mbar_expect_tx(&full_bar[s], 2 * B_BYTES);
                 bulk_copy_g2s(st, (const char*)packed_w + (int64_t)jpos * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
             }
-            uint32_t w[32];
+            // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
+            // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {          // hi: low 13 mantissa bits cleared -> exact tf32
-                w[4 * i + 0] = __float_as_uint(v[i].x) & 0xFFFFE000u;
-                w[4 * i + 1] = __float_as_uint(v[i].y) & 0xFFFFE000u;
-                w[4 * i + 2] = __float_as_uint(v[i].z) & 0xFFFFE000u;
-                w[4 * i + 3] = __float_as_uint(v[i].w) & 0xFFFFE000u;
-            }
-            tmem_st32(lane_base + A_COL0 + (uint32_t)(s * 64), w);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {          // lo: exact fp32 remainder
-                w[4 * i + 0] = __float_as_uint(v[i].x - __uint_as_float(w[4 * i + 0]));
-                w[4 * i + 1] = __float_as_uint(v[i].y - __uint_as_float(w[4 * i + 1]));
-                w[4 * i + 2] = __float_as_uint(v[i].z - __uint_as_float(w[4 * i + 2]));
-                w[4 * i + 3] = __float_as_uint(v[i].w - __uint_as_float(w[4 * i + 3]));
+                for (int i = 0; i < 4; ++i) {
+                    w[4 * i + 0] = __float_as_uint(v[4 * h + i].x) & 0xFFFFE000u;
+                    w[4 * i + 1] = __float_as_uint(v[4 * h + i].y) & 0xFFFFE000u;
+                    w[4 * i + 2] = __float_as_uint(v[4 * h + i].z) & 0xFFFFE000u;
+                    w[4 * i + 3] = __float_as_uint(v[4 * h + i].w) & 0xFFFFE000u;
+                }
+                tmem_st16(lane_base + A_COL0 + (uint32_t)(s * 64 + 16 * h), w);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w[4 * i + 0] = __float_as_uint(v[4 * h + i].x - __uint_as_float(w[4 * i + 0]));
+                    w[4 * i + 1] = __float_as_uint(v[4 * h + i].y - __uint_as_float(w[4 * i + 1]));
+                    w[4 * i + 2] = __float_as_uint(v[4 * h + i].z - __uint_as_float(w[4 * i + 2]));
+                    w[4 * i + 3] = __float_as_uint(v[4 * h + i].w - __uint_as_float(w[4 * i + 3]));
+                }
+                tmem_st16(lane_base + A_COL0 + (uint32_t)(s * 64 + 32 + 16 * h), w);
             }
-            tmem_st32(lane_base + A_COL0 + (uint32_t)(s * 64 + 32), w);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&full_bar[s]);
             // advance the consume-side counters by two global stages
-            s += 2; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
-            jpos += 2; if (jpos >= T) jpos -= T;
+            s += G; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+            jpos += G; while (jpos >= T) jpos -= T;
             if (++slot == TC_DEPTH) slot = 0;
         }
         if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);
@@ -410,7 +434,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp >= Roles::kEpi0 && warp < Roles::kEpi0 + 4) {
         // ================= epilogue =================
         const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
         for (int tl = 0; tl < my_tiles; ++tl) {
@@ -458,14 +482,14 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int N>
-static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
-                     const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
-                     int K, int c_in, int c_out, cudaStream_t st) {
+template <int N, int NPW>
+static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
+                         const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
+                         int K, int c_in, int c_out, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * N * 128;
-    size_t smem = (size_t)TC_STAGES * STAGE_BYTES + (size_t)TC_PRODUCER_WARPS * TcDepth<N>::value * 4096 +
+    size_t smem = (size_t)TC_STAGES * STAGE_BYTES + (size_t)NPW * TcDepth<N, NPW>::value * 4096 +
                   (size_t)2 * TC_BM * K * sizeof(int) + 1024 + 16;
-    auto kern = conv_fwd_tc_kernel<N>;
+    auto kern = conv_fwd_tc_kernel<N, NPW>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
@@ -473,10 +497,26 @@ static int launch_tc(const float* feat_in, const int* table, const float* packed
     }
     int tiles = (n_cap + TC_BM - 1) / TC_BM;
     dim3 grid(tiles < kNumSM ? tiles : kNumSM);    // persistent: one CTA per SM
-    kern<<<grid, TC_PERSIST_THREADS, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap,
-                                                 n_dev, K, c_in, c_out);
+    kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap,
+                                                     n_dev, K, c_in, c_out);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
+}
+
+// 16 producer warps (four groups) when shared memory allows (N <= 64); BTC_TC_NPW=8 forces the 8-warp variant (A/B).
+template <int N>
+static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
+                     const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
+                     int K, int c_in, int c_out, cudaStream_t st) {
+    static int npw = 0;
+    if (npw == 0) {
+        const char* e = getenv("BTC_TC_NPW");
+        npw = (e && atoi(e) == 8) ? 8 : 16;
+    }
+    if (N <= 64 && npw == 16)
+        return launch_tc_npw<(N <= 64 ? N : 64), 16>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap, n_dev, K,
+                                                     c_in, c_out, st);
+    return launch_tc_npw<N, 8>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap, n_dev, K, c_in, c_out, st);
 }
 
 static int tc_padded_n(int c_out) {

@@ -38,7 +38,7 @@ class Net(nn.Module):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--batch", type=int, default=2)
     args = ap.parse_args()
     rank, world = bd.init()
@@ -82,7 +82,7 @@ def main():
         print(json.dumps({"metric": "training scenes/sec (fwd+bwd+allreduce+Adam, VoxelBackBone8x + BEV head)",
                           "value": round(world * args.batch * args.steps / (ms * 1e-3), 2), "unit": "scenes/s", "n_gpus": world,
                           "steps": args.steps, "ms_per_step": round(ms / args.steps, 3), "scenes_per_gpu": args.batch,
-                          "loss": float(loss), "path": "eager spconv shim (autograd Functions over the C ABI)"}))
+                          "loss": float(loss.detach()), "path": "eager spconv shim (autograd Functions over the C ABI)"}))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
