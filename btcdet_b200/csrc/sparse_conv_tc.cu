@@ -1,23 +1,20 @@
-// tcgen05 (5th-gen tensor core) gather-GEMM tile for the wide sparse-conv layers.
+// tcgen05 (5th-gen tensor core) gather-GEMM tile for the sparse-conv layers.
 //
-// Same output-stationary formulation as sparse_conv.cu (one CTA = 128 output rows, all K
-// offsets walked in ascending order, each output row written once), but the
-// [128 x 32] x [32 x N] products run on the tensor cores with the accumulator in TMEM:
+// Same output-stationary formulation as sparse_conv.cu (128 output rows per tile, the K offsets walked in ascending
+// order, every output row written once, no atomics), with the products on the tensor cores and the accumulator in
+// TMEM.  The reduction axis is the flattened (offset, input channel) index cut into stages of 32:
 //
-//   * 4 producer warps gather the neighbour rows named by nbr_out[o][k] from global/L2 with
-//     16-byte loads, split every fp32 value into a tf32 "hi" part (low 13 mantissa bits cleared)
-//     and the exact fp32 remainder "lo", and store both as K-major, 128-byte-swizzled UMMA
-//     operand tiles in shared memory (the gather cannot be a TMA tile: rows are arbitrary);
-//   * the matching weight slice W[k][c0:c0+32][:] comes pre-packed (btc_sparse_conv_tc_pack) as
-//     the exact shared-memory image of the K-major swizzled hi/lo tiles, so one elected thread
-//     fetches it with a single cp.async.bulk (TMA 1-D bulk copy, complete_tx on the stage mbarrier);
-//   * one elected thread of warp 4 issues tcgen05.mma.kind::tf32 (M=128, N, K=8) — 3xTF32:
-//     D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi — fp32-class accuracy (the 1e-4 parity bar) from the
-//     tf32 pipe; tcgen05.commit releases the smem stage / publishes the accumulator (mbarriers);
-//   * the producer warps then read the accumulator back with tcgen05.ld (32 lanes x 16 columns per
-//     instruction), apply bias / folded-BN affine / ReLU and write the output rows.
-//
-// Shared memory per stage: A_hi + A_lo (2 x 16 KB) + B_hi + B_lo (2 x N x 128 B).
+//   * producer warps gather the neighbour rows named by nbr_out[o][k] (index tile TMA-staged in shared memory) with
+//     cp.async (8 lanes per row, zero fill for missing neighbours), read them back one row per thread, split every
+//     fp32 value into a tf32 "hi" part (low 13 mantissa bits cleared) and the exact fp32 remainder "lo", and write the
+//     A operand straight into tensor memory with tcgen05.st;
+//   * the matching weight slice comes pre-packed (btc_sparse_conv_tc_pack) as the shared-memory image of the K-major,
+//     128-byte-swizzled hi/lo tiles and is fetched with one cp.async.bulk per stage (mbarrier complete_tx);
+//   * one elected lane issues tcgen05.mma.kind::tf32 (M=128, N, K=8), A from TMEM, B from shared memory — 3xTF32:
+//     D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi — fp32-class accuracy (the 1e-4 parity bar) from the tf32 pipe;
+//     tcgen05.commit releases the stage / publishes the accumulator through mbarriers;
+//   * epilogue warps read the (double-buffered) accumulator back with tcgen05.ld, apply bias / folded-BN affine /
+//     ReLU and write the output rows while the next tile's main loop runs.
 #include <stdlib.h>
 #include "common.cuh"
 
