@@ -314,12 +314,40 @@ def sparse_conv_bwd_weight(features, d_out, nbr_out, weight_shape, want_bias):
     return d_w, d_b
 
 
+_PACK_CACHE = {}
+
+
+def _packed_weight(weight):
+    """tcgen05 operand image of a layer's weights, cached until the Parameter is modified in place or replaced."""
+    key = (weight.data_ptr(), tuple(weight.shape))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == weight._version:
+        return hit[1]
+    if len(_PACK_CACHE) > 256:
+        _PACK_CACHE.clear()
+    packed = tc_pack_weight(weight)
+    _PACK_CACHE[key] = (weight._version, packed)
+    return packed
+
+
 class SparseConvFunction(torch.autograd.Function):
-    """indice_conv of spconv.ops with autograd (forward + dX + dW + db on the CUDA library)."""
+    """indice_conv of spconv.ops with autograd (forward + dX + dW + db on the CUDA library).
+
+    algo: 0 = auto (tcgen05 3xTF32 tile when the shape qualifies, fp32 FFMA tile otherwise), 1 = FFMA, 2 = tcgen05.
+    The backward kernels are fp32 FFMA / atomics in every mode."""
 
     @staticmethod
     def forward(ctx, features, weight, bias, rulebook: Rulebook, algo):
-        out = sparse_conv_fwd(features, rulebook.nbr_out, weight, bias, algo=algo)
+        c_in, c_out = weight.shape[-2], weight.shape[-1]
+        use_tc = algo != 1 and tc_supported(rulebook.K, c_in, c_out) and features.shape[0] > 0 \
+            and features.data_ptr() % 16 == 0
+        if algo == 2 and not use_tc:
+            raise _lib.BtcError("tensor-core tile requested for an unsupported shape (K=%d Cin=%d Cout=%d)" %
+                                (rulebook.K, c_in, c_out))
+        if use_tc:
+            out = sparse_conv_fwd_tc(features.contiguous(), rulebook.nbr_out, _packed_weight(weight), c_in, c_out, bias)
+        else:
+            out = sparse_conv_fwd(features, rulebook.nbr_out, weight, bias, algo=1)
         ctx.save_for_backward(features, weight)
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
