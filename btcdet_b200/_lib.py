@@ -49,6 +49,10 @@ SIGNATURES = {
     "btc_occ_select_workspace_bytes": (_i64, [_i, _p]),
     "btc_occ_select": (_i, [_p, _p, _i, _p, ctypes.c_float, _p, _p, _p, ctypes.c_float, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_occ_vfe": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
+    "btc_occ_box_targets_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "btc_occ_box_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i,
+                                 _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_occ_loss_maps": (_i, [_p] * 10 + [_i, _p] + [_p] * 11),
     "btc_revoxelize_workspace_bytes": (_i64, [_i, _i64]),
     "btc_revoxelize": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_revoxelize_fill": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _i, _p]),

@@ -80,7 +80,7 @@ subm_table_kernel(const int4* __restrict__ coords, int n_cap, const int* __restr
                     j = (k == K / 2) ? i : hash_lookup(keys, vals, hmask, key);
                 } else {
                     int r = index_lookup(index, key);
-                    if (r >= 0) j = perm ? __ldg(perm + r) : r;
+                    if (r >= 0 && r < n_cap) j = perm ? __ldg(perm + r) : r;   // rank >= capacity: site not materialised
                 }
             }
             nbr_out[(int64_t)i * K + k] = j;

@@ -348,6 +348,9 @@ class BackbonePlan:
         counts = self.host_counts[:len(self.levels)].tolist()
         for c, l in zip(counts, self.levels):
             if c > l.cap:
+                for lv in self.levels:   # rows past a capacity were never listed, so the sparse clear missed their bits
+                    if getattr(lv, "index", None) is not None:
+                        lv.index.zero_()
                 raise _lib.BtcError("level capacity exceeded: %d sites > capacity %d — raise level_growth" % (c, l.cap))
         return counts
 

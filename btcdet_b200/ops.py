@@ -549,6 +549,106 @@ def occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom
     return out
 
 
+DEFAULT_LOSS_WEIGHTS = {"occ_fore_cls_weight": 1.0, "occ_mirr_cls_weight": 1.0, "occ_bm_cls_weight": 1.0,
+                        "occ_neg_cls_weight": 1.0, "occ_fore_res_weight": 0.1, "occ_mirr_res_weight": 0.0,
+                        "occ_bm_res_weight": 0.0}
+
+
+def occ_box_targets(voxels, voxel_coords, voxel_num_points, batch_size, gt_boxes, gt_boxes_num, geom_f, geom_i,
+                    box_mirr_flag=None, bm_points=None, rot_z=None, num_class=1, want_forebox=True, want_point_label=False,
+                    mirr_cap=None, bm_cap=None):
+    """Foreground / mirrored / best-match masks with their mean-residual volumes and the forebox label
+    (occ_targets_3d.py:70-86,95-171) in one sync-free call.
+    gt_boxes [B, M, >=8] f32, gt_boxes_num list or int tensor [B], box_mirr_flag [B, M], bm_points [n, 4] (b,x,y,z).
+    Returns a dict of dense tensors; "status" is a device int32 (1 = an accumulator capacity overflowed)."""
+    _require_cuda(voxels, voxel_coords, voxel_num_points, gt_boxes)
+    lib = _lib.load()
+    dev = voxels.device
+    voxels = voxels.to(torch.float32).contiguous()
+    coords = voxel_coords.to(torch.int32).contiguous()
+    nump = voxel_num_points.to(torch.int32).contiguous()
+    m, P, C = voxels.shape
+    B = int(batch_size)
+    boxes = gt_boxes.to(torch.float32).contiguous()
+    max_boxes, box_dim = int(boxes.shape[1]), int(boxes.shape[2])
+    bnum = torch.as_tensor(gt_boxes_num, dtype=torch.int32).to(dev).contiguous()
+    flag = None if box_mirr_flag is None else box_mirr_flag.to(device=dev, dtype=torch.float32).contiguous()
+    bm = None if bm_points is None or len(bm_points) == 0 else bm_points.to(device=dev, dtype=torch.float32).contiguous()
+    n_bm = 0 if bm is None else int(bm.shape[0])
+    gf, gi = float_array(geom_f), (ctypes.c_int * len(geom_i))(*[int(v) for v in geom_i])
+    nx, ny, nz = geom_i[0:3]
+    cells = B * nx * ny * nz
+    mirr_cap = int(mirr_cap if mirr_cap is not None else min(cells, max(1024, m * P)))
+    bm_cap = int(bm_cap if bm_cap is not None else min(cells, max(1024, n_bm)))
+    shape = (B, nz, ny, nx)
+    out = {"fore_voxelwise_mask": torch.empty(shape, dtype=torch.uint8, device=dev),
+           "mirr_fore_voxelwise_mask": torch.empty(shape, dtype=torch.uint8, device=dev),
+           "fore_res_mtrx": torch.empty((B, 3, nz, ny, nx), dtype=torch.float32, device=dev),
+           "mirr_res_mtrx": torch.empty((B, 3, nz, ny, nx), dtype=torch.float32, device=dev),
+           "bm_voxelwise_mask": torch.empty(shape, dtype=torch.uint8, device=dev) if n_bm else None,
+           "bm_res_mtrx": torch.empty((B, 3, nz, ny, nx), dtype=torch.float32, device=dev) if n_bm else None,
+           "forebox_label": torch.empty(shape, dtype=torch.int8, device=dev) if want_forebox else None,
+           "point_label": torch.empty((m, P), dtype=torch.int8, device=dev) if want_point_label else None,
+           "status": torch.empty(1, dtype=torch.int32, device=dev)}
+    ws_bytes = int(lib.btc_occ_box_targets_workspace_bytes(B, max_boxes, mirr_cap, bm_cap))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rz = None if rot_z is None else rot_z.to(torch.float32).contiguous()
+    check(lib.btc_occ_box_targets(_ptr(voxels), P, C, _ptr(coords), _ptr(nump), m, None, B, _ptr(boxes), max_boxes, box_dim,
+                                  _ptr(bnum), _ptr(flag), _ptr(bm), n_bm, _ptr(rz), gf, gi, int(num_class), mirr_cap, bm_cap,
+                                  _ptr(out["fore_voxelwise_mask"]), _ptr(out["fore_res_mtrx"]),
+                                  _ptr(out["mirr_fore_voxelwise_mask"]), _ptr(out["mirr_res_mtrx"]),
+                                  _ptr(out["bm_voxelwise_mask"]), _ptr(out["bm_res_mtrx"]), _ptr(out["forebox_label"]),
+                                  _ptr(out["point_label"]), _ptr(out["status"]), _ptr(ws), ws_bytes, _stream()),
+          "btc_occ_box_targets")
+    return out
+
+
+def occ_loss_maps(occ, box, weights=None, box_weight=0.2):
+    """prepare_cls_loss_map + prepare_reg_loss_map (occ_targets_template.py:330-401, dropout off) on the outputs of
+    occ_targets() and occ_box_targets(): every derived mask, the float weight maps and res_mtrx in one pass."""
+    lib = _lib.load()
+    w = dict(DEFAULT_LOSS_WEIGHTS)
+    w.update(weights or {})
+    vm = occ["voxelwise_mask"]
+    dev = vm.device
+    B, nz, ny, nx = vm.shape
+    forebox = box.get("forebox_label") if box_weight != 1.0 else None
+    wf = float_array([w["occ_fore_cls_weight"], w["occ_mirr_cls_weight"], w["occ_bm_cls_weight"], w["occ_neg_cls_weight"],
+                      w["occ_fore_res_weight"], w["occ_mirr_res_weight"], w["occ_bm_res_weight"],
+                      float(box_weight) - w["occ_neg_cls_weight"]])
+    u8 = lambda: torch.empty((B, nz, ny, nx), dtype=torch.uint8, device=dev)   # noqa: E731
+    f32 = lambda: torch.empty((B, nz, ny, nx), dtype=torch.float32, device=dev)   # noqa: E731
+    out = {"occ_fore_cls_mask": u8(), "occ_mirr_cls_mask": u8(), "occ_bm_cls_mask": u8(), "pos_mask": u8(),
+           "bm_voxelwise_mask": u8(), "general_cls_loss_mask_float": f32(), "general_reg_loss_mask": u8(),
+           "general_reg_loss_mask_float": f32(), "res_mtrx": torch.empty((B, 3, nz, ny, nx), dtype=torch.float32, device=dev),
+           "pos_all_num": torch.empty(1, dtype=torch.int32, device=dev)}
+    check(lib.btc_occ_loss_maps(_ptr(vm), _ptr(occ["general_cls_loss_mask"]), _ptr(box["fore_voxelwise_mask"]),
+                                _ptr(box["mirr_fore_voxelwise_mask"]), _ptr(box.get("bm_voxelwise_mask")), _ptr(forebox),
+                                _ptr(box["fore_res_mtrx"]), _ptr(box["mirr_res_mtrx"]), _ptr(box.get("bm_res_mtrx")), wf, B,
+                                int3([nx, ny, nz]), _ptr(out["occ_fore_cls_mask"]), _ptr(out["occ_mirr_cls_mask"]),
+                                _ptr(out["occ_bm_cls_mask"]), _ptr(out["pos_mask"]), _ptr(out["bm_voxelwise_mask"]),
+                                _ptr(out["general_cls_loss_mask_float"]), _ptr(out["general_reg_loss_mask"]),
+                                _ptr(out["general_reg_loss_mask_float"]), _ptr(out["res_mtrx"]), _ptr(out["pos_all_num"]),
+                                _stream()), "btc_occ_loss_maps")
+    out["forebox_label"] = forebox
+    return out
+
+
+def occ_training_targets(voxels, voxel_coords, voxel_num_points, batch_size, gt_boxes, gt_boxes_num, geom_f, geom_i,
+                         box_mirr_flag=None, bm_points=None, rot_z=None, num_class=1, weights=None, box_weight=0.2):
+    """OccTargets3D.create_voxel_res_label (occ_targets_3d.py:44-92) end to end on the GPU: three C-ABI calls, no host
+    synchronisation.  Returns the reference's batch_dict entries (masks u8, weight maps f32, res_mtrx f32)."""
+    occ = occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom_i, rot_z=rot_z)
+    box = occ_box_targets(voxels, voxel_coords, voxel_num_points, batch_size, gt_boxes, gt_boxes_num, geom_f, geom_i,
+                          box_mirr_flag=box_mirr_flag, bm_points=bm_points, rot_z=rot_z, num_class=num_class,
+                          want_forebox=box_weight != 1.0)
+    out = occ_loss_maps(occ, box, weights, box_weight)
+    out.update({k: occ[k] for k in ("voxelwise_mask", "vcc_mask", "occ_voxelwise_mask", "general_cls_loss_mask")})
+    out["fore_voxelwise_mask"] = box["fore_voxelwise_mask"]
+    out["status"] = box["status"]
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # occupancy-point injection (PassOccVox) and OccVFE
 # ------------------------------------------------------------------------------------------

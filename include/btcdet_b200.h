@@ -369,6 +369,51 @@ int btc_occ_select(const float* probs, const float* residuals, int batch, const 
 int btc_occ_vfe(const float* voxels, const int* num_points, int m_cap, const int* m_dev, int P, int C,
                 int num_raw, float* feats, float* occ_feats, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Box-driven occupancy targets                        */
+/* btc_occ_box_targets replaces, per batch and without host synchronisation,   */
+/*   get_fore_mirr_voxelwise_mask_res  (occ_targets_3d.py:146-171) over         */
+/*     torch_points_and_sym_in_box_3d_batch (point_box_utils.py:70-97,252-306), */
+/*   get_bm_voxelwise_mask_res (:95-119), get_mean_res (:122-130),              */
+/*   get_voxel_center_xyz (:133-145) and the forebox-label loop (:70-86 over    */
+/*   point_box_utils.py:198-250,332-365).                                       */
+/* voxels/voxel_coords/num_points/rot_z/geom_*: as btc_occ_targets.             */
+/* gt_boxes [batch, max_boxes, box_dim>=8] f32 (x,y,z,dx,dy,dz,heading,...,     */
+/*   label last); gt_boxes_num [batch] i32; mirr_flag [batch, max_boxes] f32    */
+/*   or NULL; bm_points [n_bm, 4] f32 (b,x,y,z) or NULL (16-byte aligned).      */
+/* num_class == 1 binarises the label column (> 1e-2) as occ_targets_3d.py:52.  */
+/* mirr_cap / bm_cap: upper bounds on the number of distinct cells hit by       */
+/*   mirrored / template points (accumulator capacity); *status (device i32)    */
+/*   is set to 1 if one overflowed.                                             */
+/* Outputs: fore_mask, mirr_mask, bm_mask u8 [batch,nz,ny,nx] (raw, before the  */
+/*   (1 - voxelwise) products); *_res f32 [batch,3,nz,ny,nx] (per-cell mean of  */
+/*   the points minus the cell centre); forebox_label i8 [batch,nz,ny,nx] or    */
+/*   NULL (BOX_WEIGHT == 1); point_label i8 [m_cap, P] or NULL.                 */
+/* Box-frame coordinates use the analytic rigid inverse, not torch.inverse:     */
+/*   see DESIGN.md for the face/bin-edge tolerance this implies.                */
+/* btc_occ_loss_maps replaces prepare_cls_loss_map / prepare_reg_loss_map       */
+/*   (occ_targets_template.py:330-401, dropout off) and the (1 - mask) products */
+/*   of occ_targets_3d.py:58-65.  weights[8] = fore_cls, mirr_cls, bm_cls,      */
+/*   neg_cls, fore_res, mirr_res, bm_res, (BOX_WEIGHT - neg_cls).               */
+/*   grid = (nx, ny, nz).  bm_* and forebox_label, bm_voxelwise_mask and        */
+/*   pos_all_num (device i32) may be NULL.                                      */
+/* ------------------------------------------------------------------------- */
+int64_t btc_occ_box_targets_workspace_bytes(int batch, int max_boxes, int mirr_cap, int bm_cap);
+int btc_occ_box_targets(const float* voxels, int P, int C, const int* voxel_coords, const int* num_points,
+                        int m_cap, const int* m_dev, int batch, const float* gt_boxes, int max_boxes, int box_dim,
+                        const int* gt_boxes_num, const float* mirr_flag, const float* bm_points, int n_bm,
+                        const float* rot_z, const float* geom_f, const int* geom_i, int num_class,
+                        int mirr_cap, int bm_cap, uint8_t* fore_mask, float* fore_res, uint8_t* mirr_mask,
+                        float* mirr_res, uint8_t* bm_mask, float* bm_res, int8_t* forebox_label,
+                        int8_t* point_label, int* status, void* workspace, int64_t workspace_bytes, void* stream);
+int btc_occ_loss_maps(const uint8_t* voxelwise_mask, const uint8_t* general_mask, const uint8_t* fore_mask,
+                      const uint8_t* mirr_mask, const uint8_t* bm_mask, const int8_t* forebox_label,
+                      const float* fore_res, const float* mirr_res, const float* bm_res, const float* weights,
+                      int batch, const int* grid, uint8_t* occ_fore_cls_mask, uint8_t* occ_mirr_cls_mask,
+                      uint8_t* occ_bm_cls_mask, uint8_t* pos_mask, uint8_t* bm_voxelwise_mask,
+                      float* cls_loss_mask_float, uint8_t* reg_loss_mask, float* reg_loss_mask_float,
+                      float* res_mtrx, int* pos_all_num, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
