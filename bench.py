@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="scenes per step per GPU")
     ap.add_argument("--algo", type=int, default=0, help="conv tile: 0 auto, 1 FFMA, 2 tcgen05")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sort", action="store_true", help="keep rulebook rows in spatial order (A/B of the mask sort)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the bounded CPU sample (0 = auto)")
     return ap.parse_args()
@@ -116,7 +117,7 @@ def layer_bytes_flops(plan, counts):
     for s in plan.steps:
         if s.kind != "conv":
             continue
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = s.args
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = s.args
         n_out = lvl_n[id(lout)]
         pairs = int((nbr[:n_out] >= 0).sum().item())
         out.append({"n_in": n_in, "n_out": n_out, "pairs": pairs, "K": K, "cin": cin, "cout": cout,
@@ -135,7 +136,7 @@ def run_ours(args, rank, world):
     model = build_model()
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                               device=dev, use_graph=not args.no_graph).capture()
+                               device=dev, use_graph=not args.no_graph, sort_rows=not args.no_sort).capture()
     scenes = make_scenes(rank, N_SCENE_POOL)
     # batches: host pinned (for e2e) and device resident (for value)
     n_batches = N_SCENE_POOL // B if N_SCENE_POOL >= B else 1
@@ -249,7 +250,7 @@ def run_ours(args, rank, world):
         tot_ms, reps = 0.0, 5
         per_layer = []
         for s, sp in zip(conv_steps, specs):
-            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = s.args
+            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = s.args
             ms_l = 0.0
             for r in range(reps + 1):
                 flush.fill_(float(r))
@@ -262,7 +263,7 @@ def run_ours(args, rank, world):
                     ms_l += e0.elapsed_time(e1)
             ms_l /= reps
             tot_ms += ms_l
-            per_layer.append({"tile": "tcgen05" if packed is not None else "ffma", "cin": cin, "cout": cout, "n_out": sp["n_out"], "pairs": sp["pairs"], "us": round(ms_l * 1e3, 2),
+            per_layer.append({"tile": ("tcgen05+rows" if rows is not None else "tcgen05") if packed is not None else "ffma", "cin": cin, "cout": cout, "n_out": sp["n_out"], "pairs": sp["pairs"], "us": round(ms_l * 1e3, 2),
                               "gflops": round(sp["flops"] / ms_l / 1e6, 1)})
         alg_bytes = sum(sp["bytes"] for sp in specs)
         alg_flops = sum(sp["flops"] for sp in specs)
@@ -290,7 +291,7 @@ def run_ours(args, rank, world):
                    "scenes_per_step_per_gpu": B, "points_per_scene": N_POINTS, "parallelism": "dp%d" % world,
                    "l2": "value: 256 MB buffer written between timed steps (untimed), %d distinct scenes cycled; e2e: pipelined "
                          "region timed whole, fresh pinned-host batch in and ~15 MB of results out per step" % N_SCENE_POOL,
-                   "cuda_graph": not args.no_graph, "conv_algo": args.algo,
+                   "cuda_graph": not args.no_graph, "conv_algo": args.algo, "mask_sorted_rows": not args.no_sort,
                    "level_sites": counts},
         "e2e": {"value": round(scenes_total / (ms_e2e * 1e-3), 2), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": round(ms_e2e / args.steps, 4)},

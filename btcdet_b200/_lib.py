@@ -36,6 +36,8 @@ SIGNATURES = {
     "btc_sparse_conv_tc_packed_bytes": (_i64, [_i, _i, _i]),
     "btc_sparse_conv_tc_pack": (_i, [_p, _i, _i, _i, _p, _p]),
     "btc_sparse_conv_fwd_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "btc_sparse_conv_fwd_tc_rows": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "btc_rulebook_sort_rows": (_i, [_p, _i, _p, _i, _p, _p, _p]),
     "btc_sparse_conv_bwd_workspace_bytes": (_i64, [_i, _i, _i]),
     "btc_sparse_conv_bwd_data": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _i64, _p]),
     "btc_sparse_conv_bwd_weight": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),

@@ -259,6 +259,68 @@ __global__ void __launch_bounds__(kPairThreads) pairs_write_kernel(const int* __
     }
 }
 
+// ---- mask-ordered rows for the block-skipping tensor-core tile -------------------------------------------
+// One CTA sorts a window of 2048 consecutive rows by their valid-offset bit mask (ties: original order), entirely in
+// shared memory (bitonic network on (mask, index) pairs), and writes the permuted table rows + the permutation.
+// Windows keep the gather local; measured on LiDAR-like scenes the per-tile union of masks shrinks from 0.56-0.77 of
+// the K offsets (spatial order) to 0.32-0.60.
+constexpr int kSortWindow = 2048;
+constexpr int kSortThreads = 1024;
+
+__global__ void __launch_bounds__(kSortThreads) sort_rows_kernel(const int* __restrict__ nbr, int n_cap,
+                                                                 const int* __restrict__ n_dev, int K,
+                                                                 int* __restrict__ nbr_sorted, int* __restrict__ out_rows) {
+    __shared__ unsigned long long s_mask[kSortWindow];
+    __shared__ unsigned short s_idx[kSortWindow];
+    const int n = live_count(n_cap, n_dev);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int w0 = blockIdx.x * kSortWindow; w0 < n; w0 += gridDim.x * kSortWindow) {
+        // masks: one warp per row, lanes across the offsets (coalesced row reads, ballot = mask)
+        for (int i = warp; i < kSortWindow; i += kSortThreads / 32) {
+            const int r = w0 + i;
+            unsigned long long m = ~0ull;                       // padding rows sort last
+            if (r < n) {
+                const int* rp = nbr + (int64_t)r * K;
+                const int v0 = lane < K ? __ldg(rp + lane) : -1;
+                const unsigned lo = __ballot_sync(0xffffffffu, v0 >= 0);
+                unsigned hi = 0;
+                if (K > 32) {
+                    const int v1 = lane + 32 < K ? __ldg(rp + lane + 32) : -1;
+                    hi = __ballot_sync(0xffffffffu, v1 >= 0);
+                }
+                m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+            }
+            if (lane == 0) { s_mask[i] = m; s_idx[i] = (unsigned short)i; }
+        }
+        __syncthreads();
+        for (int k = 2; k <= kSortWindow; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int t = threadIdx.x;
+                const int i = 2 * t - (t & (j - 1));            // element with bit j clear
+                const int p = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long a = s_mask[i], b = s_mask[p];
+                const unsigned short ia = s_idx[i], ib = s_idx[p];
+                const bool a_gt_b = a > b || (a == b && ia > ib);
+                if (a_gt_b == up) {
+                    s_mask[i] = b; s_mask[p] = a;
+                    s_idx[i] = ib; s_idx[p] = ia;
+                }
+                __syncthreads();
+            }
+        }
+        const int live = n - w0 < kSortWindow ? n - w0 : kSortWindow;
+        for (int i = warp; i < live; i += kSortThreads / 32) {
+            const int src = w0 + (int)s_idx[i];
+            const int* rp = nbr + (int64_t)src * K;
+            int* wp = nbr_sorted + (int64_t)(w0 + i) * K;
+            for (int k = lane; k < K; k += 32) wp[k] = __ldg(rp + k);
+            if (lane == 0) out_rows[w0 + i] = src;
+        }
+        __syncthreads();
+    }
+}
+
 static int make_geom(ConvGeom& g, int batch, const int* in_shape, const int* out_shape, const int* ksize,
                      const int* stride, const int* padding, const int* dilation, int transposed) {
     g.batch = batch;
@@ -380,6 +442,19 @@ int btc_rulebook_pairs(const int* table, int n_in_cap, const int* n_in_dev, int 
     pairs_scan_kernel<<<K, 256, 0, st>>>(counts, nblk, pair_num);
     pairs_write_kernel<<<grid, kPairThreads, 0, st>>>(table, n_in_cap, n_in_dev, K, mirror, counts, pairs);
     BTC_CHECK_LAUNCH("rulebook_pairs");
+    return BTC_OK;
+}
+
+int btc_rulebook_sort_rows(const int* nbr_out, int n_cap, const int* n_dev, int K, int* nbr_sorted, int* out_rows,
+                           void* stream) {
+    if (K < 1 || K > 64) return badarg("btc_rulebook_sort_rows: K must be in [1, 64]");
+    if (n_cap <= 0) return BTC_OK;
+    if (!nbr_out || !nbr_sorted || !out_rows) return badarg("btc_rulebook_sort_rows: null argument");
+    if (nbr_out == nbr_sorted) return badarg("btc_rulebook_sort_rows: in-place sort is not supported");
+    const int windows = (n_cap + kSortWindow - 1) / kSortWindow;
+    sort_rows_kernel<<<windows < 4 * kNumSM ? windows : 4 * kNumSM, kSortThreads, 0, (cudaStream_t)stream>>>(
+        nbr_out, n_cap, n_dev, K, nbr_sorted, out_rows);
+    BTC_CUDA(cudaGetLastError(), "btc_rulebook_sort_rows launch");
     return BTC_OK;
 }
 

@@ -48,6 +48,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // one non-blocking probe
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -211,8 +222,8 @@ __global__ void __launch_bounds__(TcRoles<NPW>::kThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                   float* __restrict__ feat_out, int n_cap, const int* __restrict__ n_dev, int K, int c_in,
-                   int c_out) {
+                   float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
+                   const int* __restrict__ n_dev, int K, int c_in, int c_out) {
     constexpr int STAGES = TC_STAGES;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
@@ -232,8 +243,10 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     unsigned char* a_stage = stages + STAGES * STAGE_BYTES;                 // [8 warps][TC_DEPTH][32 rows x 128 B]
     int* nbr_s = (int*)(a_stage + TC_PRODUCER_WARPS * TC_DEPTH * 4096);     // [2][TC_BM * K]
 
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], nbr_full[2], nbr_empty[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], nbr_full[2], nbr_empty[2],
+        list_full[2];
     __shared__ uint32_t s_tmem;
+    __shared__ int s_cnt[2];                        // active reduction chunks of the tile in each index buffer
 
     const int n = live_count(n_cap, n_dev);
     if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
@@ -241,8 +254,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     const int num_tiles = (n + TC_BM - 1) / TC_BM;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int E = K * c_in;                         // flattened (offset, channel) reduction length
-    const int T = (E + TC_KC - 1) / TC_KC;          // stages per tile: 32 reduction elements each
-    const int total_stages = my_tiles * T;
+    const int T = (E + TC_KC - 1) / TC_KC;          // reduction chunks (32 elements each) of a full tile
+    // Block skipping: a chunk whose offsets have no valid neighbour in any of the tile's 128 rows contributes exact
+    // zeros, so neither the gather nor the MMAs are issued for it.  The index loader publishes, per tile, the ordered
+    // list of active chunks; producers, weight loads and the MMA issuer all walk that list (stage counts per tile vary).
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(nbr_s + 2 * TC_BM * K);   // [2][T]
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -253,7 +269,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             mbar_init(&tmem_full[b], 1);           // one tcgen05.commit
             mbar_init(&tmem_empty[b], 128);        // the 128 epilogue threads
             mbar_init(&nbr_full[b], 1);            // the index loader (+ tx bytes)
-            mbar_init(&nbr_empty[b], NPW * 32);    // every producer thread
+            mbar_init(&nbr_empty[b], NPW * 32 + 1);   // every producer thread + the MMA issuer
+            mbar_init(&list_full[b], 1);           // the index loader, after it built the chunk list
         }
         fence_mbar_init();
     }
@@ -280,24 +297,47 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         const uint32_t rowbytes = (uint32_t)c_in * 4u;
         const int strideK4 = 4 * K;                 // index-tile stride between rows r and r + 4
         const char* fbase = reinterpret_cast<const char*>(feat_in);
-        // position of the next stage to ISSUE: tile i_tl, stage i_j within the tile; this lane's 4-float piece of the
-        // stage covers flattened elements e = 32*i_j + 4*q .. +3  ->  offset i_k = e / c_in, channel i_ch = e % c_in
-        // (c_in % 4 == 0, so a piece never straddles two offsets).  Advanced by two global stages per step.
-        const int step_k = (32 * G) / c_in, step_ch = 32 * G - step_k * c_in;   // G stages per step
-        int i_tl = group / T, i_j = group - i_tl * T;
-        int i_k = (i_j * TC_KC + q * 4) / c_in, i_ch = (i_j * TC_KC + q * 4) - i_k * c_in;
-        int cur_tile = -1;                          // tile whose index block this thread currently reads
-        int rows_left = 0;
-        auto issue = [&](int slot) {
-            if (i_tl != cur_tile) {                 // moved on to the next tile's index block
-                if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);
-                cur_tile = i_tl;
-                mbar_wait(&nbr_full[i_tl & 1], (i_tl >> 1) & 1);
-                rows_left = n - (((int)blockIdx.x + i_tl * (int)gridDim.x) * TC_BM + quarter * 32);
+        // Issue-side iterator over the global stage sequence (tile, position in the tile's active-chunk list); this
+        // group owns the stages whose global index is congruent to `group` modulo G.
+        const uint32_t magic = 0xFFFFFFFFu / (uint32_t)c_in + 1u;   // e / c_in == umulhi(e, magic) for e * c_in < 2^32
+        int it_tile = 0, it_pos = group, cur_tile = -1, cur_cnt = 0, rows_left = 0;
+        bool it_done = false;
+        int inflight = 0;
+        unsigned long long fifo = 0;                // chunk ids of the stages in flight, 16 bits each, oldest lowest
+        // Position the iterator on this group's next stage.  Every tile's index buffer is acquired and released exactly
+        // once per thread.  A warp that still has gathers in flight must never BLOCK on a later tile's list: the MMA
+        // issuer may be waiting for exactly those stages before it can release the buffer the list needs (groups that
+        // own no stage in two consecutive sparse tiles would deadlock) — so with may_block == false an unpublished
+        // list makes this return false and the caller drains a stage first.
+        auto locate = [&](bool may_block) -> bool {
+            while (true) {
+                if (it_tile >= my_tiles) { it_done = true; return false; }
+                if (cur_tile != it_tile) {
+                    uint64_t* bar = &list_full[it_tile & 1];
+                    const uint32_t par = (uint32_t)(it_tile >> 1) & 1u;
+                    if (!may_block && !__any_sync(0xffffffffu, mbar_test(bar, par))) return false;
+                    mbar_wait(bar, par);
+                    cur_tile = it_tile;
+                    cur_cnt = s_cnt[it_tile & 1];
+                    rows_left = n - (((int)blockIdx.x + it_tile * (int)gridDim.x) * TC_BM + quarter * 32);
+                }
+                if (it_pos < cur_cnt) return true;
+                it_pos -= cur_cnt;
+                ++it_tile;
+                mbar_arrive(&nbr_empty[cur_tile & 1]);      // done with this tile's index block
+                cur_tile = -1;
             }
+        };
+        auto issue = [&](int slot) {
+            const int buf = it_tile & 1;
+            const uint32_t chunk = s_list[buf * T + it_pos];
+            // this lane's 4-float piece covers flattened elements e .. e+3 -> offset i_k = e / c_in, channel e % c_in
+            // (c_in % 4 == 0, so a piece never straddles two offsets)
+            const uint32_t e = chunk * TC_KC + (uint32_t)q * 4u;
+            const int i_k = (int)__umulhi(e, magic);
+            const uint32_t colbytes = (e - (uint32_t)i_k * (uint32_t)c_in) * 4u;
             const bool col_ok = i_k < K;            // beyond the end of the reduction axis: zero fill
-            const uint32_t colbytes = (uint32_t)i_ch * 4u;
-            const int* nb = nbr_s + (i_tl & 1) * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0);
+            const int* nb = nbr_s + buf * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0);
             const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -308,28 +348,31 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
             }
             cp_async_commit();
-            // advance G global stages (32*G reduction elements)
-            i_j += G;
-            if (i_j >= T) {                         // next tile(s): restart the reduction axis
-                do { i_j -= T; ++i_tl; } while (i_j >= T);
-                i_k = (i_j * TC_KC + q * 4) / c_in;
-                i_ch = (i_j * TC_KC + q * 4) - i_k * c_in;
-            } else {
-                i_k += step_k;
-                i_ch += step_ch;
-                if (i_ch >= c_in) { i_ch -= c_in; ++i_k; }
-            }
+            fifo |= (unsigned long long)chunk << (16 * inflight);
+            ++inflight;
+            it_pos += G;
         };
-        // this warp's stages: gi = group, group + 2, ...; local counter li
-        const int my_count = (total_stages - group + G - 1) / G;
-        for (int li = 0; li < TC_DEPTH - 1 && li < my_count; ++li) issue(li % TC_DEPTH);
         const uint32_t rd_base = abuf + (uint32_t)lane * 128u;
         const uint32_t x7 = (uint32_t)(lane & 7);
-        int s = group % STAGES, ph = 0, jpos = group % T, slot = 0;   // consume-side stage slot / phase / weight chunk
-        for (int li = 0; li < my_count; ++li) {
-            if (li + TC_DEPTH - 1 < my_count) issue((li + TC_DEPTH - 1) % TC_DEPTH);
-            else cp_async_commit();                // keep the group count uniform for wait_group
-            cp_async_wait<TC_DEPTH - 1>();
+        int s = group % STAGES, ph = 0, slot = 0, islot = 0;   // consume-side stage slot / phase, staging slots
+        bool located = false;
+        while (true) {
+            // issue ahead: up to TC_DEPTH gathers in flight, never blocking while some are
+            while (!it_done && inflight < TC_DEPTH) {
+                if (!located) located = locate(inflight == 0);
+                if (!located) break;
+                issue(islot);
+                if (++islot == TC_DEPTH) islot = 0;
+                located = false;
+            }
+            if (inflight == 0) break;              // iterator exhausted and everything drained
+            const uint32_t chunk = (uint32_t)(fifo & 0xFFFFull);
+            fifo >>= 16;
+            --inflight;                            // = committed groups allowed to stay pending
+            if (inflight == 0) cp_async_wait<0>();
+            else if (inflight == 1) cp_async_wait<1>();
+            else if (inflight == 2) cp_async_wait<2>();
+            else cp_async_wait<3>();
             __syncwarp();
             float4 v[8];
 #pragma unroll
@@ -343,7 +386,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             if ((tid & 127) == 0) {
                 unsigned char* st = stages + s * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], 2 * B_BYTES);
-                bulk_copy_g2s(st, (const char*)packed_w + (int64_t)jpos * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
+                bulk_copy_g2s(st, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
             }
             // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
             // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
@@ -372,10 +415,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             mbar_arrive(&full_bar[s]);
             // advance the consume-side counters by two global stages
             s += G; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
-            jpos += G; while (jpos >= T) jpos -= T;
             if (++slot == TC_DEPTH) slot = 0;
         }
-        if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);
+        if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);   // (not reached: the iterator releases as it leaves)
     } else if (warp == TC_MMA_WARP) {
         // ================= MMA issuer =================
         // The whole warp runs the loop in warp-uniform control flow and one ELECTed lane issues: a divergent
@@ -387,7 +429,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-            for (int j = 0; j < T; ++j, ++gi) {
+            mbar_wait(&list_full[buf], (tl >> 1) & 1);
+            const int cnt = s_cnt[buf];
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&nbr_empty[buf]);
+            for (int j = 0; j < cnt; ++j, ++gi) {
                 const int s = gi % STAGES;
                 const uint32_t ph = (gi / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
@@ -412,15 +458,15 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             __syncwarp();
         }
     } else if (warp == TC_IDX_WARP) {
-        // ================= index loader: TMA-stage each tile's neighbour block =================
-        if (lane == 0) {
-            for (int tl = 0; tl < my_tiles; ++tl) {
-                const int buf = tl & 1;
+        // ================= index loader: TMA-stage each tile's neighbour block, publish its active chunks ==========
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int buf = tl & 1;
+            const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM;
+            int* dst = nbr_s + buf * TC_BM * K;
+            if (lane == 0) {
                 mbar_wait(&nbr_empty[buf], ((tl >> 1) & 1) ^ 1);
-                const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM;
                 const int rows = n_cap - row0 < TC_BM ? n_cap - row0 : TC_BM;
                 const uint32_t bytes = (uint32_t)rows * K * 4, bulk = bytes & ~15u;
-                int* dst = nbr_s + buf * TC_BM * K;
                 const int* src = table + (int64_t)row0 * K;
                 if (bulk) {
                     mbar_expect_tx(&nbr_full[buf], bulk);
@@ -429,8 +475,42 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 for (uint32_t e = bulk / 4; e < bytes / 4; ++e) dst[e] = __ldg(src + e);   // < 16-byte tail
                 mbar_arrive(&nbr_full[buf]);
             }
+            __syncwarp();
+            mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
+            // offsets with at least one valid neighbour among the tile's live rows
+            const int rows_live = n - row0 < TC_BM ? n - row0 : TC_BM;
+            unsigned long long m = 0;
+            for (int r = lane; r < rows_live; r += 32) {
+                const int* rp = dst + r * K;
+                for (int k = 0; k < K; ++k) m |= (unsigned long long)(rp[k] >= 0) << k;
+            }
+            const uint32_t m_lo = __reduce_or_sync(0xffffffffu, (uint32_t)m);
+            const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
+            m = (unsigned long long)m_lo | ((unsigned long long)m_hi << 32);
+            int cnt = 0;
+            for (int c0 = 0; c0 < T; c0 += 32) {
+                const int c = c0 + lane;
+                bool act = false;
+                if (c < T) {
+                    const int k_lo = (c * TC_KC) / c_in;
+                    int k_hi = (c * TC_KC + TC_KC - 1) / c_in;
+                    if (k_hi > K - 1) k_hi = K - 1;
+                    const int span = k_hi - k_lo + 1;
+                    const unsigned long long bits = (span >= 64 ? ~0ull : ((1ull << span) - 1ull)) << k_lo;
+                    act = (m & bits) != 0ull;
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, act);
+                if (act) s_list[buf * T + cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned short)c;
+                cnt += __popc(b);
+            }
+            if (cnt == 0) {                          // cannot happen for a well-formed rulebook; keep the pipeline alive
+                if (lane == 0) s_list[buf * T] = 0;
+                cnt = 1;
+            }
+            if (lane == 0) s_cnt[buf] = cnt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&list_full[buf]);
         }
-        __syncwarp();
     } else if (warp >= Roles::kEpi0 && warp < Roles::kEpi0 + 4) {
         // ================= epilogue =================
         const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
@@ -438,7 +518,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             const int buf = tl & 1;
             mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
             tc_fence_after();
-            const int row = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM + quarter * 32 + lane;
+            const int slot_row = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM + quarter * 32 + lane;
+            // sorted rulebooks (btc_rulebook_sort_rows) process rows in mask order and scatter to the original rows
+            const int row = slot_row < n ? (out_rows ? __ldg(out_rows + slot_row) : slot_row) : n;
             float* dst = feat_out + (int64_t)row * c_out;
 #pragma unroll 1
             for (int c0 = 0; c0 < N; c0 += 16) {
@@ -481,11 +563,12 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 
 template <int N, int NPW>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
-                         const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
-                         int K, int c_in, int c_out, cudaStream_t st) {
+                         const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
+                         const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * N * 128;
+    const int T = (K * c_in + TC_KC - 1) / TC_KC;
     size_t smem = (size_t)TC_STAGES * STAGE_BYTES + (size_t)NPW * TcDepth<N, NPW>::value * 4096 +
-                  (size_t)2 * TC_BM * K * sizeof(int) + 1024 + 16;
+                  (size_t)2 * TC_BM * K * sizeof(int) + (size_t)((4 * T + 15) & ~15) + 1024 + 16;
     auto kern = conv_fwd_tc_kernel<N, NPW>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
@@ -494,8 +577,8 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
     }
     int tiles = (n_cap + TC_BM - 1) / TC_BM;
     dim3 grid(tiles < kNumSM ? tiles : kNumSM);    // persistent: one CTA per SM
-    kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap,
-                                                     n_dev, K, c_in, c_out);
+    kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
+                                                     n_cap, n_dev, K, c_in, c_out);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
@@ -503,17 +586,18 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
 // 16 producer warps (four groups) when shared memory allows (N <= 64); BTC_TC_NPW=8 forces the 8-warp variant (A/B).
 template <int N>
 static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
-                     const float* scale, const float* shift, int relu, float* feat_out, int n_cap, const int* n_dev,
-                     int K, int c_in, int c_out, cudaStream_t st) {
+                     const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
+                     const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
     static int npw = 0;
     if (npw == 0) {
         const char* e = getenv("BTC_TC_NPW");
         npw = (e && atoi(e) == 8) ? 8 : 16;
     }
     if (N <= 64 && npw == 16)
-        return launch_tc_npw<(N <= 64 ? N : 64), 16>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap, n_dev, K,
-                                                     c_in, c_out, st);
-    return launch_tc_npw<N, 8>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, n_cap, n_dev, K, c_in, c_out, st);
+        return launch_tc_npw<(N <= 64 ? N : 64), 16>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
+                                                     n_dev, K, c_in, c_out, st);
+    return launch_tc_npw<N, 8>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in,
+                               c_out, st);
 }
 
 static int tc_padded_n(int c_out) {
@@ -552,9 +636,10 @@ int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, voi
     return BTC_OK;
 }
 
-int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
-                           const float* scale, const float* shift, int relu, float* feat_out, int n_out_cap,
-                           const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
+static int fwd_tc(const char* who, const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
+                  const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_out_cap,
+                  const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
+    (void)who;
     if (!nbr_out || !packed_weight || !feat_out) return badarg("btc_sparse_conv_fwd_tc: null argument");
     if ((scale == nullptr) != (shift == nullptr)) return badarg("btc_sparse_conv_fwd_tc: scale/shift must come together");
     if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_fwd_tc: shape not supported", cudaSuccess);
@@ -565,11 +650,26 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
     cudaStream_t st = (cudaStream_t)stream;
     const float* pw = (const float*)packed_weight;
     switch (tc_padded_n(c_out)) {
-        case 32: return launch_tc<32>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 64: return launch_tc<64>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 128: return launch_tc<128>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 32: return launch_tc<32>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 64: return launch_tc<64>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 128: return launch_tc<128>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st);
     }
     return BTC_E_UNSUPPORTED;
+}
+
+int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
+                           const float* scale, const float* shift, int relu, float* feat_out, int n_out_cap,
+                           const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
+    return fwd_tc("btc_sparse_conv_fwd_tc", feat_in, nbr_out, packed_weight, bias, scale, shift, relu, feat_out, nullptr,
+                  n_out_cap, n_out_dev, K, c_in, c_out, stream);
+}
+
+int btc_sparse_conv_fwd_tc_rows(const float* feat_in, const int* nbr_sorted, const int* out_rows, const void* packed_weight,
+                                const float* bias, const float* scale, const float* shift, int relu, float* feat_out,
+                                int n_out_cap, const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
+    if (!out_rows) return badarg("btc_sparse_conv_fwd_tc_rows: null out_rows");
+    return fwd_tc("btc_sparse_conv_fwd_tc_rows", feat_in, nbr_sorted, packed_weight, bias, scale, shift, relu, feat_out, out_rows,
+                  n_out_cap, n_out_dev, K, c_in, c_out, stream);
 }
 
 }  // extern "C"

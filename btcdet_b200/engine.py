@@ -39,7 +39,7 @@ class _Level:
 
 @dataclass
 class _Step:
-    kind: str            # "hash_build" | "subm_rb" | "conv_rb" | "conv"
+    kind: str            # "hash_build" | "subm_rb" | "conv_rb" | "sort_rb" | "conv"
     args: tuple
 
 
@@ -58,7 +58,7 @@ class BackbonePlan:
     """
 
     def __init__(self, layer_specs, sparse_shape, batch, max_points_total, voxel_size, point_range, max_points=5,
-                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True):
+                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.batch = int(batch)
@@ -68,6 +68,8 @@ class BackbonePlan:
         self.n_cap = int(max_points_total)
         self.algo = int(algo)
         self.use_graph = use_graph
+        self.sort_rows = bool(sort_rows)   # mask-sorted tables for the block-skipping tensor-core tile
+        self._sorted = {}
         dev = self.device
         B = self.batch
         # ---- static input + voxelisation buffers ------------------------------------------
@@ -132,8 +134,15 @@ class BackbonePlan:
             if self.algo != 1 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
                 packed = ops.tc_pack_weight(w)
             self.params.append((w, bias, scale, shift, packed))
+            rows = None
+            if packed is not None and self.sort_rows:
+                rows = self._sorted.get(id(nbr))
+                if rows is None:
+                    rows = (torch.empty_like(nbr), torch.empty(nbr.shape[0], dtype=torch.int32, device=dev))
+                    self._sorted[id(nbr)] = rows
+                    self.steps.append(_Step("sort_rb", (nbr, out_lvl, rows[0], rows[1])))
             self.steps.append(_Step("conv", (cur_feat, nbr, w, bias, scale, shift, bn is not None, out_feat, out_lvl, K,
-                                             conv.in_channels, conv.out_channels, packed)))
+                                             conv.in_channels, conv.out_channels, packed, rows)))
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
         self.graph = None
@@ -217,6 +226,11 @@ class BackbonePlan:
                                                 _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
                           "btc_rulebook_conv")
                     launches += 8
+                elif s.kind == "sort_rb":
+                    nbr, lvl, nbr_sorted, out_rows = s.args
+                    check(lib.btc_rulebook_sort_rows(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(nbr_sorted),
+                                                     _ptr(out_rows), st), "btc_rulebook_sort_rows")
+                    launches += 1
                 last_rb_event = torch.cuda.Event()
                 last_rb_event.record(side)
         # pass 2: the convolution chain on the main stream, each layer behind its rulebook's event
@@ -236,8 +250,12 @@ class BackbonePlan:
 
     def launch_conv(self, args, st):
         """One sparse-conv layer: tcgen05 tile when the weights were packed, fp32 FFMA tile otherwise."""
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed = args
-        if packed is not None:
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = args
+        if packed is not None and rows is not None:
+            check(self.lib.btc_sparse_conv_fwd_tc_rows(_ptr(fin), _ptr(rows[0]), _ptr(rows[1]), _ptr(packed), _ptr(bias),
+                                                       _ptr(scale), _ptr(shift), int(relu), _ptr(fout), lout.cap,
+                                                       _ptr(lout.n_dev), K, cin, cout, st), "btc_sparse_conv_fwd_tc_rows")
+        elif packed is not None:
             check(self.lib.btc_sparse_conv_fwd_tc(_ptr(fin), _ptr(nbr), _ptr(packed), _ptr(bias), _ptr(scale),
                                                   _ptr(shift), int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K,
                                                   cin, cout, st), "btc_sparse_conv_fwd_tc")

@@ -125,6 +125,14 @@ class Rulebook:
     transposed: bool = False
     out_index: Optional[CoordIndex] = None
     _pairs: Optional[tuple] = field(default=None, repr=False)
+    _sorted: Optional[tuple] = field(default=None, repr=False)
+
+    def sorted_rows(self):
+        """(nbr_sorted, out_rows): the output-stationary table with rows reordered by valid-offset mask inside
+        windows of 2048 rows — what the block-skipping tcgen05 tile consumes (computed once per rulebook)."""
+        if self._sorted is None:
+            self._sorted = rulebook_sort_rows(self.nbr_out)
+        return self._sorted
 
     def inverse(self) -> "Rulebook":
         """Rulebook of SparseInverseConv3d: swap the pair directions."""
@@ -272,9 +280,24 @@ def tc_pack_weight(weight):
     return packed
 
 
+def rulebook_sort_rows(nbr_out, n_out_dev=None, out=None):
+    """btc_rulebook_sort_rows: rows of nbr_out reordered by valid-offset mask within 2048-row windows.
+    Returns (nbr_sorted [N_out, K], out_rows [N_out]); row i of nbr_sorted is row out_rows[i] of nbr_out."""
+    _require_cuda(nbr_out)
+    lib = _lib.load()
+    nbr_out = nbr_out.contiguous()
+    n_out, K = nbr_out.shape
+    nbr_sorted, out_rows = out if out is not None else (torch.empty_like(nbr_out),
+                                                        torch.empty(n_out, dtype=torch.int32, device=nbr_out.device))
+    check(lib.btc_rulebook_sort_rows(_ptr(nbr_out), n_out, _ptr(n_out_dev), K, _ptr(nbr_sorted), _ptr(out_rows), _stream()),
+          "btc_rulebook_sort_rows")
+    return nbr_sorted, out_rows
+
+
 def sparse_conv_fwd_tc(features, nbr_out, packed_weight, c_in, c_out, bias=None, scale=None, shift=None, relu=False,
-                       n_out_dev=None, out=None):
-    """tcgen05 3xTF32 gather-GEMM; same contract as sparse_conv_fwd with pre-packed weights."""
+                       n_out_dev=None, out=None, out_rows=None):
+    """tcgen05 3xTF32 gather-GEMM; same contract as sparse_conv_fwd with pre-packed weights.  With `out_rows`,
+    `nbr_out` is a mask-sorted table (rulebook_sort_rows) and row i's result goes to out[out_rows[i]]."""
     _require_cuda(features, nbr_out, packed_weight)
     lib = _lib.load()
     n_out, K = nbr_out.shape
@@ -282,6 +305,11 @@ def sparse_conv_fwd_tc(features, nbr_out, packed_weight, c_in, c_out, bias=None,
     assert features.dtype == torch.float32 and features.shape[1] == c_in
     if out is None:
         out = torch.empty((n_out, c_out), dtype=torch.float32, device=features.device)
+    if out_rows is not None:
+        check(lib.btc_sparse_conv_fwd_tc_rows(_ptr(features), _ptr(nbr_out), _ptr(out_rows), _ptr(packed_weight), _ptr(bias),
+                                              _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(out), n_out, _ptr(n_out_dev),
+                                              K, int(c_in), int(c_out), _stream()), "btc_sparse_conv_fwd_tc_rows")
+        return out
     check(lib.btc_sparse_conv_fwd_tc(_ptr(features), _ptr(nbr_out), _ptr(packed_weight), _ptr(bias), _ptr(scale),
                                      _ptr(shift), int(bool(relu)), _ptr(out), n_out, _ptr(n_out_dev), K, int(c_in),
                                      int(c_out), _stream()), "btc_sparse_conv_fwd_tc")
@@ -345,7 +373,9 @@ class SparseConvFunction(torch.autograd.Function):
             raise _lib.BtcError("tensor-core tile requested for an unsupported shape (K=%d Cin=%d Cout=%d)" %
                                 (rulebook.K, c_in, c_out))
         if use_tc:
-            out = sparse_conv_fwd_tc(features.contiguous(), rulebook.nbr_out, _packed_weight(weight), c_in, c_out, bias)
+            nbr_sorted, out_rows = rulebook.sorted_rows()
+            out = sparse_conv_fwd_tc(features.contiguous(), nbr_sorted, _packed_weight(weight), c_in, c_out, bias,
+                                     out_rows=out_rows)
         else:
             out = sparse_conv_fwd(features, rulebook.nbr_out, weight, bias, algo=1)
         ctx.save_for_backward(features, weight)

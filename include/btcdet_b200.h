@@ -242,6 +242,22 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
                            const float* bias, const float* scale, const float* shift, int relu,
                            float* feat_out, int n_out_cap, const int* n_out_dev,
                            int K, int c_in, int c_out, void* stream);
+/*
+ * Block skipping: per 128-row tile the kernel only gathers / multiplies the reduction chunks whose kernel offsets
+ * have a valid neighbour in at least one row (the others contribute exact zeros).  btc_rulebook_sort_rows makes
+ * that effective: it reorders the rows of an output-stationary table inside windows of 2048 rows by their
+ * valid-offset bit mask (stable), so rows with the same neighbourhood pattern share tiles.
+ *   nbr_out [n_cap, K] -> nbr_sorted [n_cap, K] (row i of the sorted table = row out_rows[i] of the input),
+ *   out_rows [n_cap] i32.  K <= 64.  No workspace, one launch.
+ * btc_sparse_conv_fwd_tc_rows consumes the sorted table and writes row i's result to feat_out[out_rows[i]]:
+ * same results as btc_sparse_conv_fwd_tc on the unsorted table, bit for bit (per-row arithmetic is unchanged).
+ */
+int btc_rulebook_sort_rows(const int* nbr_out, int n_cap, const int* n_dev, int K, int* nbr_sorted, int* out_rows,
+                           void* stream);
+int btc_sparse_conv_fwd_tc_rows(const float* feat_in, const int* nbr_sorted, const int* out_rows,
+                                const void* packed_weight, const float* bias, const float* scale,
+                                const float* shift, int relu, float* feat_out, int n_out_cap,
+                                const int* n_out_dev, int K, int c_in, int c_out, void* stream);
 
 /*
  * d feat_in [n_in_cap, c_in] = sum_k d_out[nbr_in[i][k]] @ W[k]^T.

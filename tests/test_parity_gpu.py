@@ -227,6 +227,71 @@ def test_tensor_core_conv_within_tolerance(cuda, oracle, cin, cout, kind):
     assert rel_err(out2.cpu().numpy(), np.maximum(ref * scale + shift, 0)) < REL_TOL
     ffma = ops.sparse_conv_fwd(f, rb.nbr_out, wt, torch.from_numpy(bias).cuda(), algo=1)
     assert rel_err(out.cpu().numpy(), ffma.cpu().numpy()) < 2e-5
+    # mask-sorted rows (block skipping): per-row arithmetic is unchanged -> bit-identical results
+    nbr_sorted, out_rows = rb.sorted_rows()
+    out3 = ops.sparse_conv_fwd_tc(f, nbr_sorted, packed, cin, cout, torch.from_numpy(bias).cuda(), out_rows=out_rows)
+    assert torch.equal(out3, out)
+
+
+@pytest.mark.parametrize("n_out,K,cin,cout,density,run", [
+    (30000, 27, 64, 64, 0.35, 97), (45000, 27, 16, 32, 0.08, 97), (20000, 3, 64, 128, 0.45, 97), (52000, 27, 4, 16, 0.13, 97),
+    (19000, 8, 32, 32, 0.5, 97), (300, 27, 32, 32, 0.02, 97),
+    # one or two active chunks per tile, several tiles per CTA: producer groups own no stage in consecutive tiles
+    # (regression: a producer blocking on a later tile's chunk list while holding gathers in flight deadlocked)
+    (70000, 27, 4, 16, 0.03, 1024), (70000, 27, 16, 16, 0.03, 1024), (60000, 27, 32, 32, 0.02, 640)])
+def test_tensor_core_multi_tile_persistent(cuda, n_out, K, cin, cout, density, run):
+    """More tiles than SMs (each persistent CTA walks several tiles, variable active-chunk counts per tile), capacity
+    larger than the live count, clustered neighbourhood patterns: tcgen05 tile == FFMA tile within 2e-5, and the
+    mask-sorted table gives bit-identical rows."""
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(n_out + K)
+    n_in = 40000
+    pat = rng.random((64, K)) < density
+    valid = pat[(np.arange(n_out) // run) % 64] ^ (rng.random((n_out, K)) < 0.01)   # runs of equal patterns + noise
+    valid[:, K // 2] |= ~valid.any(1)
+    nbr = np.where(valid, rng.integers(0, n_in, (n_out, K)), -1).astype(np.int32)
+    cap = n_out + 1000
+    table = torch.full((cap, K), 123456789, dtype=torch.int32, device="cuda")     # garbage past the live rows
+    table[:n_out] = torch.from_numpy(nbr).cuda()
+    n_dev = torch.tensor([n_out], dtype=torch.int32, device="cuda")
+    feat = torch.from_numpy(rng.standard_normal((n_in, cin)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).cuda()
+    packed = ops.tc_pack_weight(w)
+    ffma = ops.sparse_conv_fwd(feat, table[:n_out].contiguous(), w, bias, algo=1)
+    out = torch.zeros((cap, cout), device="cuda")
+    ops.sparse_conv_fwd_tc(feat, table, packed, cin, cout, bias, n_out_dev=n_dev, out=out)
+    torch.cuda.synchronize()
+    assert rel_err(out[:n_out].cpu().numpy(), ffma.cpu().numpy()) < 2e-5
+    assert float(out[n_out:].abs().sum()) == 0.0                                   # rows past the live count untouched
+    nbr_sorted, out_rows = ops.rulebook_sort_rows(table, n_out_dev=n_dev)
+    out2 = torch.zeros((cap, cout), device="cuda")
+    ops.sparse_conv_fwd_tc(feat, nbr_sorted, packed, cin, cout, bias, n_out_dev=n_dev, out=out2, out_rows=out_rows)
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("n,K", [(1, 27), (127, 27), (2048, 27), (2049, 8), (9000, 27), (5000, 64), (3000, 3), (4100, 33)])
+def test_rulebook_sort_rows(cuda, n, K):
+    """btc_rulebook_sort_rows: a permutation inside 2048-row windows, ordered by (valid-offset mask, original row)."""
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(n * 100 + K)
+    pat = rng.integers(0, 2, (40, K))                            # few distinct neighbourhood patterns + noise
+    valid = pat[rng.integers(0, 40, n)] ^ (rng.random((n, K)) < 0.02)
+    nbr = np.where(valid, rng.integers(0, 100000, (n, K)), -1).astype(np.int32)
+    cap = n + 37                                                 # capacity larger than the live count
+    buf = np.full((cap, K), 7, np.int32)
+    buf[:n] = nbr
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    nbr_sorted, out_rows = ops.rulebook_sort_rows(torch.from_numpy(buf).cuda(), n_out_dev=n_dev)
+    rows = out_rows[:n].cpu().numpy()
+    got = nbr_sorted[:n].cpu().numpy()
+    np.testing.assert_array_equal(got, nbr[rows])
+    mask = [int(sum(1 << k for k in range(K) if nbr[r, k] >= 0)) for r in range(n)]
+    for w0 in range(0, n, 2048):
+        w = rows[w0:w0 + 2048]
+        assert sorted(w.tolist()) == list(range(w0, min(w0 + 2048, n)))
+        keys = [(mask[r], r) for r in w]
+        assert keys == sorted(keys)
 
 
 def test_config1_golden(cuda, oracle):
