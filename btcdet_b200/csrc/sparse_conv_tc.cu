@@ -59,6 +59,37 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
         : "memory");
     return done != 0;
 }
+// raw shared-window addresses (computed once per role: &bar -> cvta + cluster-window math is not free in a hot loop)
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+// explicit shared-space loads: pointers derived from the aligned dynamic-smem base lose their address space and
+// compile to generic LD.E (long-scoreboard latency, plus padding instructions in front of every LDGSTS)
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (uint32_t)v;
+}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -217,7 +248,13 @@ template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int N, int NPW>
+// CAT: the hi and lo weight tiles of a stage are adjacent in shared memory, i.e. one K-major tile of 2N rows, so
+// A_hi x [B_hi | B_lo] is ONE MMA of width 2N into two accumulator column blocks (D1 | D2) and the 3xTF32 step is two
+// instructions (A_hi x [B_hi|B_lo], A_lo x B_hi -> D1) instead of three; the epilogue adds D1 + D2.  Same tensor-pipe
+// cycles, a third fewer instructions and half the descriptors on the single issuing thread, which the round-1 source-
+// level profile showed to be the critical path (~100 instructions, ~800 cycles per stage against 384 cycles of MMA).
+// Needs 4N + 64*STAGES <= 512 TMEM columns: N <= 64.
+template <int N, int NPW, bool CAT>
 __global__ void __launch_bounds__(TcRoles<NPW>::kThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
@@ -233,10 +270,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = 512;
-    constexpr uint32_t A_COL0 = 2 * N;            // first A-operand column
+    constexpr uint32_t ACC_COLS = CAT ? 2 * N : N;   // TMEM columns of one accumulator buffer
+    constexpr uint32_t A_COL0 = 2 * ACC_COLS;     // first A-operand column
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    static_assert(2 * N + 64 * STAGES <= 512, "TMEM budget");
+    constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    static_assert(2 * ACC_COLS + 64 * STAGES <= 512, "TMEM budget");
+    static_assert(!CAT || 2 * N <= 256, "UMMA N limit");
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* stages = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
@@ -290,6 +330,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         const int sub = lane >> 3, q = lane & 7;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t abuf = smem_u32(a_stage + warp * (TC_DEPTH * 4096));
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint32_t nbr_s32 = smem_u32(nbr_s), list_s32 = smem_u32(s_list);
         // Lane constants (the issue path is instruction-bound: keep the per-copy address math to a few ops).
         // Row r = g*4 + sub of the warp's 32 rows goes to r*128 + ((q ^ (r & 7)) << 4); (r & 7) = (g & 1)*4 + sub.
         const uint32_t dst_even = sub * 128 + ((q ^ sub) << 4);
@@ -330,18 +372,18 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         };
         auto issue = [&](int slot) {
             const int buf = it_tile & 1;
-            const uint32_t chunk = s_list[buf * T + it_pos];
+            const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + it_pos));
             // this lane's 4-float piece covers flattened elements e .. e+3 -> offset i_k = e / c_in, channel e % c_in
             // (c_in % 4 == 0, so a piece never straddles two offsets)
             const uint32_t e = chunk * TC_KC + (uint32_t)q * 4u;
             const int i_k = (int)__umulhi(e, magic);
             const uint32_t colbytes = (e - (uint32_t)i_k * (uint32_t)c_in) * 4u;
             const bool col_ok = i_k < K;            // beyond the end of the reduction axis: zero fill
-            const int* nb = nbr_s + buf * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0);
+            const uint32_t nb = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0));
             const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const int src = nb[g * strideK4];
+                const int src = lds_i32(nb + 4u * (uint32_t)(g * strideK4));
                 const bool ok = col_ok && (g * 4 + sub) < rows_left && src >= 0;
                 const uint32_t off = ok ? (uint32_t)src * rowbytes + colbytes : 0u;
                 const uint32_t dst = dbase + (uint32_t)(g * 512) + ((g & 1) ? dst_odd : dst_even);
@@ -381,7 +423,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(a));
             }
             __syncwarp();                          // everyone has read the slot before it is refilled
-            mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
+            mbar_wait_a(empty0 + 8u * (uint32_t)s, (uint32_t)(ph ^ 1));
             tc_fence_after();
             if ((tid & 127) == 0) {
                 unsigned char* st = stages + s * STAGE_BYTES;
@@ -412,7 +454,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&full_bar[s]);
+            mbar_arrive_a(full0 + 8u * (uint32_t)s);
             // advance the consume-side counters by two global stages
             s += G; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
             if (++slot == TC_DEPTH) slot = 0;
@@ -423,36 +465,47 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // The whole warp runs the loop in warp-uniform control flow and one ELECTed lane issues: a divergent
         // `if (lane == 0)` makes the compiler wrap every UTCHMMA in a serialisation loop (~100 cycles per MMA
         // instead of the 32-cycle M*N/256 floor measured with tools/mma_rate.cu).
-        int gi = 0;
+        // The issue loop is a dependent chain on one thread: stage slot / phase are running counters, barrier addresses
+        // and the descriptor words are hoisted, and a stage's descriptors differ from the base only by an add on the
+        // 14-bit start-address field (no carry: shared addresses < 256 KB).
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint64_t desc0 = make_desc_sw128(smem_u32(stages));
+        const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo0 = (uint32_t)desc0;
+        uint32_t s = 0, ph = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int buf = tl & 1;
             mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
             mbar_wait(&list_full[buf], (tl >> 1) & 1);
             const int cnt = s_cnt[buf];
             __syncwarp();
             if (elect_one()) mbar_arrive(&nbr_empty[buf]);
-            for (int j = 0; j < cnt; ++j, ++gi) {
-                const int s = gi % STAGES;
-                const uint32_t ph = (gi / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            for (int j = 0; j < cnt; ++j) {
+                mbar_wait_a(full0 + 8u * s, ph);
                 tc_fence_after();
-                const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(s * 64);
-                const uint32_t a_lo = a_hi + 32;
-                const uint32_t b_hi = smem_u32(stages + s * STAGE_BYTES);
-                const uint32_t b_lo = b_hi + B_BYTES;
                 if (elect_one()) {
+                    const uint32_t a_hi = tmem_base + A_COL0 + s * 64u;
+                    const uint32_t a_lo = a_hi + 32u;
+                    const uint32_t dl = desc_lo0 + s * (uint32_t)(STAGE_BYTES >> 4);
 #pragma unroll
                     for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
-                        const uint64_t db_hi = make_desc_sw128(b_hi + kk * 32), db_lo = make_desc_sw128(b_lo + kk * 32);
-                        umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, (j | kk) != 0);   // small terms first
-                        umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
-                        umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
+                        const uint64_t db_hi = desc_hi64 | (uint64_t)(dl + 2u * (uint32_t)kk);
+                        if (CAT) {
+                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC2, (j | kk) != 0);   // D1 | D2
+                            umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, 1u);                // D1
+                        } else {
+                            const uint64_t db_lo = desc_hi64 | (uint64_t)(dl + (uint32_t)(B_BYTES >> 4) + 2u * (uint32_t)kk);
+                            umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, (j | kk) != 0);   // small terms first
+                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
+                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
+                        }
                     }
-                    umma_commit(&empty_bar[s]);      // frees the stage once the MMAs above retire
+                    umma_commit_a(empty0 + 8u * s);      // frees the stage once the MMAs above retire
                 }
                 __syncwarp();
+                if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
             }
             if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
             __syncwarp();
@@ -525,7 +578,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 #pragma unroll 1
             for (int c0 = 0; c0 < N; c0 += 16) {
                 uint32_t acc[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0), acc);
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * ACC_COLS + (uint32_t)c0, acc);
+                if (CAT) {                             // D = D1 + D2 (the A_hi x B_lo terms)
+                    uint32_t acc2[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * ACC_COLS + (uint32_t)(N + c0), acc2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
+                }
                 if (row < n && c0 < c_out) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -561,7 +620,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int N, int NPW>
+template <int N, int NPW, bool CAT>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
@@ -569,7 +628,7 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
     const int T = (K * c_in + TC_KC - 1) / TC_KC;
     size_t smem = (size_t)TC_STAGES * STAGE_BYTES + (size_t)NPW * TcDepth<N, NPW>::value * 4096 +
                   (size_t)2 * TC_BM * K * sizeof(int) + (size_t)((4 * T + 15) & ~15) + 1024 + 16;
-    auto kern = conv_fwd_tc_kernel<N, NPW>;
+    auto kern = conv_fwd_tc_kernel<N, NPW, CAT>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
@@ -583,21 +642,39 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
     return BTC_OK;
 }
 
-// 16 producer warps (four groups) when shared memory allows (N <= 64); BTC_TC_NPW=8 forces the 8-warp variant (A/B).
+// Tile variant knobs (A/B measurements and tests; defaults are the measured-best ones).  16 producer warps (four
+// groups) when shared memory allows (N <= 64), else 8; concatenated [B_hi|B_lo] MMAs when TMEM allows (N <= 64).
+// Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_CAT=0; btc_sparse_conv_tc_config() changes them at run time.
+static int g_tc_npw = 0, g_tc_cat = -1;
+static void tc_config_init() {
+    if (g_tc_npw == 0) {
+        const char* e = getenv("BTC_TC_NPW");
+        g_tc_npw = (e && atoi(e) == 8) ? 8 : 16;
+    }
+    if (g_tc_cat < 0) {
+        const char* e = getenv("BTC_TC_CAT");
+        g_tc_cat = (e && atoi(e) == 0) ? 0 : 1;
+    }
+}
+
 template <int N>
 static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                      const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                      const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
-    static int npw = 0;
-    if (npw == 0) {
-        const char* e = getenv("BTC_TC_NPW");
-        npw = (e && atoi(e) == 8) ? 8 : 16;
+    tc_config_init();
+    constexpr int NS = N <= 64 ? N : 64;   // instantiation guard for the N <= 64 only variants
+    if (N <= 64 && g_tc_npw == 16) {
+        if (g_tc_cat)
+            return launch_tc_npw<NS, 16, true>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
+                                               n_dev, K, c_in, c_out, st);
+        return launch_tc_npw<NS, 16, false>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
+                                            n_dev, K, c_in, c_out, st);
     }
-    if (N <= 64 && npw == 16)
-        return launch_tc_npw<(N <= 64 ? N : 64), 16>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
-                                                     n_dev, K, c_in, c_out, st);
-    return launch_tc_npw<N, 8>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in,
-                               c_out, st);
+    if (N <= 64 && g_tc_cat)
+        return launch_tc_npw<NS, 8, true>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev,
+                                          K, c_in, c_out, st);
+    return launch_tc_npw<N, 8, false>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K,
+                                      c_in, c_out, st);
 }
 
 static int tc_padded_n(int c_out) {
@@ -612,6 +689,16 @@ static int tc_padded_n(int c_out) {
 using namespace btc;
 
 extern "C" {
+
+int btc_sparse_conv_tc_config(int producer_warps, int concat_b) {
+    tc_config_init();
+    if (producer_warps >= 0) {
+        if (producer_warps != 8 && producer_warps != 16) return badarg("btc_sparse_conv_tc_config: producer_warps must be 8 or 16");
+        g_tc_npw = producer_warps;
+    }
+    if (concat_b >= 0) g_tc_cat = concat_b ? 1 : 0;
+    return BTC_OK;
+}
 
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out) {
     return (K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 4 && c_out % 4 == 0 && tc_padded_n(c_out) != 0 &&

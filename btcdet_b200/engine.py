@@ -182,15 +182,9 @@ class BackbonePlan:
         side.wait_stream(main)
         last_rb_event = None
         with torch.cuda.stream(side):
-            st = ctypes.c_void_p(side.cuda_stream)
-            check(lib.btc_voxelize(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
-                                   float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
-                                   self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
-                                   _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
-                                   self.vox_ws.numel(), st), "btc_voxelize")
+            launches += self.launch_voxelize(ctypes.c_void_p(side.cuda_stream))
             last_rb_event = torch.cuda.Event()
             last_rb_event.record(side)
-        launches += 9
         # pass 1: the whole rulebook chain on the side stream, one event per step
         conv_deps = []
         for s in self.steps:
@@ -198,39 +192,7 @@ class BackbonePlan:
                 conv_deps.append((s, last_rb_event))   # needs every rulebook step enqueued before it
                 continue
             with torch.cuda.stream(side):
-                st = ctypes.c_void_p(side.cuda_stream)
-                if s.kind == "hash_build":
-                    (lvl,) = s.args
-                    check(lib.btc_hash_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                             _ptr(lvl.hash_keys), _ptr(lvl.hash_vals), lvl.hash_keys.numel(), st),
-                          "btc_hash_build")
-                    launches += 1
-                elif s.kind == "subm_rb":
-                    lvl, ksize, dil, nbr = s.args
-                    if lvl.hash_keys is not None:
-                        check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                                         int3(ksize), int3(dil), _ptr(lvl.hash_keys), _ptr(lvl.hash_vals),
-                                                         lvl.hash_keys.numel(), _ptr(nbr), st), "btc_rulebook_subm_hash")
-                    else:
-                        check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
-                                                    int3(ksize), int3(dil), _ptr(lvl.index), lvl.index.numel(),
-                                                    _ptr(lvl.perm), _ptr(nbr), st), "btc_rulebook_subm")
-                    launches += 1
-                elif s.kind == "conv_rb":
-                    lin, lout, ksize, stride, pad, dil, nbr = s.args
-                    lout.index.zero_()
-                    ws = self._workspace(lib.btc_index_workspace_bytes(lout.index.numel()))
-                    check(lib.btc_rulebook_conv(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
-                                                int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
-                                                _ptr(lout.index), lout.index.numel(), _ptr(lout.coords), lout.cap,
-                                                _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
-                          "btc_rulebook_conv")
-                    launches += 8
-                elif s.kind == "sort_rb":
-                    nbr, lvl, nbr_sorted, out_rows = s.args
-                    check(lib.btc_rulebook_sort_rows(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(nbr_sorted),
-                                                     _ptr(out_rows), st), "btc_rulebook_sort_rows")
-                    launches += 1
+                launches += self.launch_index_step(s, ctypes.c_void_p(side.cuda_stream))
                 last_rb_event = torch.cuda.Event()
                 last_rb_event.record(side)
         # pass 2: the convolution chain on the main stream, each layer behind its rulebook's event
@@ -247,6 +209,55 @@ class BackbonePlan:
             self.dev_counts[i:i + 1].copy_(l.n_dev)
         self.launches_per_step = launches
         return launches
+
+    def launch_voxelize(self, st):
+        """points -> voxels / coords / counts / MeanVFE features of level 0 (9 launches)."""
+        lib, B, lvl0 = self.lib, self.batch, self.levels[0]
+        check(lib.btc_voxelize(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
+                               float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
+                               self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
+                               _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
+                               self.vox_ws.numel(), st), "btc_voxelize")
+        return 9
+
+    def launch_index_step(self, s, st):
+        """One step of the rulebook chain (hash build / neighbour table / mask sort) on stream `st`;
+        returns the number of kernel launches it enqueued.  Must be called with `st` as torch's current stream
+        (the bitmap clear of a strided level is a torch op)."""
+        lib, B = self.lib, self.batch
+        if s.kind == "hash_build":
+            (lvl,) = s.args
+            check(lib.btc_hash_build(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                     _ptr(lvl.hash_keys), _ptr(lvl.hash_vals), lvl.hash_keys.numel(), st),
+                  "btc_hash_build")
+            return 1
+        if s.kind == "subm_rb":
+            lvl, ksize, dil, nbr = s.args
+            if lvl.hash_keys is not None:
+                check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                                 int3(ksize), int3(dil), _ptr(lvl.hash_keys), _ptr(lvl.hash_vals),
+                                                 lvl.hash_keys.numel(), _ptr(nbr), st), "btc_rulebook_subm_hash")
+            else:
+                check(lib.btc_rulebook_subm(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                                            int3(ksize), int3(dil), _ptr(lvl.index), lvl.index.numel(),
+                                            _ptr(lvl.perm), _ptr(nbr), st), "btc_rulebook_subm")
+            return 1
+        if s.kind == "conv_rb":
+            lin, lout, ksize, stride, pad, dil, nbr = s.args
+            lout.index.zero_()
+            ws = self._workspace(lib.btc_index_workspace_bytes(lout.index.numel()))
+            check(lib.btc_rulebook_conv(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
+                                        int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
+                                        _ptr(lout.index), lout.index.numel(), _ptr(lout.coords), lout.cap,
+                                        _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
+                  "btc_rulebook_conv")
+            return 8
+        if s.kind == "sort_rb":
+            nbr, lvl, nbr_sorted, out_rows = s.args
+            check(lib.btc_rulebook_sort_rows(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(nbr_sorted),
+                                             _ptr(out_rows), st), "btc_rulebook_sort_rows")
+            return 1
+        raise ValueError(s.kind)
 
     def launch_conv(self, args, st):
         """One sparse-conv layer: tcgen05 tile when the weights were packed, fp32 FFMA tile otherwise."""

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Per-stage CUDA-event breakdown of one bench.py step (configs[1], same plan as bench.py).
+
+Times, eagerly on one stream and warm (the step's working set is L2-resident in the real step as well):
+every rulebook-chain step, every conv layer, then the two chains as wholes and the captured graph.
+Answers "which chain is the critical path of the two-stream graph".  Prints one JSON object.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from btcdet_b200 import backbones, engine, synthetic as S  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--algo", type=int, default=0)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, N = args.batch, 20000
+    torch.manual_seed(0)
+    model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+    plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                               max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
+                               device=dev, use_graph=True, sort_rows=not args.no_sort).capture()
+    pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
+    plan.load_points(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
+    plan.step()
+    torch.cuda.synchronize()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def timed(fn):
+        ms = []
+        for r in range(args.reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                ms.append(e0.elapsed_time(e1))
+        return round(float(np.median(ms)) * 1e3, 2)   # microseconds
+
+    rows = [{"step": "voxelize(+MeanVFE)", "us": timed(lambda: plan.launch_voxelize(st))}]
+    for s in plan.steps:
+        if s.kind == "conv":
+            a = s.args
+            name = "conv %d->%d K=%d" % (a[10], a[11], a[9])
+            rows.append({"step": name, "us": timed(lambda: plan.launch_conv(s.args, st))})
+        else:
+            name = s.kind
+            if s.kind == "conv_rb":
+                name += " -> %s" % (s.args[1].shape,)
+            elif s.kind in ("subm_rb", "hash_build"):
+                name += " @ %s" % (s.args[0].shape,)
+            else:
+                name += " K=%d cap=%d" % (s.args[0].shape[1], s.args[0].shape[0])
+            rows.append({"step": name, "us": timed(lambda: plan.launch_index_step(s, st))})
+
+    def index_chain():
+        plan.launch_voxelize(st)
+        for s in plan.steps:
+            if s.kind != "conv":
+                plan.launch_index_step(s, st)
+
+    def conv_chain():
+        for s in plan.steps:
+            if s.kind == "conv":
+                plan.launch_conv(s.args, st)
+
+    res = {"batch": B, "sorted_rows": not args.no_sort, "steps": rows,
+           "sum_index_us": round(sum(r["us"] for r in rows if not r["step"].startswith("conv ")), 1),
+           "sum_conv_us": round(sum(r["us"] for r in rows if r["step"].startswith("conv ")), 1),
+           "index_chain_us": timed(index_chain), "conv_chain_us": timed(conv_chain),
+           "graph_us": timed(plan.step), "counts": plan.read_counts()}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
