@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="scenes per step per GPU")
     ap.add_argument("--algo", type=int, default=0, help="conv tile: 0 auto, 1 FFMA, 2 tcgen05")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-sort", action="store_true", help="keep rulebook rows in spatial order (A/B of the mask sort)")
+    ap.add_argument("--sort", action="store_true", help="mask-sort the rulebook rows inside 2048-row windows (A/B; off by default)")
+    ap.add_argument("--no-sort", action="store_true", help=argparse.SUPPRESS)   # former default-on switch, now a no-op
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the bounded CPU sample (0 = auto)")
     return ap.parse_args()
@@ -136,7 +137,7 @@ def run_ours(args, rank, world):
     model = build_model()
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                               device=dev, use_graph=not args.no_graph, sort_rows=not args.no_sort).capture()
+                               device=dev, use_graph=not args.no_graph, sort_rows=args.sort).capture()
     scenes = make_scenes(rank, N_SCENE_POOL)
     # batches: host pinned (for e2e) and device resident (for value)
     n_batches = N_SCENE_POOL // B if N_SCENE_POOL >= B else 1
@@ -291,7 +292,7 @@ def run_ours(args, rank, world):
                    "scenes_per_step_per_gpu": B, "points_per_scene": N_POINTS, "parallelism": "dp%d" % world,
                    "l2": "value: 256 MB buffer written between timed steps (untimed), %d distinct scenes cycled; e2e: pipelined "
                          "region timed whole, fresh pinned-host batch in and ~15 MB of results out per step" % N_SCENE_POOL,
-                   "cuda_graph": not args.no_graph, "conv_algo": args.algo, "mask_sorted_rows": not args.no_sort,
+                   "cuda_graph": not args.no_graph, "conv_algo": args.algo, "mask_sorted_rows": args.sort,
                    "level_sites": counts},
         "e2e": {"value": round(scenes_total / (ms_e2e * 1e-3), 2), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": round(ms_e2e / args.steps, 4)},

@@ -88,6 +88,44 @@ subm_table_kernel(const int4* __restrict__ coords, int n_cap, const int* __restr
     }
 }
 
+// Symmetric variant (K/2 <= 16, i.e. every 3x3x3 layer): the neighbour relation of a sub-manifold rulebook is its own
+// mirror image — j = nbr[i][k]  <=>  i = nbr[j][K-1-k] — so only the first K/2 taps are probed (13 instead of 26
+// lookups per site) and each hit writes both entries; misses write nothing (the table is pre-filled with -1 by
+// fill_table_kernel, a coalesced 16-byte-store pass).  A warp row handles two sites x 16 tap lanes.
+template <bool HASH>
+__global__ void __launch_bounds__(32 * kSubmSites)
+subm_table_sym_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
+                      const uint2* __restrict__ index, const int* __restrict__ perm, const long long* __restrict__ keys,
+                      const int* __restrict__ vals, uint32_t hmask, int* __restrict__ nbr_out) {
+    __shared__ int s_tap[256];
+    fill_tap_table(g, s_tap);
+    const int n = live_count(n_cap, n_dev);
+    const int K = g.K, half = K >> 1;
+    const int sub = threadIdx.x >> 4, k = threadIdx.x & 15;
+    for (int i = (blockIdx.x * kSubmSites + threadIdx.y) * 2 + sub; i < n; i += gridDim.x * kSubmSites * 2) {
+        const int4 c = __ldg(coords + i);
+        if (k == 0) nbr_out[(int64_t)i * K + half] = i;          // centre tap: the site itself
+        if (k < half) {
+            const int tap = s_tap[k];
+            const int z = c.y + (tap & 255) - 64, y = c.z + ((tap >> 8) & 255) - 64, x = c.w + ((tap >> 16) & 255) - 64;
+            if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w) {
+                const int64_t key = flat_key(c.x, z, y, x, g.in);
+                int j = -1;
+                if (HASH) {
+                    j = hash_lookup(keys, vals, hmask, key);
+                } else {
+                    int r = index_lookup(index, key);
+                    if (r >= 0 && r < n_cap) j = perm ? __ldg(perm + r) : r;   // rank >= capacity: site not materialised
+                }
+                if (j >= 0 && j < n) {
+                    nbr_out[(int64_t)i * K + k] = j;
+                    nbr_out[(int64_t)j * K + (K - 1 - k)] = i;
+                }
+            }
+        }
+    }
+}
+
 // ---- strided / transposed -----------------------------------------------------------
 // Valid taps of one axis for input coordinate `in`: regular conv -> those kk with (in + p - kk*d) divisible by s
 // (k=3, s=2: one or two of the three), transposed -> every kk landing inside the output.  At most 8 per axis.
@@ -128,9 +166,11 @@ __global__ void conv_mark_kernel(const int4* __restrict__ coords, int n_cap, con
     }
 }
 
-// Decode every occupied cell of the output index into a coordinate row; init its table row.
+// Decode every occupied cell of the output index into a coordinate row.  (The table rows are initialised by the
+// coalesced fill_table_kernel: doing it here, 27 scattered stores per set bit by the few threads that own occupied
+// words, made this kernel 4x slower than the bitmap read it is bound by — round-1 launch list, 67 us -> ~15 us.)
 __global__ void conv_emit_kernel(const uint2* __restrict__ out_index, int64_t n_entries, Shape3 out, int out_cap,
-                                 int K, int4* __restrict__ out_coords, int* __restrict__ nbr_out) {
+                                 int4* __restrict__ out_coords) {
     for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_entries; w += (int64_t)gridDim.x * blockDim.x) {
         uint2 e = __ldg(out_index + w);
         unsigned bits = e.x;
@@ -147,18 +187,25 @@ __global__ void conv_emit_kernel(const uint2* __restrict__ out_index, int64_t n_
                 int z = (int)(t % out.d);
                 int b = (int)(t / out.d);
                 out_coords[row] = make_int4(b, z, y, x);
-                if (nbr_out)   // initialise this output row of the neighbour table (conv_tables fills the taps)
-                    for (int k = 0; k < K; ++k) nbr_out[(int64_t)row * K + k] = -1;
             }
             ++row;
         }
     }
 }
 
+// All live rows of a neighbour table to -1: 16-byte stores over the flat [live * K] range (cudaMalloc'ed tables are
+// 256-byte aligned; the scalar tail covers live * K % 4).
 __global__ void fill_table_kernel(int* __restrict__ table, int n_cap, const int* __restrict__ n_dev, int K) {
     const int64_t work = (int64_t)live_count(n_cap, n_dev) * K;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x)
-        table[t] = -1;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if (((uintptr_t)table & 15) == 0) {
+        const int64_t vec = work >> 2;
+        int4* t4 = reinterpret_cast<int4*>(table);
+        for (int64_t t = tid; t < vec; t += nthr) t4[t] = make_int4(-1, -1, -1, -1);
+        for (int64_t t = (vec << 2) + tid; t < work; t += nthr) table[t] = -1;
+    } else {
+        for (int64_t t = tid; t < work; t += nthr) table[t] = -1;
+    }
 }
 
 __global__ void conv_tables_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
@@ -358,8 +405,15 @@ int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch,
     if (g.K > 256 || g.k[0] * g.dil[0] > 120 || g.k[1] * g.dil[1] > 120 || g.k[2] * g.dil[2] > 120)
         return badarg("btc_rulebook_subm: kernel too large");
     dim3 blk(32, kSubmSites);
-    subm_table_kernel<false><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, (cudaStream_t)stream>>>(
-        (const int4*)coords, n_cap, n_dev, g, (const uint2*)index, perm, nullptr, nullptr, 0u, nbr_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((g.K & 1) && g.K / 2 <= 16) {
+        fill_table_kernel<<<grid_for((int64_t)n_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, n_cap, n_dev, g.K);
+        subm_table_sym_kernel<false><<<grid_for((n_cap + 2 * kSubmSites - 1) / (2 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
+            (const int4*)coords, n_cap, n_dev, g, (const uint2*)index, perm, nullptr, nullptr, 0u, nbr_out);
+    } else {
+        subm_table_kernel<false><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, st>>>(
+            (const int4*)coords, n_cap, n_dev, g, (const uint2*)index, perm, nullptr, nullptr, 0u, nbr_out);
+    }
     BTC_CHECK_LAUNCH("subm_table");
     return BTC_OK;
 }
@@ -377,8 +431,17 @@ int btc_rulebook_subm_hash(const int* coords, int n_cap, const int* n_dev, int b
     if (g.K > 256 || g.k[0] * g.dil[0] > 120 || g.k[1] * g.dil[1] > 120 || g.k[2] * g.dil[2] > 120)
         return badarg("btc_rulebook_subm_hash: kernel too large");
     dim3 blk(32, kSubmSites);
-    subm_table_kernel<true><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, (cudaStream_t)stream>>>(
-        (const int4*)coords, n_cap, n_dev, g, nullptr, nullptr, (const long long*)keys, vals, (uint32_t)(n_slots - 1), nbr_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((g.K & 1) && g.K / 2 <= 16) {
+        fill_table_kernel<<<grid_for((int64_t)n_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, n_cap, n_dev, g.K);
+        subm_table_sym_kernel<true><<<grid_for((n_cap + 2 * kSubmSites - 1) / (2 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
+            (const int4*)coords, n_cap, n_dev, g, nullptr, nullptr, (const long long*)keys, vals, (uint32_t)(n_slots - 1),
+            nbr_out);
+    } else {
+        subm_table_kernel<true><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, st>>>(
+            (const int4*)coords, n_cap, n_dev, g, nullptr, nullptr, (const long long*)keys, vals, (uint32_t)(n_slots - 1),
+            nbr_out);
+    }
     BTC_CHECK_LAUNCH("subm_table_hash");
     return BTC_OK;
 }
@@ -409,8 +472,10 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, i
     int rc = launch_index_scan((uint2*)out_index, out_entries, (int*)workspace, n_out, st);
     if (rc) return rc;
     if (out_cap > 0 && out_coords)
-        conv_emit_kernel<<<grid_for(out_entries, T), T, 0, st>>>((const uint2*)out_index, out_entries, g.out, out_cap, g.K,
-                                                                (int4*)out_coords, nbr_out);
+        conv_emit_kernel<<<grid_for(out_entries, T), T, 0, st>>>((const uint2*)out_index, out_entries, g.out, out_cap,
+                                                                (int4*)out_coords);
+    if (out_cap > 0 && nbr_out)   // n_out is on the device by now (the scan wrote it)
+        fill_table_kernel<<<grid_for((int64_t)out_cap * g.K / 4 + 1, T), T, 0, st>>>(nbr_out, out_cap, n_out, g.K);
     if (n_in_cap > 0 && (nbr_out || nbr_in))
         conv_tables_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
                                                             (const uint2*)out_index, out_cap, nbr_out, nbr_in);

@@ -260,7 +260,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
-                   const int* __restrict__ n_dev, int K, int c_in, int c_out) {
+                   const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr) {
     constexpr int STAGES = TC_STAGES;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
@@ -287,6 +287,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         list_full[2];
     __shared__ uint32_t s_tmem;
     __shared__ int s_cnt[2];                        // active reduction chunks of the tile in each index buffer
+    __shared__ int s_tile[2];                       // tile id in each index buffer (-1: no more tiles for this CTA)
+    __shared__ int s_epi_tile[2];                   // tile id behind each accumulator buffer (MMA issuer -> epilogue)
 
     const int n = live_count(n_cap, n_dev);
     if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
@@ -306,7 +308,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             mbar_init(&empty_bar[s], 1);           // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&tmem_full[b], 1);           // one tcgen05.commit
+            mbar_init(&tmem_full[b], 2);           // the issuer's early arrive (publishes the tile id) + one tcgen05.commit
             mbar_init(&tmem_empty[b], 128);        // the 128 epilogue threads
             mbar_init(&nbr_full[b], 1);            // the index loader (+ tx bytes)
             mbar_init(&nbr_empty[b], NPW * 32 + 1);   // every producer thread + the MMA issuer
@@ -353,15 +355,16 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // list makes this return false and the caller drains a stage first.
         auto locate = [&](bool may_block) -> bool {
             while (true) {
-                if (it_tile >= my_tiles) { it_done = true; return false; }
                 if (cur_tile != it_tile) {
                     uint64_t* bar = &list_full[it_tile & 1];
                     const uint32_t par = (uint32_t)(it_tile >> 1) & 1u;
                     if (!may_block && !__any_sync(0xffffffffu, mbar_test(bar, par))) return false;
                     mbar_wait(bar, par);
+                    const int tile = s_tile[it_tile & 1];
+                    if (tile < 0) { it_done = true; return false; }   // the scheduler's end marker
                     cur_tile = it_tile;
                     cur_cnt = s_cnt[it_tile & 1];
-                    rows_left = n - (((int)blockIdx.x + it_tile * (int)gridDim.x) * TC_BM + quarter * 32);
+                    rows_left = n - (tile * TC_BM + quarter * 32);
                 }
                 if (it_pos < cur_cnt) return true;
                 it_pos -= cur_cnt;
@@ -473,15 +476,23 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = (uint32_t)desc0;
         uint32_t s = 0, ph = 0;
-        for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
-            mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
             mbar_wait(&list_full[buf], (tl >> 1) & 1);
+            const int tile = s_tile[buf];
             const int cnt = s_cnt[buf];
             __syncwarp();
-            if (elect_one()) mbar_arrive(&nbr_empty[buf]);
+            mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator (and read its tile id)
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
+            if (elect_one()) {
+                s_epi_tile[buf] = tile;
+                mbar_arrive(&tmem_full[buf]);           // release: the tile id is visible once the phase completes
+                if (tile < 0) mbar_arrive(&tmem_full[buf]);          // end marker: no MMAs, complete the phase now
+                else mbar_arrive(&nbr_empty[buf]);
+            }
+            __syncwarp();
+            if (tile < 0) break;
             for (int j = 0; j < cnt; ++j) {
                 mbar_wait_a(full0 + 8u * s, ph);
                 tc_fence_after();
@@ -512,12 +523,43 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         }
     } else if (warp == TC_IDX_WARP) {
         // ================= index loader: TMA-stage each tile's neighbour block, publish its active chunks ==========
-        for (int tl = 0; tl < my_tiles; ++tl) {
+        // Tile scheduler.  Static: tile = blockIdx.x + tl * gridDim.x.  Dynamic (tile_ctr != null): the first tile is
+        // blockIdx.x, the following ones come from a global counter — tiles cost between a few and all T chunks, so a
+        // fixed round-robin leaves SMs idle ~20 % of a layer.  Exactly num_tiles fetches happen per
+        // launch (num_tiles - P that return a tile + one failing fetch per participating CTA, P = min(grid, tiles));
+        // the fetch that returns num_tiles - 1 is the last one and resets the counter for the next launch.
+        const int P = num_tiles < (int)gridDim.x ? num_tiles : (int)gridDim.x;
+        const uint32_t nbr_s32 = smem_u32(nbr_s);
+        for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
-            const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM;
-            int* dst = nbr_s + buf * TC_BM * K;
+            int tile = -1;
             if (lane == 0) {
                 mbar_wait(&nbr_empty[buf], ((tl >> 1) & 1) ^ 1);
+                if (!tile_ctr) {
+                    tile = tl < my_tiles ? (int)blockIdx.x + tl * (int)gridDim.x : -1;
+                } else if (tl == 0) {
+                    tile = (int)blockIdx.x;
+                } else {
+                    const int t = atomicAdd(tile_ctr, 1);
+                    tile = P + t;
+                    if (tile >= num_tiles) {
+                        tile = -1;
+                        if (t == num_tiles - 1) atomicExch(tile_ctr, 0);
+                    }
+                }
+            }
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile < 0) {                            // publish the end marker and leave
+                if (lane == 0) {
+                    s_tile[buf] = -1;
+                    s_cnt[buf] = 0;
+                    mbar_arrive(&list_full[buf]);
+                }
+                break;
+            }
+            const int row0 = tile * TC_BM;
+            int* dst = nbr_s + buf * TC_BM * K;
+            if (lane == 0) {
                 const int rows = n_cap - row0 < TC_BM ? n_cap - row0 : TC_BM;
                 const uint32_t bytes = (uint32_t)rows * K * 4, bulk = bytes & ~15u;
                 const int* src = table + (int64_t)row0 * K;
@@ -534,8 +576,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             const int rows_live = n - row0 < TC_BM ? n - row0 : TC_BM;
             unsigned long long m = 0;
             for (int r = lane; r < rows_live; r += 32) {
-                const int* rp = dst + r * K;
-                for (int k = 0; k < K; ++k) m |= (unsigned long long)(rp[k] >= 0) << k;
+                const uint32_t rp = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + r * K);
+                for (int k = 0; k < K; ++k) m |= (unsigned long long)(lds_i32(rp + 4u * (uint32_t)k) >= 0) << k;
             }
             const uint32_t m_lo = __reduce_or_sync(0xffffffffu, (uint32_t)m);
             const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
@@ -560,18 +602,20 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 if (lane == 0) s_list[buf * T] = 0;
                 cnt = 1;
             }
-            if (lane == 0) s_cnt[buf] = cnt;
+            if (lane == 0) { s_cnt[buf] = cnt; s_tile[buf] = tile; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&list_full[buf]);
         }
     } else if (warp >= Roles::kEpi0 && warp < Roles::kEpi0 + 4) {
         // ================= epilogue =================
         const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
-        for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
             mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
             tc_fence_after();
-            const int slot_row = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BM + quarter * 32 + lane;
+            const int tile = s_epi_tile[buf];
+            if (tile < 0) break;
+            const int slot_row = tile * TC_BM + quarter * 32 + lane;
             // sorted rulebooks (btc_rulebook_sort_rows) process rows in mask order and scatter to the original rows
             const int row = slot_row < n ? (out_rows ? __ldg(out_rows + slot_row) : slot_row) : n;
             float* dst = feat_out + (int64_t)row * c_out;
@@ -620,6 +664,26 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter at zero again (see
+// the scheduler warp).  Launches rotate through the slots, so kernels that overlap on different streams (or a captured
+// graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
+constexpr int kTcCtrSlots = 1024;
+__device__ int g_tc_tile_ctr[kTcCtrSlots];
+static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1;
+
+static int* next_tile_counter() {
+    static int* base[64] = {nullptr};
+    static unsigned next = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!base[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_tc_tile_ctr) != cudaSuccess) return nullptr;
+        base[dev] = (int*)p;
+    }
+    return base[dev] + (next++ % kTcCtrSlots);
+}
+
 template <int N, int NPW, bool CAT>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
@@ -636,16 +700,22 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
     }
     int tiles = (n_cap + TC_BM - 1) / TC_BM;
     dim3 grid(tiles < kNumSM ? tiles : kNumSM);    // persistent: one CTA per SM
+    int* ctr = nullptr;
+    if (g_tc_dyn) {
+        ctr = next_tile_counter();
+        if (!ctr) return set_error(BTC_E_CUDA, "btc_sparse_conv_fwd_tc: tile counter symbol not available", cudaGetLastError());
+    }
     kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
-                                                     n_cap, n_dev, K, c_in, c_out);
+                                                     n_cap, n_dev, K, c_in, c_out, ctr);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
 
 // Tile variant knobs (A/B measurements and tests; defaults are the measured-best ones).  16 producer warps (four
 // groups) when shared memory allows (N <= 64), else 8; concatenated [B_hi|B_lo] MMAs when TMEM allows (N <= 64).
-// Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_CAT=0; btc_sparse_conv_tc_config() changes them at run time.
-static int g_tc_npw = 0, g_tc_cat = -1;
+// Dynamic tile scheduling (global counter) instead of a fixed round-robin.
+// Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_CAT=0, BTC_TC_DYN=0; btc_sparse_conv_tc_config() changes
+// them at run time.
 static void tc_config_init() {
     if (g_tc_npw == 0) {
         const char* e = getenv("BTC_TC_NPW");
@@ -654,6 +724,10 @@ static void tc_config_init() {
     if (g_tc_cat < 0) {
         const char* e = getenv("BTC_TC_CAT");
         g_tc_cat = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (g_tc_dyn < 0) {
+        const char* e = getenv("BTC_TC_DYN");
+        g_tc_dyn = (e && atoi(e) == 0) ? 0 : 1;
     }
 }
 
@@ -690,13 +764,14 @@ using namespace btc;
 
 extern "C" {
 
-int btc_sparse_conv_tc_config(int producer_warps, int concat_b) {
+int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tiles) {
     tc_config_init();
     if (producer_warps >= 0) {
         if (producer_warps != 8 && producer_warps != 16) return badarg("btc_sparse_conv_tc_config: producer_warps must be 8 or 16");
         g_tc_npw = producer_warps;
     }
     if (concat_b >= 0) g_tc_cat = concat_b ? 1 : 0;
+    if (dynamic_tiles >= 0) g_tc_dyn = dynamic_tiles ? 1 : 0;
     return BTC_OK;
 }
 

@@ -264,6 +264,13 @@ def tc_supported(K, c_in, c_out):
     return bool(_lib.load().btc_sparse_conv_tc_supported(int(K), int(c_in), int(c_out)))
 
 
+def tc_config(producer_warps=-1, concat_b=-1, dynamic_tiles=-1):
+    """Process-wide variant knobs of the tcgen05 tile (A/B measurements, tests); -1 keeps a setting.
+    Defaults: 16 producer warps, concatenated [B_hi|B_lo] MMAs, dynamic tile scheduling."""
+    check(_lib.load().btc_sparse_conv_tc_config(int(producer_warps), int(concat_b), int(dynamic_tiles)),
+          "btc_sparse_conv_tc_config")
+
+
 def tc_pack_weight(weight):
     """Pack [K,Cin,Cout] (or [*k,Cin,Cout]) fp32 weights into the tcgen05 operand image (hi/lo tf32 split,
     K-major, 128-byte swizzle) consumed by sparse_conv_fwd_tc."""

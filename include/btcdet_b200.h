@@ -237,9 +237,11 @@ int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out,
  */
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out);
 /* Tile-variant knobs for A/B measurements and tests (process-wide; -1 keeps a setting): producer_warps 8 | 16
- * (16 needs c_out <= 64), concat_b 0 | 1 = issue A_hi x [B_hi|B_lo] as one MMA of width 2N (c_out <= 64).
- * Results of the variants agree to fp32 rounding (the order of the three 3xTF32 partial sums differs). */
-int btc_sparse_conv_tc_config(int producer_warps, int concat_b);
+ * (16 needs c_out <= 64), concat_b 0 | 1 = issue A_hi x [B_hi|B_lo] as one MMA of width 2N (c_out <= 64),
+ * dynamic_tiles 0 | 1 = persistent CTAs fetch 128-row tiles from a global counter instead of a fixed round-robin.
+ * Results of the variants agree to fp32 rounding (the order of the three 3xTF32 partial sums differs with concat_b;
+ * dynamic_tiles does not change any result bit). */
+int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tiles);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
 int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,

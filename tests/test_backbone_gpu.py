@@ -69,14 +69,16 @@ def test_training_step_runs_and_matches_dense_autograd_direction(cuda, oracle):
     assert sum(float(p.grad.abs().sum()) for p in model.parameters()) > 0
 
 
-@pytest.mark.parametrize("batch,use_graph,algo", [(1, True, 1), (3, True, 0), (2, False, 0), (1, True, 2)])
-def test_planned_engine_matches_oracle(cuda, oracle, batch, use_graph, algo):
+@pytest.mark.parametrize("batch,use_graph,algo,sort", [(1, True, 1, False), (3, True, 0, False), (2, False, 0, False),
+                                                        (1, True, 2, False), (2, True, 0, True)])
+def test_planned_engine_matches_oracle(cuda, oracle, batch, use_graph, algo, sort):
     """points -> GPU voxelize -> MeanVFE -> folded-BN backbone under one CUDA graph, no host sync."""
     from btcdet_b200 import backbones, engine, synthetic as S
     torch.manual_seed(0)
     model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, batch, batch * 20000, S.DET_VOXEL_SIZE,
-                               S.KITTI_RANGE, max_points=5, max_voxels=16000, algo=algo, use_graph=use_graph).capture()
+                               S.KITTI_RANGE, max_points=5, max_voxels=16000, algo=algo, use_graph=use_graph,
+                               sort_rows=sort).capture()
     for rep in range(2):  # replay the same graph on different inputs
         scenes, mean, coords = _inputs(oracle, batch, seed=200 + 10 * rep)
         ref = _oracle_forward(model, mean, coords, batch)["out"]

@@ -270,6 +270,49 @@ def test_tensor_core_multi_tile_persistent(cuda, n_out, K, cin, cout, density, r
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("npw,cat,dyn", [(16, 1, 1), (16, 0, 1), (16, 1, 0), (8, 1, 1), (8, 0, 0), (16, 0, 0)])
+@pytest.mark.parametrize("n_out,K,cin,cout,density,run", [
+    (45000, 27, 32, 32, 0.27, 97), (33000, 27, 64, 64, 0.35, 300), (70000, 27, 16, 16, 0.03, 1024),
+    (21000, 3, 64, 128, 0.45, 97), (130, 27, 32, 64, 0.2, 7)])
+def test_tensor_core_tile_variants(cuda, npw, cat, dyn, n_out, K, cin, cout, density, run):
+    """Every variant of the tcgen05 tile (8 / 16 producer warps, 3-MMA / concatenated [B_hi|B_lo] 2-MMA k-steps, static /
+    dynamic tile scheduling) against the fp32 FFMA tile; the dynamic scheduler's counter must return to zero after
+    every launch (three launches, identical bits), and scheduling must not change a single bit."""
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(n_out + K + cin)
+    n_in = 40000
+    pat = rng.random((64, K)) < density
+    valid = pat[(np.arange(n_out) // run) % 64] ^ (rng.random((n_out, K)) < 0.01)
+    valid[:, K // 2] |= ~valid.any(1)
+    nbr = np.where(valid, rng.integers(0, n_in, (n_out, K)), -1).astype(np.int32)
+    cap = n_out + 777
+    table = torch.full((cap, K), 123456789, dtype=torch.int32, device="cuda")
+    table[:n_out] = torch.from_numpy(nbr).cuda()
+    n_dev = torch.tensor([n_out], dtype=torch.int32, device="cuda")
+    feat = torch.from_numpy(rng.standard_normal((n_in, cin)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).cuda()
+    packed = ops.tc_pack_weight(w)
+    ffma = ops.sparse_conv_fwd(feat, table[:n_out].contiguous(), w, bias, algo=1)
+    try:
+        ops.tc_config(npw, cat, dyn)
+        outs = []
+        for rep in range(3):
+            out = torch.zeros((cap, cout), device="cuda")
+            ops.sparse_conv_fwd_tc(feat, table, packed, cin, cout, bias, n_out_dev=n_dev, out=out)
+            outs.append(out)
+        torch.cuda.synchronize()
+        assert rel_err(outs[0][:n_out].cpu().numpy(), ffma.cpu().numpy()) < 2e-5
+        assert float(outs[0][n_out:].abs().sum()) == 0.0
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+        ops.tc_config(npw, cat, 0)
+        static = torch.zeros((cap, cout), device="cuda")
+        ops.sparse_conv_fwd_tc(feat, table, packed, cin, cout, bias, n_out_dev=n_dev, out=static)
+        assert torch.equal(static, outs[0])
+    finally:
+        ops.tc_config(16, 1, 1)
+
+
 @pytest.mark.parametrize("n,K", [(1, 27), (127, 27), (2048, 27), (2049, 8), (9000, 27), (5000, 64), (3000, 3), (4100, 33)])
 def test_rulebook_sort_rows(cuda, n, K):
     """btc_rulebook_sort_rows: a permutation inside 2048-row windows, ordered by (valid-offset mask, original row)."""

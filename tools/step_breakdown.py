@@ -23,9 +23,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--sort", action="store_true")
     ap.add_argument("--algo", type=int, default=0)
+    ap.add_argument("--variants", default="16,1,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
+                    "(one JSON line each), e.g. '16,1,1;16,0,1;16,1,0'")
     args = ap.parse_args()
+    for v in args.variants.split(";"):
+        npw, cat, dyn = (int(x) for x in v.split(","))
+        run(args, npw, cat, dyn)
+
+
+def run(args, npw, cat, dyn):
+    from btcdet_b200 import ops
+    ops.tc_config(npw, cat, dyn)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, N = args.batch, 20000
@@ -33,7 +43,7 @@ def main():
     model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                               device=dev, use_graph=True, sort_rows=not args.no_sort).capture()
+                               device=dev, use_graph=True, sort_rows=args.sort).capture()
     pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
     plan.load_points(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     plan.step()
@@ -79,12 +89,15 @@ def main():
             if s.kind == "conv":
                 plan.launch_conv(s.args, st)
 
-    res = {"batch": B, "sorted_rows": not args.no_sort, "steps": rows,
+    res = {"batch": B, "sorted_rows": args.sort, "variant": {"producer_warps": npw, "concat_b": cat, "dynamic_tiles": dyn},
+           "steps": rows,
            "sum_index_us": round(sum(r["us"] for r in rows if not r["step"].startswith("conv ")), 1),
            "sum_conv_us": round(sum(r["us"] for r in rows if r["step"].startswith("conv ")), 1),
            "index_chain_us": timed(index_chain), "conv_chain_us": timed(conv_chain),
            "graph_us": timed(plan.step), "counts": plan.read_counts()}
-    print(json.dumps(res))
+    print(json.dumps(res), flush=True)
+    del plan
+    torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
