@@ -260,7 +260,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
-                   const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr) {
+                   const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag) {
     constexpr int STAGES = TC_STAGES;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
@@ -384,6 +384,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             const bool col_ok = i_k < K;            // beyond the end of the reduction axis: zero fill
             const uint32_t nb = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0));
             const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
+            if (!(diag & 1))                        // (timing diagnostics: bit 0 drops the gather)
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int src = lds_i32(nb + 4u * (uint32_t)(g * strideK4));
@@ -420,10 +421,15 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             else cp_async_wait<3>();
             __syncwarp();
             float4 v[8];
+            if (!(diag & 2)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t a = rd_base + (uint32_t)slot * 4096u + (((uint32_t)i ^ x7) << 4);
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(a));
+            }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();                          // everyone has read the slot before it is refilled
             mbar_wait_a(empty0 + 8u * (uint32_t)s, (uint32_t)(ph ^ 1));
@@ -435,6 +441,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
             // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
+            if (!(diag & 2))                        // (bit 1 drops the smem read-back, the hi/lo split and the TMEM stores)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t w[16];
@@ -509,8 +516,10 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                         } else {
                             const uint64_t db_lo = desc_hi64 | (uint64_t)(dl + (uint32_t)(B_BYTES >> 4) + 2u * (uint32_t)kk);
                             umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, (j | kk) != 0);   // small terms first
-                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
-                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
+                            if (!(diag & 4)) {            // (bit 2: one MMA per k-step instead of three)
+                                umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
+                                umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
+                            }
                         }
                     }
                     umma_commit_a(empty0 + 8u * s);      // frees the stage once the MMAs above retire
@@ -669,7 +678,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
-static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1;
+static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0;
 
 static int* next_tile_counter() {
     static int* base[64] = {nullptr};
@@ -706,15 +715,15 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
         if (!ctr) return set_error(BTC_E_CUDA, "btc_sparse_conv_fwd_tc: tile counter symbol not available", cudaGetLastError());
     }
     kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
-                                                     n_cap, n_dev, K, c_in, c_out, ctr);
+                                                     n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
 
 // Tile variant knobs (A/B measurements and tests; defaults are the measured-best ones).  16 producer warps (four
-// groups) when shared memory allows (N <= 64), else 8; concatenated [B_hi|B_lo] MMAs when TMEM allows (N <= 64).
+// groups) when shared memory allows (N <= 64), else 8; concatenated [B_hi|B_lo] MMAs (N <= 64) are off by default.
 // Dynamic tile scheduling (global counter) instead of a fixed round-robin.
-// Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_CAT=0, BTC_TC_DYN=0; btc_sparse_conv_tc_config() changes
+// Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_CAT=1, BTC_TC_DYN=0; btc_sparse_conv_tc_config() changes
 // them at run time.
 static void tc_config_init() {
     if (g_tc_npw == 0) {
@@ -723,7 +732,7 @@ static void tc_config_init() {
     }
     if (g_tc_cat < 0) {
         const char* e = getenv("BTC_TC_CAT");
-        g_tc_cat = (e && atoi(e) == 0) ? 0 : 1;
+        g_tc_cat = (e && atoi(e) == 1) ? 1 : 0;   // measured: no gain from fewer MMA instructions (the issuer is not the limiter)
     }
     if (g_tc_dyn < 0) {
         const char* e = getenv("BTC_TC_DYN");
@@ -772,6 +781,11 @@ int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tile
     }
     if (concat_b >= 0) g_tc_cat = concat_b ? 1 : 0;
     if (dynamic_tiles >= 0) g_tc_dyn = dynamic_tiles ? 1 : 0;
+    return BTC_OK;
+}
+
+int btc_sparse_conv_tc_diag(int mask) {
+    g_tc_diag = mask;
     return BTC_OK;
 }
 

@@ -266,7 +266,7 @@ def tc_supported(K, c_in, c_out):
 
 def tc_config(producer_warps=-1, concat_b=-1, dynamic_tiles=-1):
     """Process-wide variant knobs of the tcgen05 tile (A/B measurements, tests); -1 keeps a setting.
-    Defaults: 16 producer warps, concatenated [B_hi|B_lo] MMAs, dynamic tile scheduling."""
+    Defaults: 16 producer warps, three MMAs per k-step (no [B_hi|B_lo] concatenation), dynamic tile scheduling."""
     check(_lib.load().btc_sparse_conv_tc_config(int(producer_warps), int(concat_b), int(dynamic_tiles)),
           "btc_sparse_conv_tc_config")
 

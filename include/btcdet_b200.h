@@ -242,6 +242,11 @@ int btc_sparse_conv_tc_supported(int K, int c_in, int c_out);
  * Results of the variants agree to fp32 rounding (the order of the three 3xTF32 partial sums differs with concat_b;
  * dynamic_tiles does not change any result bit). */
 int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tiles);
+/* Timing diagnostics for the profile write-ups (tools/step_breakdown.py --diag): a non-zero mask makes the tile skip a
+ * part of its work — bit 0 the gather, bit 1 the smem read-back / hi-lo split / TMEM stores, bit 2 two of the three
+ * MMAs per k-step — so the cost of each pipeline side can be read off a wall-clock difference.  RESULTS ARE WRONG
+ * while the mask is non-zero; 0 (the default) restores the product path. */
+int btc_sparse_conv_tc_diag(int mask);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
 int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,

@@ -310,7 +310,7 @@ def test_tensor_core_tile_variants(cuda, npw, cat, dyn, n_out, K, cin, cout, den
         ops.sparse_conv_fwd_tc(feat, table, packed, cin, cout, bias, n_out_dev=n_dev, out=static)
         assert torch.equal(static, outs[0])
     finally:
-        ops.tc_config(16, 1, 1)
+        ops.tc_config(16, 0, 1)
 
 
 @pytest.mark.parametrize("n,K", [(1, 27), (127, 27), (2048, 27), (2049, 8), (9000, 27), (5000, 64), (3000, 3), (4100, 33)])

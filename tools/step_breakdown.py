@@ -25,7 +25,9 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--sort", action="store_true")
     ap.add_argument("--algo", type=int, default=0)
-    ap.add_argument("--variants", default="16,1,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
+    ap.add_argument("--diag", action="store_true", help="also time the conv chain with parts of the tcgen05 tile skipped "
+                    "(btc_sparse_conv_tc_diag masks; wrong results, timing only)")
+    ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
                     "(one JSON line each), e.g. '16,1,1;16,0,1;16,1,0'")
     args = ap.parse_args()
     for v in args.variants.split(";"):
@@ -95,6 +97,20 @@ def run(args, npw, cat, dyn):
            "sum_conv_us": round(sum(r["us"] for r in rows if r["step"].startswith("conv ")), 1),
            "index_chain_us": timed(index_chain), "conv_chain_us": timed(conv_chain),
            "graph_us": timed(plan.step), "counts": plan.read_counts()}
+    if args.diag:
+        from btcdet_b200 import _lib
+        lib = _lib.load()
+        names = {0: "full", 1: "no gather", 2: "no readback/split/tmem-store", 3: "no gather, no split", 4: "1 of 3 MMAs",
+                 5: "no gather, 1 MMA", 6: "no split, 1 MMA", 7: "barriers + 1 MMA only"}
+        convs = [s for s in plan.steps if s.kind == "conv"]
+        diag = []
+        for mask in range(8):
+            lib.btc_sparse_conv_tc_diag(mask)
+            diag.append({"mask": mask, "what": names[mask], "conv_chain_us": timed(conv_chain),
+                         "conv32_us": timed(lambda: plan.launch_conv(convs[3].args, st)),
+                         "conv64_us": timed(lambda: plan.launch_conv(convs[6].args, st))})
+        lib.btc_sparse_conv_tc_diag(0)
+        res["diag"] = diag
     print(json.dumps(res), flush=True)
     del plan
     torch.cuda.empty_cache()
