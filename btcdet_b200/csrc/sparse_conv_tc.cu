@@ -9,7 +9,8 @@
 //     fp32 value into a tf32 "hi" part (low 13 mantissa bits cleared) and the exact fp32 remainder "lo", and write the
 //     A operand straight into tensor memory with tcgen05.st;
 //   * the matching weight slice comes pre-packed (btc_sparse_conv_tc_pack) as the shared-memory image of the K-major,
-//     128-byte-swizzled hi/lo tiles and is fetched with one cp.async.bulk per stage (mbarrier complete_tx);
+//     128-byte-swizzled hi/lo tiles; a dedicated loader warp fetches it with one cp.async.bulk per stage (mbarrier
+//     complete_tx) into its own ring, NB stages ahead of the MMAs;
 //   * one elected lane issues tcgen05.mma.kind::tf32 (M=128, N, K=8), A from TMEM, B from shared memory — 3xTF32:
 //     D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi — fp32-class accuracy (the 1e-4 parity bar) from the tf32 pipe;
 //     tcgen05.commit releases the stage / publishes the accumulator through mbarriers;
@@ -190,15 +191,21 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
 //                memory with one cp.async.bulk, one tile ahead.
 // TMEM map (512 columns): [0, 2N) two accumulators | [2N + 64*s, +32) A_hi of stage s | [+32, +64) A_lo.
 // Warp roles for NPW producer warps (8 or 16): [0, NPW) producers in NPW/4 groups, NPW = MMA issuer, NPW+1..NPW+4
-// epilogue (TMEM lane quarter = warp % 4 covers 1,2,3,0), NPW+5 = index loader, the rest (to a multiple of four warps,
-// so that setmaxnreg acts on whole warpgroups) idle until the final barrier.
+// epilogue (TMEM lane quarter = warp % 4 covers 1,2,3,0), NPW+5 = index loader + tile scheduler, NPW+6 = weight loader,
+// the rest (to a multiple of four warps) idle until the final barrier.
 template <int NPW> struct TcRoles {
     static constexpr int kGroups = NPW / 4;
-    static constexpr int kMma = NPW, kEpi0 = NPW + 1, kIdx = NPW + 5;
-    static constexpr int kWarps = ((NPW + 6 + 3) / 4) * 4;
+    static constexpr int kMma = NPW, kEpi0 = NPW + 1, kIdx = NPW + 5, kBld = NPW + 6;
+    static constexpr int kWarps = ((NPW + 7 + 3) / 4) * 4;
     static constexpr int kThreads = kWarps * 32;
 };
 constexpr int TC_STAGES = 4;
+// Weight-tile ring: deeper than the A ring where shared memory allows (64 KB: 8 stages at N = 32, 4 at N = 64; 4 x 32 KB at
+// N = 128) and fed by its own loader warp.  Round-1 timing diagnostics (tools/step_breakdown.py --diag): with the gather,
+// the split and two of the three MMAs removed the layer still took 70 % of its time — the weight tile of a stage was
+// requested by a producer thread only after it had finished its own gather work AND the stage had drained, so every
+// stage exposed a full L2 -> smem TMA latency.  The loader requests tile c + NB the moment the MMAs of tile c retire.
+template <int N> struct TcBStages { static constexpr int value = N <= 32 ? 8 : 4; };
 template <int N, int NPW> struct TcDepth { static constexpr int value = (N > 64 || NPW > 8) ? 2 : 4; };   // cp.async gather stages in flight per producer warp (smem budget)
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
@@ -265,7 +272,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
     constexpr int G = Roles::kGroups;               // producer groups; group g feeds the stages with gi % G == g
-    constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx;
+    constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx, TC_BLD_WARP = Roles::kBld;
+    constexpr int NB = TcBStages<N>::value;         // weight-tile ring depth
     static_assert(TC_STAGES % G == 0 || G % TC_STAGES == 0, "stage ring / group count");
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
@@ -280,11 +288,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* stages = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
-    unsigned char* a_stage = stages + STAGES * STAGE_BYTES;                 // [8 warps][TC_DEPTH][32 rows x 128 B]
+    unsigned char* a_stage = stages + NB * STAGE_BYTES;                 // [8 warps][TC_DEPTH][32 rows x 128 B]
     int* nbr_s = (int*)(a_stage + TC_PRODUCER_WARPS * TC_DEPTH * 4096);     // [2][TC_BM * K]
 
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], nbr_full[2], nbr_empty[2],
-        list_full[2];
+        list_full[2], b_full[8], b_empty[8];
     __shared__ uint32_t s_tmem;
     __shared__ int s_cnt[2];                        // active reduction chunks of the tile in each index buffer
     __shared__ int s_tile[2];                       // tile id in each index buffer (-1: no more tiles for this CTA)
@@ -304,14 +312,18 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 128);          // the 128 threads of one producer group (+ bulk-copy tx bytes)
+            mbar_init(&full_bar[s], 128);          // the 128 threads of one producer group
             mbar_init(&empty_bar[s], 1);           // one tcgen05.commit
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&b_full[s], 1);              // the weight loader's arrive (+ bulk-copy tx bytes)
+            mbar_init(&b_empty[s], 1);             // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 2);           // the issuer's early arrive (publishes the tile id) + one tcgen05.commit
             mbar_init(&tmem_empty[b], 128);        // the 128 epilogue threads
             mbar_init(&nbr_full[b], 1);            // the index loader (+ tx bytes)
-            mbar_init(&nbr_empty[b], NPW * 32 + 1);   // every producer thread + the MMA issuer
+            mbar_init(&nbr_empty[b], NPW * 32 + 2);   // every producer thread + the MMA issuer + the weight loader
             mbar_init(&list_full[b], 1);           // the index loader, after it built the chunk list
         }
         fence_mbar_init();
@@ -347,7 +359,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         int it_tile = 0, it_pos = group, cur_tile = -1, cur_cnt = 0, rows_left = 0;
         bool it_done = false;
         int inflight = 0;
-        unsigned long long fifo = 0;                // chunk ids of the stages in flight, 16 bits each, oldest lowest
         // Position the iterator on this group's next stage.  Every tile's index buffer is acquired and released exactly
         // once per thread.  A warp that still has gathers in flight must never BLOCK on a later tile's list: the MMA
         // issuer may be waiting for exactly those stages before it can release the buffer the list needs (groups that
@@ -394,7 +405,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
             }
             cp_async_commit();
-            fifo |= (unsigned long long)chunk << (16 * inflight);
             ++inflight;
             it_pos += G;
         };
@@ -412,8 +422,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 located = false;
             }
             if (inflight == 0) break;              // iterator exhausted and everything drained
-            const uint32_t chunk = (uint32_t)(fifo & 0xFFFFull);
-            fifo >>= 16;
             --inflight;                            // = committed groups allowed to stay pending
             if (inflight == 0) cp_async_wait<0>();
             else if (inflight == 1) cp_async_wait<1>();
@@ -434,11 +442,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             __syncwarp();                          // everyone has read the slot before it is refilled
             mbar_wait_a(empty0 + 8u * (uint32_t)s, (uint32_t)(ph ^ 1));
             tc_fence_after();
-            if ((tid & 127) == 0) {
-                unsigned char* st = stages + s * STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], 2 * B_BYTES);
-                bulk_copy_g2s(st, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
-            }
             // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
             // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
             if (!(diag & 2))                        // (bit 1 drops the smem read-back, the hi/lo split and the TMEM stores)
@@ -479,10 +482,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // and the descriptor words are hoisted, and a stage's descriptors differ from the base only by an add on the
         // 14-bit start-address field (no carry: shared addresses < 256 KB).
         const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]);
         const uint64_t desc0 = make_desc_sw128(smem_u32(stages));
         const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = (uint32_t)desc0;
-        uint32_t s = 0, ph = 0;
+        uint32_t s = 0, ph = 0, sb = 0, pb = 0;   // A ring slot / phase, weight ring slot / phase
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
             mbar_wait(&list_full[buf], (tl >> 1) & 1);
@@ -501,12 +505,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             __syncwarp();
             if (tile < 0) break;
             for (int j = 0; j < cnt; ++j) {
-                mbar_wait_a(full0 + 8u * s, ph);
+                mbar_wait_a(bfull0 + 8u * sb, pb);       // weight tile landed (requested NB stages ago)
+                mbar_wait_a(full0 + 8u * s, ph);         // A operand in TMEM
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_hi = tmem_base + A_COL0 + s * 64u;
                     const uint32_t a_lo = a_hi + 32u;
-                    const uint32_t dl = desc_lo0 + s * (uint32_t)(STAGE_BYTES >> 4);
+                    const uint32_t dl = desc_lo0 + sb * (uint32_t)(STAGE_BYTES >> 4);
 #pragma unroll
                     for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
                         const uint64_t db_hi = desc_hi64 | (uint64_t)(dl + 2u * (uint32_t)kk);
@@ -522,13 +527,38 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                             }
                         }
                     }
-                    umma_commit_a(empty0 + 8u * s);      // frees the stage once the MMAs above retire
+                    umma_commit_a(empty0 + 8u * s);      // frees the A stage once the MMAs above retire
+                    umma_commit_a(bempty0 + 8u * sb);    // ... and the weight stage
                 }
                 __syncwarp();
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+                if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
             }
             if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
             __syncwarp();
+        }
+    } else if (warp == TC_BLD_WARP) {
+        // ================= weight loader: one cp.async.bulk per stage, NB stages ahead of the MMAs =================
+        if (lane == 0) {
+            const uint32_t list_s32 = smem_u32(s_list);
+            uint32_t sb = 0, pb = 0;
+            for (int tl = 0;; ++tl) {
+                const int buf = tl & 1;
+                mbar_wait(&list_full[buf], (tl >> 1) & 1);
+                if (s_tile[buf] < 0) break;
+                const int cnt = s_cnt[buf];
+                for (int j = 0; j < cnt; ++j) {
+                    const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + j));
+                    mbar_wait(&b_empty[sb], pb ^ 1u);          // the MMAs that read this slot have retired
+                    tc_fence_after();
+                    mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
+                    bulk_copy_g2s(stages + sb * STAGE_BYTES, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES), 2 * B_BYTES,
+                                  &b_full[sb]);
+                    mbar_arrive(&b_full[sb]);
+                    if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
+                }
+                mbar_arrive(&nbr_empty[buf]);                  // done with this tile's chunk list
+            }
         }
     } else if (warp == TC_IDX_WARP) {
         // ================= index loader: TMA-stage each tile's neighbour block, publish its active chunks ==========
@@ -693,14 +723,23 @@ static int* next_tile_counter() {
     return base[dev] + (next++ % kTcCtrSlots);
 }
 
+// dynamic shared memory of one CTA: weight ring + cp.async staging + two index tiles + two chunk lists + alignment slack
+static size_t tc_smem_bytes(int N, int npw, int K, int c_in) {
+    const int stage_bytes = 2 * N * 128;
+    const int nb = N <= 32 ? 8 : 4, depth = (N > 64 || npw > 8) ? 2 : 4;
+    const int T = (K * c_in + TC_KC - 1) / TC_KC;
+    return (size_t)nb * stage_bytes + (size_t)npw * depth * 4096 + (size_t)2 * TC_BM * K * sizeof(int) +
+           (size_t)((4 * T + 15) & ~15) + 1024 + 16;
+}
+constexpr size_t kTcMaxSmem = 227 * 1024;
+
 template <int N, int NPW, bool CAT>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
-    constexpr int STAGE_BYTES = 2 * N * 128;
-    const int T = (K * c_in + TC_KC - 1) / TC_KC;
-    size_t smem = (size_t)TC_STAGES * STAGE_BYTES + (size_t)NPW * TcDepth<N, NPW>::value * 4096 +
-                  (size_t)2 * TC_BM * K * sizeof(int) + (size_t)((4 * T + 15) & ~15) + 1024 + 16;
+    static_assert(TcBStages<N>::value == (N <= 32 ? 8 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
+                  "tc_smem_bytes mirrors these");
+    const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
     auto kern = conv_fwd_tc_kernel<N, NPW, CAT>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
@@ -790,8 +829,11 @@ int btc_sparse_conv_tc_diag(int mask) {
 }
 
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out) {
-    return (K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 4 && c_out % 4 == 0 && tc_padded_n(c_out) != 0 &&
-            (int64_t)K * c_in >= 32) ? 1 : 0;
+    if (!(K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 4 && c_out % 4 == 0 && tc_padded_n(c_out) != 0 &&
+          (int64_t)K * c_in >= 32))
+        return 0;
+    const int N = tc_padded_n(c_out);   // the index tiles of large kernels (K > 33) do not fit next to the rings
+    return tc_smem_bytes(N, N <= 64 ? 16 : 8, K, c_in) <= kTcMaxSmem && tc_smem_bytes(N, 8, K, c_in) <= kTcMaxSmem ? 1 : 0;
 }
 
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out) {
