@@ -199,7 +199,10 @@ template <int NPW> struct TcRoles {
     static constexpr int kWarps = ((NPW + 7 + 3) / 4) * 4;
     static constexpr int kThreads = kWarps * 32;
 };
-constexpr int TC_STAGES = 4;
+// A-operand ring in TMEM: 64 columns (hi + lo) per stage next to the two accumulators — six stages where they fit
+// (N <= 64 without the concatenated-B accumulators), four otherwise.  Each producer group then has a stage to fill while
+// its previous one is still being multiplied.
+template <int N, bool CAT> struct TcAStages { static constexpr int value = (2 * (CAT ? 2 * N : N) + 64 * 6 <= 512) ? 6 : 4; };
 // Weight-tile ring: deeper than the A ring where shared memory allows (64 KB: 8 stages at N = 32, 4 at N = 64; 4 x 32 KB at
 // N = 128) and fed by its own loader warp.  Round-1 timing diagnostics (tools/step_breakdown.py --diag): with the gather,
 // the split and two of the three MMAs removed the layer still took 70 % of its time — the weight tile of a stage was
@@ -268,13 +271,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
                    const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag) {
-    constexpr int STAGES = TC_STAGES;
+    constexpr int STAGES = TcAStages<N, CAT>::value;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
     constexpr int G = Roles::kGroups;               // producer groups; group g feeds the stages with gi % G == g
     constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx, TC_BLD_WARP = Roles::kBld;
     constexpr int NB = TcBStages<N>::value;         // weight-tile ring depth
-    static_assert(TC_STAGES % G == 0 || G % TC_STAGES == 0, "stage ring / group count");
+    static_assert(G <= STAGES, "a group advances by G stages and may wrap the ring at most once per step");
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = 512;
@@ -395,14 +398,19 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             const bool col_ok = i_k < K;            // beyond the end of the reduction axis: zero fill
             const uint32_t nb = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0));
             const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
-            if (!(diag & 1))                        // (timing diagnostics: bit 0 drops the gather)
+            if (!(diag & 1)) {                      // (timing diagnostics: bit 0 drops the gather)
+                // all eight index loads first: volatile asm keeps program order, and one LDS latency in front of every
+                // copy was the largest stall of this warp's dependent chain (round-1 source-level profile)
+                int src[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const int src = lds_i32(nb + 4u * (uint32_t)(g * strideK4));
-                const bool ok = col_ok && (g * 4 + sub) < rows_left && src >= 0;
-                const uint32_t off = ok ? (uint32_t)src * rowbytes + colbytes : 0u;
-                const uint32_t dst = dbase + (uint32_t)(g * 512) + ((g & 1) ? dst_odd : dst_even);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
+                for (int g = 0; g < 8; ++g) src[g] = lds_i32(nb + 4u * (uint32_t)(g * strideK4));
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const bool ok = col_ok && (g * 4 + sub) < rows_left && src[g] >= 0;
+                    const uint32_t off = ok ? (uint32_t)src[g] * rowbytes + colbytes : 0u;
+                    const uint32_t dst = dbase + (uint32_t)(g * 512) + ((g & 1) ? dst_odd : dst_even);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(fbase + off), "r"(ok ? 16u : 0u) : "memory");
+                }
             }
             cp_async_commit();
             ++inflight;
