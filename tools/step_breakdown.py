@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--sort", action="store_true")
     ap.add_argument("--algo", type=int, default=0)
+    ap.add_argument("--side-priority", type=int, default=-1, help="priority of the rulebook stream (-1 high, 0 default)")
     ap.add_argument("--diag", action="store_true", help="also time the conv chain with parts of the tcgen05 tile skipped "
                     "(btc_sparse_conv_tc_diag masks; wrong results, timing only)")
     ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
@@ -45,7 +46,7 @@ def run(args, npw, cat, dyn):
     model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                               device=dev, use_graph=True, sort_rows=args.sort).capture()
+                               device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority).capture()
     pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
     plan.load_points(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     plan.step()
