@@ -716,7 +716,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
-static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0;
+static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM;
 
 static int* next_tile_counter() {
     static int* base[64] = {nullptr};
@@ -755,7 +755,7 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
         attr_set = smem;
     }
     int tiles = (n_cap + TC_BM - 1) / TC_BM;
-    dim3 grid(tiles < kNumSM ? tiles : kNumSM);    // persistent: one CTA per SM
+    dim3 grid(tiles < g_tc_grid ? tiles : g_tc_grid);    // persistent: one CTA per SM (or fewer: btc_sparse_conv_tc_grid)
     int* ctr = nullptr;
     if (g_tc_dyn) {
         ctr = next_tile_counter();
@@ -828,6 +828,12 @@ int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tile
     }
     if (concat_b >= 0) g_tc_cat = concat_b ? 1 : 0;
     if (dynamic_tiles >= 0) g_tc_dyn = dynamic_tiles ? 1 : 0;
+    return BTC_OK;
+}
+
+int btc_sparse_conv_tc_grid(int max_ctas) {
+    if (max_ctas < 1 || max_ctas > kNumSM) return badarg("btc_sparse_conv_tc_grid: max_ctas must be in [1, 148]");
+    g_tc_grid = max_ctas;
     return BTC_OK;
 }
 

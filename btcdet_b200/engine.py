@@ -58,7 +58,7 @@ class BackbonePlan:
     """
 
     def __init__(self, layer_specs, sparse_shape, batch, max_points_total, voxel_size, point_range, max_points=5,
-                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=False, side_priority=-1):
+                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=False, side_priority=0):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.batch = int(batch)
@@ -148,8 +148,7 @@ class BackbonePlan:
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
         self.graph = None
-        # high priority: at every conv-kernel boundary the pending rulebook kernels go first (they are short, and the
-        # next layers wait for them), instead of queueing behind 148 persistent conv CTAs
+        # (a high-priority rulebook stream, side_priority=-1, was measured: no effect on the captured step, 1515 us both ways)
         self._side_stream = torch.cuda.Stream(device=dev, priority=side_priority)
         self.launches_per_step = 0
         self.host_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32).pin_memory()

@@ -248,6 +248,9 @@ int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tile
  * MMAs per k-step — so the cost of each pipeline side can be read off a wall-clock difference.  RESULTS ARE WRONG
  * while the mask is non-zero; 0 (the default) restores the product path. */
 int btc_sparse_conv_tc_diag(int mask);
+/* Cap on the persistent grid of the tcgen05 tile (default 148 = one CTA per SM): a smaller grid leaves whole SMs to
+ * kernels running concurrently on other streams (the rulebook chain of the engine).  Process-wide. */
+int btc_sparse_conv_tc_grid(int max_ctas);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
 int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,

@@ -25,15 +25,53 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--sort", action="store_true")
     ap.add_argument("--algo", type=int, default=0)
-    ap.add_argument("--side-priority", type=int, default=-1, help="priority of the rulebook stream (-1 high, 0 default)")
+    ap.add_argument("--side-priority", type=int, default=0, help="priority of the rulebook stream (-1 high, 0 default)")
     ap.add_argument("--diag", action="store_true", help="also time the conv chain with parts of the tcgen05 tile skipped "
                     "(btc_sparse_conv_tc_diag masks; wrong results, timing only)")
+    ap.add_argument("--grids", default="", help="comma-separated caps on the conv grid: only the captured graph is timed per cap")
     ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
                     "(one JSON line each), e.g. '16,1,1;16,0,1;16,1,0'")
     args = ap.parse_args()
+    if args.grids:
+        grid_sweep(args)
+        return
     for v in args.variants.split(";"):
         npw, cat, dyn = (int(x) for x in v.split(","))
         run(args, npw, cat, dyn)
+
+
+def grid_sweep(args):
+    """Captured-graph time of the whole step for several caps on the persistent conv grid."""
+    from btcdet_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, N = args.batch, 20000
+    pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
+    pts_d, offs_d = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
+    out = []
+    for g in [int(x) for x in args.grids.split(",")]:
+        lib.btc_sparse_conv_tc_grid(g)
+        torch.manual_seed(0)
+        model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+        plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                                   max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
+                                   device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority).capture()
+        plan.load_points(pts_d, offs_d)
+        ms = []
+        for r in range(args.reps + 3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.step()
+            e1.record()
+            torch.cuda.synchronize()
+            if r >= 3:
+                ms.append(e0.elapsed_time(e1))
+        out.append({"conv_grid": g, "graph_us": round(float(np.median(ms)) * 1e3, 1)})
+        del plan
+        torch.cuda.empty_cache()
+    lib.btc_sparse_conv_tc_grid(148)
+    print(json.dumps({"batch": B, "grid_sweep": out}), flush=True)
 
 
 def run(args, npw, cat, dyn):
