@@ -559,9 +559,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + j));
                     mbar_wait(&b_empty[sb], pb ^ 1u);          // the MMAs that read this slot have retired
                     tc_fence_after();
-                    mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
-                    bulk_copy_g2s(stages + sb * STAGE_BYTES, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES), 2 * B_BYTES,
-                                  &b_full[sb]);
+                    if (!(diag & 8)) {                         // (timing diagnostics: bit 3 drops the weight-tile copy)
+                        mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
+                        bulk_copy_g2s(stages + sb * STAGE_BYTES, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES),
+                                      2 * B_BYTES, &b_full[sb]);
+                    }
                     mbar_arrive(&b_full[sb]);
                     if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
                 }

@@ -245,7 +245,7 @@ int btc_sparse_conv_tc_supported(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tiles);
 /* Timing diagnostics for the profile write-ups (tools/step_breakdown.py --diag): a non-zero mask makes the tile skip a
  * part of its work — bit 0 the gather, bit 1 the smem read-back / hi-lo split / TMEM stores, bit 2 two of the three
- * MMAs per k-step — so the cost of each pipeline side can be read off a wall-clock difference.  RESULTS ARE WRONG
+ * MMAs per k-step, bit 3 the weight-tile copies — so the cost of each pipeline side can be read off a wall-clock difference.  RESULTS ARE WRONG
  * while the mask is non-zero; 0 (the default) restores the product path. */
 int btc_sparse_conv_tc_diag(int mask);
 /* Cap on the persistent grid of the tcgen05 tile (default 148 = one CTA per SM): a smaller grid leaves whole SMs to

@@ -143,7 +143,8 @@ def run(args, npw, cat, dyn):
                  5: "no gather, 1 MMA", 6: "no split, 1 MMA", 7: "barriers + 1 MMA only"}
         convs = [s for s in plan.steps if s.kind == "conv"]
         diag = []
-        for mask in range(8):
+        names.update({8: "no weight tiles", 9: "no gather, no weight tiles", 15: "barriers + 1 MMA, no weight tiles"})
+        for mask in list(range(8)) + [8, 9, 15]:
             lib.btc_sparse_conv_tc_diag(mask)
             diag.append({"mask": mask, "what": names[mask], "conv_chain_us": timed(conv_chain),
                          "conv32_us": timed(lambda: plan.launch_conv(convs[3].args, st)),
