@@ -512,32 +512,58 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             __syncwarp();
             if (tile < 0) break;
-            for (int j = 0; j < cnt; ++j) {
+            // one stage = 12 (8 with CAT) MMAs + the two commits that free its A and weight slots
+            auto issue_stage = [&](uint32_t sa, uint32_t sw, bool first) {
+                const uint32_t a_hi = tmem_base + A_COL0 + sa * 64u;
+                const uint32_t a_lo = a_hi + 32u;
+                const uint32_t dl = desc_lo0 + sw * (uint32_t)(STAGE_BYTES >> 4);
+#pragma unroll
+                for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
+                    const uint64_t db_hi = desc_hi64 | (uint64_t)(dl + 2u * (uint32_t)kk);
+                    const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+                    if (CAT) {
+                        umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC2, acc);   // D1 | D2
+                        umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, 1u);     // D1
+                    } else {
+                        const uint64_t db_lo = desc_hi64 | (uint64_t)(dl + (uint32_t)(B_BYTES >> 4) + 2u * (uint32_t)kk);
+                        umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, acc);   // small terms first
+                        if (!(diag & 4)) {            // (bit 2: one MMA per k-step instead of three)
+                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
+                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
+                        }
+                    }
+                }
+                umma_commit_a(empty0 + 8u * sa);      // frees the A stage once the MMAs above retire
+                umma_commit_a(bempty0 + 8u * sw);     // ... and the weight stage
+            };
+            // Two stages per trip where the list allows (diag bit 4 forces one): the wait -> fence -> elect -> issue ->
+            // reconverge sequence has a fixed latency that a 12-MMA stage does not cover.
+            int j = 0;
+            if (!(diag & 16))
+            for (; j + 1 < cnt; j += 2) {
+                uint32_t s1 = s + 1, ph1 = ph, sb1 = sb + 1, pb1 = pb;
+                if (s1 == (uint32_t)STAGES) { s1 = 0; ph1 ^= 1u; }
+                if (sb1 == (uint32_t)NB) { sb1 = 0; pb1 ^= 1u; }
+                mbar_wait_a(bfull0 + 8u * sb, pb);
+                mbar_wait_a(full0 + 8u * s, ph);
+                mbar_wait_a(bfull0 + 8u * sb1, pb1);
+                mbar_wait_a(full0 + 8u * s1, ph1);
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_stage(s, sb, j == 0);
+                    issue_stage(s1, sb1, false);
+                }
+                __syncwarp();
+                s = s1 + 1; ph = ph1;
+                if (s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+                sb = sb1 + 1; pb = pb1;
+                if (sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
+            }
+            for (; j < cnt; ++j) {
                 mbar_wait_a(bfull0 + 8u * sb, pb);       // weight tile landed (requested NB stages ago)
                 mbar_wait_a(full0 + 8u * s, ph);         // A operand in TMEM
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_hi = tmem_base + A_COL0 + s * 64u;
-                    const uint32_t a_lo = a_hi + 32u;
-                    const uint32_t dl = desc_lo0 + sb * (uint32_t)(STAGE_BYTES >> 4);
-#pragma unroll
-                    for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
-                        const uint64_t db_hi = desc_hi64 | (uint64_t)(dl + 2u * (uint32_t)kk);
-                        if (CAT) {
-                            umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC2, (j | kk) != 0);   // D1 | D2
-                            umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, 1u);                // D1
-                        } else {
-                            const uint64_t db_lo = desc_hi64 | (uint64_t)(dl + (uint32_t)(B_BYTES >> 4) + 2u * (uint32_t)kk);
-                            umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, (j | kk) != 0);   // small terms first
-                            if (!(diag & 4)) {            // (bit 2: one MMA per k-step instead of three)
-                                umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
-                                umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
-                            }
-                        }
-                    }
-                    umma_commit_a(empty0 + 8u * s);      // frees the A stage once the MMAs above retire
-                    umma_commit_a(bempty0 + 8u * sb);    // ... and the weight stage
-                }
+                if (elect_one()) issue_stage(s, sb, j == 0);
                 __syncwarp();
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
                 if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }

@@ -143,8 +143,9 @@ def run(args, npw, cat, dyn):
                  5: "no gather, 1 MMA", 6: "no split, 1 MMA", 7: "barriers + 1 MMA only"}
         convs = [s for s in plan.steps if s.kind == "conv"]
         diag = []
-        names.update({8: "no weight tiles", 9: "no gather, no weight tiles", 15: "barriers + 1 MMA, no weight tiles"})
-        for mask in list(range(8)) + [8, 9, 15]:
+        names.update({8: "no weight tiles", 15: "barriers + 1 MMA, no weight tiles", 16: "full, one stage per issue trip",
+                      31: "skeleton, one stage per issue trip"})
+        for mask in [0, 16, 15, 31, 7, 3, 4]:
             lib.btc_sparse_conv_tc_diag(mask)
             diag.append({"mask": mask, "what": names[mask], "conv_chain_us": timed(conv_chain),
                          "conv32_us": timed(lambda: plan.launch_conv(convs[3].args, st)),
