@@ -202,13 +202,13 @@ template <int NPW> struct TcRoles {
 // A-operand ring in TMEM: 64 columns (hi + lo) per stage next to the two accumulators — six stages where they fit
 // (N <= 64 without the concatenated-B accumulators), four otherwise.  Each producer group then has a stage to fill while
 // its previous one is still being multiplied.
-template <int N, bool CAT> struct TcAStages { static constexpr int value = (2 * (CAT ? 2 * N : N) + 64 * 6 <= 512) ? 6 : 4; };
+template <int N, bool CAT> struct TcAStages { static constexpr int value = N <= 32 ? 6 : 4; };
 // Weight-tile ring: deeper than the A ring where shared memory allows (64 KB: 8 stages at N = 32, 4 at N = 64; 4 x 32 KB at
 // N = 128) and fed by its own loader warp.  Round-1 timing diagnostics (tools/step_breakdown.py --diag): with the gather,
 // the split and two of the three MMAs removed the layer still took 70 % of its time — the weight tile of a stage was
 // requested by a producer thread only after it had finished its own gather work AND the stage had drained, so every
 // stage exposed a full L2 -> smem TMA latency.  The loader requests tile c + NB the moment the MMAs of tile c retire.
-template <int N> struct TcBStages { static constexpr int value = N <= 32 ? 8 : 4; };
+template <int N> struct TcBStages { static constexpr int value = N <= 32 ? 6 : 4; };   // == TcAStages: one ring index, one commit
 template <int N, int NPW> struct TcDepth { static constexpr int value = (N > 64 || NPW > 8) ? 2 : 4; };   // cp.async gather stages in flight per producer warp (smem budget)
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
@@ -277,6 +277,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     constexpr int G = Roles::kGroups;               // producer groups; group g feeds the stages with gi % G == g
     constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx, TC_BLD_WARP = Roles::kBld;
     constexpr int NB = TcBStages<N>::value;         // weight-tile ring depth
+    static_assert(NB == TcAStages<N, CAT>::value, "the A ring and the weight ring share slot index, phase and the commit");
     static_assert(G <= STAGES, "a group advances by G stages and may wrap the ring at most once per step");
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
@@ -295,7 +296,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     int* nbr_s = (int*)(a_stage + TC_PRODUCER_WARPS * TC_DEPTH * 4096);     // [2][TC_BM * K]
 
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], nbr_full[2], nbr_empty[2],
-        list_full[2], b_full[8], b_empty[8];
+        list_full[2], b_full[8];
     __shared__ uint32_t s_tmem;
     __shared__ int s_cnt[2];                        // active reduction chunks of the tile in each index buffer
     __shared__ int s_tile[2];                       // tile id in each index buffer (-1: no more tiles for this CTA)
@@ -320,7 +321,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(&b_full[s], 1);              // the weight loader's arrive (+ bulk-copy tx bytes)
-            mbar_init(&b_empty[s], 1);             // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 2);           // the issuer's early arrive (publishes the tile id) + one tcgen05.commit
@@ -490,11 +490,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // and the descriptor words are hoisted, and a stage's descriptors differ from the base only by an add on the
         // 14-bit start-address field (no carry: shared addresses < 256 KB).
         const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]);
+        const uint32_t bfull0 = smem_u32(&b_full[0]);
         const uint64_t desc0 = make_desc_sw128(smem_u32(stages));
         const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = (uint32_t)desc0;
-        uint32_t s = 0, ph = 0, sb = 0, pb = 0;   // A ring slot / phase, weight ring slot / phase
+        uint32_t s = 0, ph = 0;   // ring slot / phase (A operand in TMEM and weight tile in smem share both)
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
             mbar_wait(&list_full[buf], (tl >> 1) & 1);
@@ -513,10 +513,10 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             __syncwarp();
             if (tile < 0) break;
             // one stage = 12 (8 with CAT) MMAs + the two commits that free its A and weight slots
-            auto issue_stage = [&](uint32_t sa, uint32_t sw, bool first) {
+            auto issue_stage = [&](uint32_t sa, bool first) {
                 const uint32_t a_hi = tmem_base + A_COL0 + sa * 64u;
                 const uint32_t a_lo = a_hi + 32u;
-                const uint32_t dl = desc_lo0 + sw * (uint32_t)(STAGE_BYTES >> 4);
+                const uint32_t dl = desc_lo0 + sa * (uint32_t)(STAGE_BYTES >> 4);
 #pragma unroll
                 for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
                     const uint64_t db_hi = desc_hi64 | (uint64_t)(dl + 2u * (uint32_t)kk);
@@ -533,40 +533,35 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                         }
                     }
                 }
-                umma_commit_a(empty0 + 8u * sa);      // frees the A stage once the MMAs above retire
-                umma_commit_a(bempty0 + 8u * sw);     // ... and the weight stage
+                umma_commit_a(empty0 + 8u * sa);      // frees the A stage and the weight stage once the MMAs above retire
             };
             // Two stages per trip where the list allows (diag bit 4 forces one): the wait -> fence -> elect -> issue ->
             // reconverge sequence has a fixed latency that a 12-MMA stage does not cover.
             int j = 0;
             if (!(diag & 16))
             for (; j + 1 < cnt; j += 2) {
-                uint32_t s1 = s + 1, ph1 = ph, sb1 = sb + 1, pb1 = pb;
+                uint32_t s1 = s + 1, ph1 = ph;
                 if (s1 == (uint32_t)STAGES) { s1 = 0; ph1 ^= 1u; }
-                if (sb1 == (uint32_t)NB) { sb1 = 0; pb1 ^= 1u; }
-                mbar_wait_a(bfull0 + 8u * sb, pb);
+                mbar_wait_a(bfull0 + 8u * s, ph);
                 mbar_wait_a(full0 + 8u * s, ph);
-                mbar_wait_a(bfull0 + 8u * sb1, pb1);
+                mbar_wait_a(bfull0 + 8u * s1, ph1);
                 mbar_wait_a(full0 + 8u * s1, ph1);
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_stage(s, sb, j == 0);
-                    issue_stage(s1, sb1, false);
+                    issue_stage(s, j == 0);
+                    issue_stage(s1, false);
                 }
                 __syncwarp();
                 s = s1 + 1; ph = ph1;
                 if (s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
-                sb = sb1 + 1; pb = pb1;
-                if (sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
             }
             for (; j < cnt; ++j) {
-                mbar_wait_a(bfull0 + 8u * sb, pb);       // weight tile landed (requested NB stages ago)
+                mbar_wait_a(bfull0 + 8u * s, ph);        // weight tile landed (requested STAGES stages ago)
                 mbar_wait_a(full0 + 8u * s, ph);         // A operand in TMEM
                 tc_fence_after();
-                if (elect_one()) issue_stage(s, sb, j == 0);
+                if (elect_one()) issue_stage(s, j == 0);
                 __syncwarp();
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
-                if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
             }
             if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
             __syncwarp();
@@ -583,7 +578,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 const int cnt = s_cnt[buf];
                 for (int j = 0; j < cnt; ++j) {
                     const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + j));
-                    mbar_wait(&b_empty[sb], pb ^ 1u);          // the MMAs that read this slot have retired
+                    mbar_wait(&empty_bar[sb], pb ^ 1u);        // the MMAs that read this slot have retired
                     tc_fence_after();
                     if (!(diag & 8)) {                         // (timing diagnostics: bit 3 drops the weight-tile copy)
                         mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
@@ -762,7 +757,7 @@ static int* next_tile_counter() {
 // dynamic shared memory of one CTA: weight ring + cp.async staging + two index tiles + two chunk lists + alignment slack
 static size_t tc_smem_bytes(int N, int npw, int K, int c_in) {
     const int stage_bytes = 2 * N * 128;
-    const int nb = N <= 32 ? 8 : 4, depth = (N > 64 || npw > 8) ? 2 : 4;
+    const int nb = N <= 32 ? 6 : 4, depth = (N > 64 || npw > 8) ? 2 : 4;
     const int T = (K * c_in + TC_KC - 1) / TC_KC;
     return (size_t)nb * stage_bytes + (size_t)npw * depth * 4096 + (size_t)2 * TC_BM * K * sizeof(int) +
            (size_t)((4 * T + 15) & ~15) + 1024 + 16;
@@ -773,7 +768,7 @@ template <int N, int NPW, bool CAT>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
-    static_assert(TcBStages<N>::value == (N <= 32 ? 8 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
+    static_assert(TcBStages<N>::value == (N <= 32 ? 6 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
                   "tc_smem_bytes mirrors these");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
     auto kern = conv_fwd_tc_kernel<N, NPW, CAT>;
