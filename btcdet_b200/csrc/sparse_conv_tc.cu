@@ -199,16 +199,14 @@ template <int NPW> struct TcRoles {
     static constexpr int kWarps = ((NPW + 7 + 3) / 4) * 4;
     static constexpr int kThreads = kWarps * 32;
 };
-// A-operand ring in TMEM: 64 columns (hi + lo) per stage next to the two accumulators — six stages where they fit
-// (N <= 64 without the concatenated-B accumulators), four otherwise.  Each producer group then has a stage to fill while
-// its previous one is still being multiplied.
+// Operand rings.  A: 64 TMEM columns (hi + lo) per stage next to the two accumulators; weights: one packed hi/lo tile
+// (2 * N * 128 B) per stage in shared memory, fetched by the loader warp the moment the MMAs that read the slot retire.
+// Both rings share the slot index, the phase and ONE tcgen05.commit per stage (empty_bar), so their depth is the same:
+// six stages at N = 32 (448 TMEM columns, 48 KB of weight tiles), four at N = 64 / 128 (64 / 128 KB of weight tiles).
+// Round-1 timing diagnostics (tools/step_breakdown.py --diag) on the way here: separate, deeper rings (6 x A, 8 x B) and
+// a second commit per stage were within 1 % of this; dropping the weight copies altogether changes < 1 %.
 template <int N, bool CAT> struct TcAStages { static constexpr int value = N <= 32 ? 6 : 4; };
-// Weight-tile ring: deeper than the A ring where shared memory allows (64 KB: 8 stages at N = 32, 4 at N = 64; 4 x 32 KB at
-// N = 128) and fed by its own loader warp.  Round-1 timing diagnostics (tools/step_breakdown.py --diag): with the gather,
-// the split and two of the three MMAs removed the layer still took 70 % of its time — the weight tile of a stage was
-// requested by a producer thread only after it had finished its own gather work AND the stage had drained, so every
-// stage exposed a full L2 -> smem TMA latency.  The loader requests tile c + NB the moment the MMAs of tile c retire.
-template <int N> struct TcBStages { static constexpr int value = N <= 32 ? 6 : 4; };   // == TcAStages: one ring index, one commit
+template <int N> struct TcBStages { static constexpr int value = N <= 32 ? 6 : 4; };   // == TcAStages
 template <int N, int NPW> struct TcDepth { static constexpr int value = (N > 64 || NPW > 8) ? 2 : 4; };   // cp.async gather stages in flight per producer warp (smem budget)
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
@@ -254,8 +252,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // CAT: the hi and lo weight tiles of a stage are adjacent in shared memory, i.e. one K-major tile of 2N rows, so
