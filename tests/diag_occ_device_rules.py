@@ -1,3 +1,7 @@
+"""Diagnostic (not collected by pytest): where the occlusion masks of the CUDA kernel, the torch restatement on the
+GPU and the torch restatement on the CPU differ, and why (torch's tensor / python_scalar rule per device, libm ulps on
+bin edges).  Lives under tests/ because it uses the oracle, which only test infrastructure may import.
+  python tests/diag_occ_device_rules.py        # on a B200"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -7,7 +7,7 @@ edges, so results are one-ulp sensitive.  The CPU oracle (pinned bit-for-bit to 
 tests/test_occ_oracle_cpu.py) differs from a CUDA run of the same torch code in ~10 % of the occluded cells
 because torch divides by python scalars differently per device; with oracle.occ_masks.CUDA_SCALAR_DIV the CPU run
 follows the CUDA rule and only libm-ulp edge cases remain (~5 % of the occluded cells on the fixture scene, bounded
-at 10 % below; tools/occ_diag.py prints the breakdown)."""
+at 10 % below; tests/diag_occ_device_rules.py prints the breakdown)."""
 import os
 import sys
 
