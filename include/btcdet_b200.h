@@ -229,8 +229,9 @@ int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out,
 
 /*
  * Tensor-core variant (tcgen05.mma kind::tf32 with the 3xTF32 split, accumulator in TMEM):
- * same contract as btc_sparse_conv_fwd, for c_in % 4 == 0, c_out % 4 == 0, c_out <= 128, K <= 33 (the two
- * [128 x K] index tiles must fit in shared memory next to the operand rings; btc_sparse_conv_tc_supported says),
+ * same contract as btc_sparse_conv_fwd, for c_in % 4 == 0, c_out % 4 == 0, c_out <= 128, K <= 33 (49 when
+ * c_out <= 32: the two [128 x K] index tiles must fit in shared memory next to the operand rings;
+ * btc_sparse_conv_tc_supported says),
  * K * c_in >= 32.  The reduction runs over the flattened (offset, input channel) axis in chunks
  * of 32, so thin layers (c_in = 4, 16) pack several offsets into one MMA stage.  The weights are
  * packed once per layer into the shared-memory image of the K-major, 128-byte-swizzled hi/lo

@@ -64,3 +64,48 @@ def test_product_does_not_import_oracle():
                     src = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle|liboracle|orc_[a-z_]+\(", src, flags=re.M), \
                         os.path.join(dirpath, f)
+
+
+def test_tensor_core_tile_host_queries(lib_path):
+    """Host-side contract of the tcgen05 tile: supported shapes (incl. the shared-memory bound on K), packed sizes, knobs."""
+    from btcdet_b200 import _lib
+    lib = _lib.load()
+    sup = lib.btc_sparse_conv_tc_supported
+    # every layer shape of VoxelBackBone8x / VoxelBackBone8xOcc / the occupancy backbone that is a multiple of 4 channels
+    for K, cin, cout in [(27, 4, 16), (27, 16, 16), (27, 16, 32), (27, 32, 32), (27, 32, 64), (27, 64, 64), (3, 64, 128),
+                         (2, 128, 64), (27, 256, 128), (27, 128, 128), (27, 32, 2 * 2)]:
+        assert sup(K, cin, cout) == 1, (K, cin, cout)
+    assert sup(27, 6, 16) == 0 and sup(27, 34, 32) == 0          # c_in % 4 != 0 -> FFMA tile
+    assert sup(27, 32, 3) == 0 and sup(27, 32, 256) == 0         # c_out % 4 != 0 / > 128
+    assert sup(1, 4, 16) == 0                                    # reduction shorter than one 32-element stage
+    assert sup(33, 32, 64) == 1 and sup(34, 32, 64) == 0         # two [128 x K] index tiles must fit next to the rings
+    assert sup(49, 32, 32) == 1 and sup(50, 32, 32) == 0         # (the N = 32 weight ring is 16 KB smaller)
+    assert sup(64, 32, 32) == 0 and sup(125, 16, 16) == 0
+    # packed image: per 32-element chunk a hi and a lo tile of N x 128 bytes, N = c_out padded to 32 / 64 / 128
+    assert lib.btc_sparse_conv_tc_packed_bytes(27, 64, 64) == (27 * 64 // 32) * 2 * 64 * 128
+    assert lib.btc_sparse_conv_tc_packed_bytes(27, 4, 16) == 4 * 2 * 32 * 128          # ceil(108 / 32) = 4 chunks
+    assert lib.btc_sparse_conv_tc_packed_bytes(3, 64, 128) == 6 * 2 * 128 * 128
+    assert lib.btc_sparse_conv_tc_packed_bytes(27, 6, 16) < 0
+    # knobs validate their arguments and keep the defaults otherwise
+    assert lib.btc_sparse_conv_tc_config(-1, -1, -1) == 0
+    assert lib.btc_sparse_conv_tc_config(12, -1, -1) == -1 and b"producer_warps" in lib.btc_last_error()
+    assert lib.btc_sparse_conv_tc_config(16, 0, 1) == 0
+    assert lib.btc_sparse_conv_tc_grid(0) == -1 and lib.btc_sparse_conv_tc_grid(149) == -1
+    assert lib.btc_sparse_conv_tc_grid(148) == 0
+    assert lib.btc_sparse_conv_tc_diag(0) == 0
+
+
+def test_workspace_and_capacity_queries(lib_path):
+    from btcdet_b200 import _lib
+    lib = _lib.load()
+    n = lib.btc_hash_slots(20000)
+    assert n >= 2 * 20000 and n & (n - 1) == 0                   # open addressing at load <= 0.5, power of two
+    assert lib.btc_hash_slots(0) >= 1
+    e = lib.btc_index_entries(2, _lib.int3([21, 800, 704]))
+    assert e == (2 * 21 * 800 * 704 + 31) // 32
+    assert lib.btc_index_workspace_bytes(e) > 0
+    assert lib.btc_rulebook_pairs_workspace_bytes(100000, 27) >= ((100000 + 2047) // 2048) * 27 * 4
+    assert lib.btc_sparse_conv_bwd_workspace_bytes(27, 64, 64) >= 27 * 64 * 64 * 4
+    assert lib.btc_revoxelize_workspace_bytes(40000, e) > 0
+    assert lib.btc_occ_select_workspace_bytes(2, _lib.int3([209, 157, 9])) > 0
+    assert lib.btc_occ_box_targets_workspace_bytes(2, 12, 40000, 1000) > 0
