@@ -260,7 +260,10 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // cycles, a third fewer instructions and half the descriptors on the single issuing thread, which the round-1 source-
 // level profile showed to be the critical path (~100 instructions, ~800 cycles per stage against 384 cycles of MMA).
 // Needs 4N + 64*STAGES <= 512 TMEM columns: N <= 64.
-template <int N, int NPW, bool CAT>
+// CG (commit group): the stages of a ring are released in groups of CG with ONE tcgen05.commit after the last stage of a
+// group (empty barrier per slot group).  CG = 1 is the measured round-1 default; CG = 2 / 3 is the experiment DESIGN.md
+// §8.1(0) calls for (a per-stage commit appears to drain the MMA pipeline) and is not yet verified on hardware.
+template <int N, int NPW, bool CAT, int CG>
 __global__ void __launch_bounds__(TcRoles<NPW>::kThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
@@ -274,6 +277,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx, TC_BLD_WARP = Roles::kBld;
     constexpr int NB = TcBStages<N>::value;         // weight-tile ring depth
     static_assert(NB == TcAStages<N, CAT>::value, "the A ring and the weight ring share slot index, phase and the commit");
+    static_assert(CG >= 1 && STAGES % CG == 0, "commit groups tile the ring");
     static_assert(G <= STAGES, "a group advances by G stages and may wrap the ring at most once per step");
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
@@ -444,7 +448,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();                          // everyone has read the slot before it is refilled
-            mbar_wait_a(empty0 + 8u * (uint32_t)s, (uint32_t)(ph ^ 1));
+            mbar_wait_a(empty0 + 8u * (uint32_t)(s / CG), (uint32_t)(ph ^ 1));
             tc_fence_after();
             // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
             // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
@@ -529,7 +533,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                         }
                     }
                 }
-                umma_commit_a(empty0 + 8u * sa);      // frees the A stage and the weight stage once the MMAs above retire
+                if (CG == 1 || sa % CG == CG - 1)   // last stage of its commit group
+                    umma_commit_a(empty0 + 8u * (sa / CG));   // frees the A and weight stages (of the group) once the MMAs retire
             };
             // Two stages per trip where the list allows (diag bit 4 forces one): the wait -> fence -> elect -> issue ->
             // reconverge sequence has a fixed latency that a 12-MMA stage does not cover.
@@ -574,7 +579,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 const int cnt = s_cnt[buf];
                 for (int j = 0; j < cnt; ++j) {
                     const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + j));
-                    mbar_wait(&empty_bar[sb], pb ^ 1u);        // the MMAs that read this slot have retired
+                    mbar_wait(&empty_bar[sb / CG], pb ^ 1u);   // the MMAs that read this slot (group) have retired
                     tc_fence_after();
                     if (!(diag & 8)) {                         // (timing diagnostics: bit 3 drops the weight-tile copy)
                         mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
@@ -735,7 +740,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
-static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM;
+static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM, g_tc_cg = 1;
 
 static int* next_tile_counter() {
     static int* base[64] = {nullptr};
@@ -760,14 +765,14 @@ static size_t tc_smem_bytes(int N, int npw, int K, int c_in) {
 }
 constexpr size_t kTcMaxSmem = 227 * 1024;
 
-template <int N, int NPW, bool CAT>
+template <int N, int NPW, bool CAT, int CG = 1>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
     static_assert(TcBStages<N>::value == (N <= 32 ? 6 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
                   "tc_smem_bytes mirrors these");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
-    auto kern = conv_fwd_tc_kernel<N, NPW, CAT>;
+    auto kern = conv_fwd_tc_kernel<N, NPW, CAT, CG>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
@@ -812,18 +817,20 @@ static int launch_tc(const float* feat_in, const int* table, const float* packed
                      const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
     tc_config_init();
     constexpr int NS = N <= 64 ? N : 64;   // instantiation guard for the N <= 64 only variants
-    if (N <= 64 && g_tc_npw == 16) {
-        if (g_tc_cat)
-            return launch_tc_npw<NS, 16, true>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
-                                               n_dev, K, c_in, c_out, st);
-        return launch_tc_npw<NS, 16, false>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
-                                            n_dev, K, c_in, c_out, st);
+#define BTC_TC_ARGS feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in, c_out, st
+    if (g_tc_cg > 1 && !g_tc_cat) {        // experimental commit groups (3-MMA k-steps only; 3 needs the six-stage ring)
+        constexpr int CG3 = TcAStages<N, false>::value % 3 == 0 ? 3 : 2;
+        if (N <= 64 && g_tc_npw == 16)
+            return g_tc_cg == 3 ? launch_tc_npw<NS, 16, false, CG3>(BTC_TC_ARGS) : launch_tc_npw<NS, 16, false, 2>(BTC_TC_ARGS);
+        return g_tc_cg == 3 ? launch_tc_npw<N, 8, false, CG3>(BTC_TC_ARGS) : launch_tc_npw<N, 8, false, 2>(BTC_TC_ARGS);
     }
-    if (N <= 64 && g_tc_cat)
-        return launch_tc_npw<NS, 8, true>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev,
-                                          K, c_in, c_out, st);
-    return launch_tc_npw<N, 8, false>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K,
-                                      c_in, c_out, st);
+    if (N <= 64 && g_tc_npw == 16) {
+        if (g_tc_cat) return launch_tc_npw<NS, 16, true>(BTC_TC_ARGS);
+        return launch_tc_npw<NS, 16, false>(BTC_TC_ARGS);
+    }
+    if (N <= 64 && g_tc_cat) return launch_tc_npw<NS, 8, true>(BTC_TC_ARGS);
+    return launch_tc_npw<N, 8, false>(BTC_TC_ARGS);
+#undef BTC_TC_ARGS
 }
 
 static int tc_padded_n(int c_out) {
@@ -847,6 +854,12 @@ int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tile
     }
     if (concat_b >= 0) g_tc_cat = concat_b ? 1 : 0;
     if (dynamic_tiles >= 0) g_tc_dyn = dynamic_tiles ? 1 : 0;
+    return BTC_OK;
+}
+
+int btc_sparse_conv_tc_commit_group(int stages) {
+    if (stages < 1 || stages > 3) return badarg("btc_sparse_conv_tc_commit_group: stages must be 1, 2 or 3");
+    g_tc_cg = stages;
     return BTC_OK;
 }
 

@@ -271,6 +271,11 @@ def tc_config(producer_warps=-1, concat_b=-1, dynamic_tiles=-1):
           "btc_sparse_conv_tc_config")
 
 
+def tc_commit_group(stages=1):
+    """EXPERIMENTAL: one tcgen05.commit per group of `stages` ring stages (1 = verified default)."""
+    check(_lib.load().btc_sparse_conv_tc_commit_group(int(stages)), "btc_sparse_conv_tc_commit_group")
+
+
 def tc_pack_weight(weight):
     """Pack [K,Cin,Cout] (or [*k,Cin,Cout]) fp32 weights into the tcgen05 operand image (hi/lo tf32 split,
     K-major, 128-byte swizzle) consumed by sparse_conv_fwd_tc."""

@@ -252,6 +252,10 @@ int btc_sparse_conv_tc_diag(int mask);
 /* Cap on the persistent grid of the tcgen05 tile (default 148 = one CTA per SM): a smaller grid leaves whole SMs to
  * kernels running concurrently on other streams (the rulebook chain of the engine).  Process-wide. */
 int btc_sparse_conv_tc_grid(int max_ctas);
+/* EXPERIMENTAL (not verified on hardware in round 1; default 1 = the verified path, whose machine code is unchanged):
+ * release the operand-ring stages in groups of `stages` (1, 2 or 3; 3 falls back to 2 where the ring has four slots)
+ * with one tcgen05.commit per group instead of one per stage.  Process-wide. */
+int btc_sparse_conv_tc_commit_group(int stages);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
 int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA library (through its C ABI / the spconv shim) against the CPU oracle on
 the same seeded inputs.  Integer outputs (voxel ids, coordinates, rulebooks) bit-exact; sparse-conv
 activations within 1e-4 relative fp32 (north_star tolerance)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -310,6 +312,40 @@ def test_tensor_core_tile_variants(cuda, npw, cat, dyn, n_out, K, cin, cout, den
         ops.sparse_conv_fwd_tc(feat, table, packed, cin, cout, bias, n_out_dev=n_dev, out=static)
         assert torch.equal(static, outs[0])
     finally:
+        ops.tc_config(16, 0, 1)
+
+
+@pytest.mark.skipif(os.environ.get("BTC_TEST_EXPERIMENTAL") != "1",
+                    reason="commit groups > 1 are not verified on hardware yet (DESIGN.md §8.1(0)); set BTC_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("cg,npw", [(2, 16), (3, 16), (2, 8)])
+@pytest.mark.parametrize("n_out,K,cin,cout,density,run", [
+    (45000, 27, 32, 32, 0.27, 97), (33000, 27, 64, 64, 0.35, 300), (70000, 27, 16, 16, 0.03, 1024),
+    (21000, 3, 64, 128, 0.45, 97), (130, 27, 32, 64, 0.2, 7)])
+def test_tensor_core_commit_groups_experimental(cuda, cg, npw, n_out, K, cin, cout, density, run):
+    """One tcgen05.commit per 2 / 3 stages: bit-identical to the per-stage-commit tile (same MMAs, same order)."""
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(n_out + K + cin)
+    n_in = 40000
+    pat = rng.random((64, K)) < density
+    valid = pat[(np.arange(n_out) // run) % 64] ^ (rng.random((n_out, K)) < 0.01)
+    valid[:, K // 2] |= ~valid.any(1)
+    nbr = torch.from_numpy(np.where(valid, rng.integers(0, n_in, (n_out, K)), -1).astype(np.int32)).cuda()
+    n_dev = torch.tensor([n_out], dtype=torch.int32, device="cuda")
+    feat = torch.from_numpy(rng.standard_normal((n_in, cin)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32)).cuda()
+    packed = ops.tc_pack_weight(w)
+    try:
+        ops.tc_config(npw, 0, 1)
+        ref = torch.zeros((n_out, cout), device="cuda")
+        ops.sparse_conv_fwd_tc(feat, nbr, packed, cin, cout, None, n_out_dev=n_dev, out=ref)
+        ops.tc_commit_group(cg)
+        for rep in range(2):
+            out = torch.zeros((n_out, cout), device="cuda")
+            ops.sparse_conv_fwd_tc(feat, nbr, packed, cin, cout, None, n_out_dev=n_dev, out=out)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)
+    finally:
+        ops.tc_commit_group(1)
         ops.tc_config(16, 0, 1)
 
 
