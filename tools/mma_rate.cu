@@ -1,6 +1,10 @@
 // Micro-benchmark: issue-to-retire cost of tcgen05.mma (kind::tf32 / kind::f16) on sm_100a as a
 // function of N and of the accumulator dependency pattern.  One CTA, one issuing thread.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu && ./mma_rate
+// Modes 6 / 7 (added at the end of round 1, not run on hardware yet) probe the hypothesis of DESIGN.md §8.1(0):
+//   6: elect-uniform TS issue with a tcgen05.commit after every `group` MMAs (rotating mbarriers nobody waits on):
+//      if a commit drains the MMA pipeline, cycles/MMA rises as `group` shrinks;
+//   7: mode 6 while warps 1-3 keep writing other TMEM columns with tcgen05.st (the producers' traffic).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -32,15 +36,19 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
 
 // mode: 0 = SS one accumulator, 1 = SS two accumulators alternating, 2 = TS one accumulator, 3 = TS two accumulators
 template <int KIND>
-__global__ void __launch_bounds__(128) bench(int N, int mode, int iters, long long* out) {
+__global__ void __launch_bounds__(128) bench(int N, int mode, int iters, long long* out, int group = 12) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar;
+    __shared__ uint64_t ring[8];
     __shared__ uint32_t s_tmem;
+    __shared__ volatile int s_stop;
     for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((float*)smem)[i] = 0.001f * (i % 7);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring[i])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_stop = 0;
     }
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
@@ -51,6 +59,48 @@ __global__ void __launch_bounds__(128) bench(int N, int mode, int iters, long lo
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tm = s_tmem;
+    if (mode == 6 || mode == 7) {
+        if (threadIdx.x < 32) {
+            uint32_t fmt = KIND == 0 ? 2u : 1u;
+            uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint64_t db = make_desc_sw128(smem_u32(smem + 16384));
+            long long t0 = clock64();
+            int since = 0, slot = 0;
+            for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t pred = 0;
+                    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+                    if (pred) mma_ts<KIND>(tm, tm + 384 + (u & 3) * 8, db + (u & 3) * 2, idesc, 1u);
+                }
+                since += 4;
+                if (since >= group) {
+                    since = 0;
+                    uint32_t pred = 0;
+                    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+                    if (pred) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ring[slot])) : "memory");
+                    slot = (slot + 1) & 7;
+                }
+            }
+            uint32_t pred = 0;
+            asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+            if (pred) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+            } while (!done);
+            long long t1 = clock64();
+            if (threadIdx.x == 0) { out[0] = t1 - t0; s_stop = 1; }
+        } else if (mode == 7) {
+            // warps 1-3: keep storing 32 columns of their TMEM lane quarter (columns 256..287, not touched by the MMAs)
+            const uint32_t lane_base = tm + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + 256u;
+            while (!s_stop) {
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(lane_base), "r"(threadIdx.x) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(lane_base + 16u), "r"(threadIdx.x) : "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+        }
+    } else
     if (mode == 5) {
         // warp-uniform issue loop: the whole warp runs the loop, one ELECTed lane issues (CUTLASS style)
         if (threadIdx.x < 32) {
@@ -130,6 +180,20 @@ int main() {
                 double cyc = (double)h / iters;
                 int K = kind == 0 ? 8 : 16;
                 printf("%s M=128 N=%3d K=%2d %s: %7.1f cycles/MMA  -> %7.0f MAC/clk\n", kind == 0 ? "tf32" : "bf16", N, K, names[mode], cyc, 128.0 * N * K / cyc);
+            }
+    // commit-drain probe (modes 6 / 7), tf32 only
+    for (int N : {32, 64})
+        for (int mode = 6; mode < 8; ++mode)
+            for (int group : {4, 12, 24, 48, 4096}) {
+                long long h = 0;
+                for (int rep = 0; rep < 2; ++rep) {
+                    bench<0><<<1, 128, smem>>>(N, mode, iters, d_out, group);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                    cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+                }
+                printf("tf32 M=128 N=%3d K= 8 TS elect-uniform, commit every %4d MMAs%s: %7.1f cycles/MMA\n", N, group,
+                       mode == 7 ? " + tcgen05.st traffic" : "", (double)h / iters);
             }
     return 0;
 }
