@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# First GPU call of the next round: the experiments DESIGN.md §8.1(0) asks for, cheapest first (~2 min on one B200).
+#   gpurun --timeout 600 -- 'bash tools/round2_battery.sh'
+# Everything lands in gpurun_out/battery_*.  Nothing here changes defaults; read the numbers, then decide.
+set -u
+mkdir -p gpurun_out
+# 1. cycles per MMA against MMAs per tcgen05.commit, in isolation (modes 6 / 7 at the end of the output)
+timeout 60 ./tools/mma_rate > gpurun_out/battery_mma_rate.txt 2>&1 || echo "mma_rate failed" >> gpurun_out/battery_mma_rate.txt
+tail -22 gpurun_out/battery_mma_rate.txt
+# 2. commit groups: bit-identity with the per-stage-commit tile (a hang is cut by pytest's timeout)
+BTC_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_parity_gpu.py -k commit_groups -x -q --timeout 120 \
+    > gpurun_out/battery_cg_tests.log 2>&1
+tail -3 gpurun_out/battery_cg_tests.log
+# 3. step anatomy + timing diagnostics for commit groups 1 / 2 / 3 (only if 2. passed)
+if grep -q " passed" gpurun_out/battery_cg_tests.log && ! grep -q "failed\|error" gpurun_out/battery_cg_tests.log; then
+    for cg in 1 2 3; do
+        timeout 120 python tools/step_breakdown.py --commit-group $cg --diag --reps 10 > gpurun_out/battery_breakdown_cg$cg.json \
+            2> gpurun_out/battery_breakdown_cg$cg.err
+        python - <<PY
+import json
+d = json.loads(open("gpurun_out/battery_breakdown_cg$cg.json").read().strip().splitlines()[-1])
+print("commit group $cg: conv chain %.0f us, graph %.0f us" % (d["conv_chain_us"], d["graph_us"]))
+for r in d["diag"]:
+    print("   mask %2d %-40s conv chain %7.1f  32->32 %6.1f  64->64 %6.1f" % (r["mask"], r["what"], r["conv_chain_us"], r["conv32_us"], r["conv64_us"]))
+PY
+    done
+fi
