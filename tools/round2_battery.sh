@@ -5,6 +5,7 @@
 set -u
 mkdir -p gpurun_out
 # 1. cycles per MMA against MMAs per tcgen05.commit, in isolation (modes 6 / 7 at the end of the output)
+[ -x tools/mma_rate ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_rate tools/mma_rate.cu
 timeout 60 ./tools/mma_rate > gpurun_out/battery_mma_rate.txt 2>&1 || echo "mma_rate failed" >> gpurun_out/battery_mma_rate.txt
 tail -22 gpurun_out/battery_mma_rate.txt
 # 2. commit groups: bit-identity with the per-stage-commit tile (a hang is cut by pytest's timeout)
