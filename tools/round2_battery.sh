@@ -26,3 +26,15 @@ for r in d["diag"]:
 PY
     done
 fi
+# 4. step level: rulebook chain of batch i+1 overlapped with the conv chain of batch i (engine.OverlappedBackbone)
+BTC_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_backbone_gpu.py -k overlapped -x -q --timeout 150 \
+    > gpurun_out/battery_overlap_test.log 2>&1
+tail -3 gpurun_out/battery_overlap_test.log
+if grep -q " passed" gpurun_out/battery_overlap_test.log; then
+    timeout 200 python bench.py --overlap --no-cpu-baseline > gpurun_out/battery_bench_overlap.log 2> gpurun_out/battery_bench_overlap.err
+    python - <<PY
+import json
+b = json.loads(open("gpurun_out/battery_bench_overlap.log").read().strip().splitlines()[-1])
+print("value", b["value"], "e2e", b["e2e"]["value"], "e2e_overlapped", b.get("e2e_overlapped"))
+PY
+fi
