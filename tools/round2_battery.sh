@@ -38,3 +38,11 @@ b = json.loads(open("gpurun_out/battery_bench_overlap.log").read().strip().split
 print("value", b["value"], "e2e", b["e2e"]["value"], "e2e_overlapped", b.get("e2e_overlapped"))
 PY
 fi
+# 5. 8 vs 16 producer warps at the current state of the tile
+timeout 150 python tools/step_breakdown.py --variants "16,0,1;8,0,1" --reps 10 > gpurun_out/battery_npw.json 2> gpurun_out/battery_npw.err
+python - <<PY
+import json
+for line in open("gpurun_out/battery_npw.json"):
+    d = json.loads(line)
+    print(d["variant"], "conv chain", d["conv_chain_us"], "graph", d["graph_us"])
+PY
