@@ -62,6 +62,10 @@ SIGNATURES = {
     "btc_revoxelize_workspace_bytes": (_i64, [_i, _i64]),
     "btc_revoxelize": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_revoxelize_fill": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _i, _p]),
+    # aliases under the names of SURVEY §8(b)'s minimum export set
+    "btc_voxelize_cuda": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_rulebook_pool": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _i64, _p]),
+    "btc_occ_inject_revoxelize": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
 }
 
 _lib = None

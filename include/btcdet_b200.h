@@ -450,6 +450,36 @@ int btc_occ_loss_maps(const uint8_t* voxelwise_mask, const uint8_t* general_mask
                       float* cls_loss_mask_float, uint8_t* reg_loss_mask, float* reg_loss_mask_float,
                       float* res_mtrx, int* pos_all_num, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Aliases under the names of SURVEY.md §8(b)'s minimum export set (thin forwards):                       */
+/*   btc_voxelize_cuda          = btc_voxelize                                                            */
+/*   btc_rulebook_pool          = btc_rulebook_conv with transposed = 0 (SparseMaxPool3d builds a regular   */
+/*                                conv rulebook, spconv 1.2.1 pool.py / SURVEY App. A.6)                   */
+/*   btc_occ_inject_revoxelize  = btc_revoxelize (combine_gt_occ_voxel_point + voxelize_pad,               */
+/*                                btcdet/models/occ_pnt/occ_adder/add_occ_template.py:248-268)               */
+/* ------------------------------------------------------------------------- */
+int btc_voxelize_cuda(const float* points, int n_points, int n_feat,
+                      const int* scene_offsets, int n_scenes,
+                      const float* voxel_size, const float* range, const int* grid,
+                      int max_points, int max_voxels,
+                      float* voxels, int* coords, int* num_points, float* voxel_mean,
+                      int* n_voxels,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int btc_rulebook_pool(const int* coords_in, int n_in_cap, const int* n_in_dev,
+                      int batch, const int* in_shape, const int* out_shape,
+                      const int* ksize, const int* stride, const int* padding,
+                      const int* dilation,
+                      uint64_t* out_index, int64_t out_entries,
+                      int* out_coords, int out_cap, int* n_out,
+                      int* nbr_out, int* nbr_in,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int btc_occ_inject_revoxelize(const int* pt_coords, int n_cap, const int* n_dev,
+                              int batch, const int* shape,
+                              uint64_t* index, int64_t n_entries,
+                              int* vox_coords, int vox_cap, int* vox_count,
+                              int* slots, int* pt_voxel, int* n_voxels, int* max_count,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,3 +109,17 @@ def test_workspace_and_capacity_queries(lib_path):
     assert lib.btc_revoxelize_workspace_bytes(40000, e) > 0
     assert lib.btc_occ_select_workspace_bytes(2, _lib.int3([209, 157, 9])) > 0
     assert lib.btc_occ_box_targets_workspace_bytes(2, 12, 40000, 1000) > 0
+
+
+def test_survey_named_aliases_forward(lib_path):
+    """btc_voxelize_cuda / btc_rulebook_pool / btc_occ_inject_revoxelize are thin forwards: same argument checking."""
+    from btcdet_b200 import _lib
+    lib = _lib.load()
+    three = _lib.int3([1, 1, 1])
+    assert lib.btc_rulebook_pool(None, 0, None, 1, None, None, None, None, None, None, None, 0, None, 0, None, None, None, None, 0,
+                                 None) == lib.btc_rulebook_conv(None, 0, None, 1, None, None, None, None, None, None, 0, None, 0,
+                                                                None, 0, None, None, None, None, 0, None) == -1
+    assert lib.btc_voxelize_cuda(None, 10, 4, None, 1, None, None, three, 5, 100, None, None, None, None, None, None, 0, None) == \
+        lib.btc_voxelize(None, 10, 4, None, 1, None, None, three, 5, 100, None, None, None, None, None, None, 0, None)
+    assert lib.btc_occ_inject_revoxelize(None, 10, None, 1, None, None, 0, None, 0, None, None, None, None, None, None, 0, None) == \
+        lib.btc_revoxelize(None, 10, None, 1, None, None, 0, None, 0, None, None, None, None, None, None, 0, None)
