@@ -46,3 +46,8 @@ for line in open("gpurun_out/battery_npw.json"):
     d = json.loads(line)
     print(d["variant"], "conv chain", d["conv_chain_us"], "graph", d["graph_us"])
 PY
+# 6. training step (config 4 shape, eager shim: fwd + bwd + Adam) and the mask-path timings, for profiles/
+timeout 200 python tools/train_step.py --steps 10 > gpurun_out/battery_train_step.json 2> gpurun_out/battery_train_step.err
+tail -1 gpurun_out/battery_train_step.json
+timeout 120 python -m pytest tests/test_mask_timings_gpu.py tests/test_stress_properties_gpu.py -m gpu -x -q > gpurun_out/battery_masks_stress.log 2>&1
+tail -3 gpurun_out/battery_masks_stress.log
