@@ -17,6 +17,7 @@
 //   * epilogue warps read the (double-buffered) accumulator back with tcgen05.ld, apply bias / folded-BN affine /
 //     ReLU and write the output rows while the next tile's main loop runs.
 #include <stdlib.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace btc {
@@ -743,8 +744,8 @@ __device__ int g_tc_tile_ctr[kTcCtrSlots];
 static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM, g_tc_cg = 1;
 
 static int* next_tile_counter() {
-    static int* base[64] = {nullptr};
-    static unsigned next = 0;
+    static int* base[64] = {nullptr};            // (benign race: every thread computes the same address)
+    static std::atomic<unsigned> next{0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!base[dev]) {
@@ -752,7 +753,7 @@ static int* next_tile_counter() {
         if (cudaGetSymbolAddress(&p, g_tc_tile_ctr) != cudaSuccess) return nullptr;
         base[dev] = (int*)p;
     }
-    return base[dev] + (next++ % kTcCtrSlots);
+    return base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
 }
 
 // dynamic shared memory of one CTA: weight ring + cp.async staging + two index tiles + two chunk lists + alignment slack
