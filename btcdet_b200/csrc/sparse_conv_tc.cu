@@ -178,19 +178,24 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-// Persistent, warp-specialised: one CTA per SM loops over 128-row output tiles.
-//   warps 0-7  : two producer groups (4 warps each, thread == output row); group g feeds the stages with
-//                (global stage index % 2 == g): gather the neighbour row chunk with 16-byte loads (next stage
-//                prefetched in registers), split hi/lo and write the A operand STRAIGHT INTO TENSOR MEMORY with
-//                tcgen05.st — the MMA then reads A from TMEM (".ts" form), so shared memory only carries the
-//                weight tiles.  (An SS-form 3xTF32 step reads 18 KB of smem per 8-deep k-step and is smem-
-//                bandwidth bound at ~70 cycles per MMA; with A in TMEM the same step is compute bound.)
-//   warp  8    : MMA issuer (one elected lane);
-//   warps 9-12 : epilogue (TMEM lane quarter = warp % 4), overlapping the next tile's main loop through a
-//                double-buffered TMEM accumulator;
-//   warp  13   : index loader — TMA-stages each tile's [128 x K] block of the neighbour table into shared
-//                memory with one cp.async.bulk, one tile ahead.
-// TMEM map (512 columns): [0, 2N) two accumulators | [2N + 64*s, +32) A_hi of stage s | [+32, +64) A_lo.
+// Persistent, warp-specialised: one CTA per SM walks 128-row output tiles handed out by a tile scheduler.
+//   producers  : NPW warps in NPW/4 groups (4 warps = 128 rows = the four TMEM lane quarters; thread == output row).
+//                Group g owns the stages whose global index is congruent to g modulo the group count.  Per stage:
+//                cp.async gather of the neighbour rows (8 lanes per row, zero fill, TcDepth stages in flight) into a
+//                swizzled staging slot, read back one row per thread, hi/lo split, tcgen05.st STRAIGHT INTO TENSOR
+//                MEMORY — the MMA reads A from TMEM (".ts" form), so shared memory only carries the weight tiles.
+//                (An SS-form 3xTF32 step reads 18 KB of smem per 8-deep k-step and is smem-bandwidth bound at ~70
+//                cycles per MMA.)
+//   MMA issuer : one warp in warp-uniform control flow, one ELECTed lane issues; two stages per wait/fence/elect trip;
+//                one tcgen05.commit per stage (or per commit group) frees the A slot and the weight slot together;
+//   epilogue   : four warps (TMEM lane quarter = warp % 4), overlapping the next tile's main loop through a
+//                double-buffered TMEM accumulator; the tile id reaches them through s_epi_tile;
+//   index loader / tile scheduler : TMA-stages each tile's [128 x K] block of the neighbour table one tile ahead, builds
+//                the tile's list of active 32-element chunks (block skipping) and fetches tiles statically or from a
+//                global counter; a negative tile id is the end marker every role leaves on;
+//   weight loader : one cp.async.bulk per stage into the weight ring, as soon as the slot's previous MMAs have retired.
+// TMEM map (512 columns): [0, 2*ACC) two accumulators (ACC = N, or 2N with concatenated B) | then per stage s 64 columns:
+// [+0, +32) A_hi, [+32, +64) A_lo.  The protocol is modelled in tests/test_tc_protocol_model.py.
 // Warp roles for NPW producer warps (8 or 16): [0, NPW) producers in NPW/4 groups, NPW = MMA issuer, NPW+1..NPW+4
 // epilogue (TMEM lane quarter = warp % 4 covers 1,2,3,0), NPW+5 = index loader + tile scheduler, NPW+6 = weight loader,
 // the rest (to a multiple of four warps) idle until the final barrier.
