@@ -37,6 +37,7 @@ SIGNATURES = {
     "btc_sparse_conv_tc_diag": (_i, [_i]),
     "btc_sparse_conv_tc_grid": (_i, [_i]),
     "btc_sparse_conv_tc_commit_group": (_i, [_i]),
+    "btc_sparse_conv_tc_pdl": (_i, [_i]),
     "btc_sparse_conv_tc_packed_bytes": (_i64, [_i, _i, _i]),
     "btc_sparse_conv_tc_pack": (_i, [_p, _i, _i, _i, _p, _p]),
     "btc_sparse_conv_fwd_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),

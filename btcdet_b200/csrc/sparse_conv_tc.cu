@@ -269,7 +269,11 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // CG (commit group): the stages of a ring are released in groups of CG with ONE tcgen05.commit after the last stage of a
 // group (empty barrier per slot group).  CG = 1 is the measured round-1 default; CG = 2 / 3 is the experiment DESIGN.md
 // §8.1(0) calls for (a per-stage commit appears to drain the MMA pipeline) and is not yet verified on hardware.
-template <int N, int NPW, bool CAT, int CG>
+// PDL (programmatic dependent launch, EXPERIMENTAL, not verified on hardware in round 1): the kernel lets its dependents
+// be scheduled as soon as its own CTAs leave an SM (griddepcontrol.launch_dependents) and, launched with the
+// programmatic-serialisation attribute itself, runs its prologue, first index tile and weight prefetch under the tail of
+// the previous layer; only the producers' first gather waits for that layer to complete (griddepcontrol.wait).
+template <int N, int NPW, bool CAT, int CG, bool PDL = false>
 __global__ void __launch_bounds__(TcRoles<NPW>::kThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
@@ -342,6 +346,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp < TC_PRODUCER_WARPS) {
         // ================= producers =================
@@ -424,6 +429,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         };
         const uint32_t rd_base = abuf + (uint32_t)lane * 128u;
         const uint32_t x7 = (uint32_t)(lane & 7);
+        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");   // feat_in is the previous layer's output
         int s = group % STAGES, ph = 0, slot = 0, islot = 0;   // consume-side stage slot / phase, staging slots
         bool located = false;
         while (true) {
@@ -746,7 +752,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
-static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM, g_tc_cg = 1;
+static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM, g_tc_cg = 1, g_tc_pdl = 0;
 
 static int* next_tile_counter() {
     static int* base[64] = {nullptr};            // (benign race: every thread computes the same address)
@@ -771,14 +777,14 @@ static size_t tc_smem_bytes(int N, int npw, int K, int c_in) {
 }
 constexpr size_t kTcMaxSmem = 227 * 1024;
 
-template <int N, int NPW, bool CAT, int CG = 1>
+template <int N, int NPW, bool CAT, int CG = 1, bool PDL = false>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
     static_assert(TcBStages<N>::value == (N <= 32 ? 6 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
                   "tc_smem_bytes mirrors these");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
-    auto kern = conv_fwd_tc_kernel<N, NPW, CAT, CG>;
+    auto kern = conv_fwd_tc_kernel<N, NPW, CAT, CG, PDL>;
     static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
     if (attr_set < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
@@ -790,6 +796,21 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
     if (g_tc_dyn) {
         ctr = next_tile_counter();
         if (!ctr) return set_error(BTC_E_CUDA, "btc_sparse_conv_fwd_tc: tile counter symbol not available", cudaGetLastError());
+    }
+    if (PDL) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TcRoles<NPW>::kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        BTC_CUDA(cudaLaunchKernelEx(&cfg, kern, feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
+                                    n_dev, K, c_in, c_out, ctr, g_tc_diag), "conv_fwd_tc (programmatic dependent launch)");
+        return BTC_OK;
     }
     kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
                                                      n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag);
@@ -824,6 +845,10 @@ static int launch_tc(const float* feat_in, const int* table, const float* packed
     tc_config_init();
     constexpr int NS = N <= 64 ? N : 64;   // instantiation guard for the N <= 64 only variants
 #define BTC_TC_ARGS feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in, c_out, st
+    if (g_tc_pdl && !g_tc_cat && g_tc_cg == 1) {   // experimental programmatic dependent launch (default tile only)
+        if (N <= 64 && g_tc_npw == 16) return launch_tc_npw<NS, 16, false, 1, true>(BTC_TC_ARGS);
+        return launch_tc_npw<N, 8, false, 1, true>(BTC_TC_ARGS);
+    }
     if (g_tc_cg > 1 && !g_tc_cat) {        // experimental commit groups (3-MMA k-steps only; 3 needs the six-stage ring)
         constexpr int CG3 = TcAStages<N, false>::value % 3 == 0 ? 3 : 2;
         if (N <= 64 && g_tc_npw == 16)
@@ -866,6 +891,11 @@ int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tile
 int btc_sparse_conv_tc_commit_group(int stages) {
     if (stages < 1 || stages > 3) return badarg("btc_sparse_conv_tc_commit_group: stages must be 1, 2 or 3");
     g_tc_cg = stages;
+    return BTC_OK;
+}
+
+int btc_sparse_conv_tc_pdl(int on) {
+    g_tc_pdl = on ? 1 : 0;
     return BTC_OK;
 }
 

@@ -276,6 +276,11 @@ def tc_commit_group(stages=1):
     check(_lib.load().btc_sparse_conv_tc_commit_group(int(stages)), "btc_sparse_conv_tc_commit_group")
 
 
+def tc_pdl(on=False):
+    """EXPERIMENTAL: programmatic dependent launch of the tcgen05 tile (off = verified default)."""
+    check(_lib.load().btc_sparse_conv_tc_pdl(int(bool(on))), "btc_sparse_conv_tc_pdl")
+
+
 def tc_pack_weight(weight):
     """Pack [K,Cin,Cout] (or [*k,Cin,Cout]) fp32 weights into the tcgen05 operand image (hi/lo tf32 split,
     K-major, 128-byte swizzle) consumed by sparse_conv_fwd_tc."""

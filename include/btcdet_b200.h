@@ -256,6 +256,10 @@ int btc_sparse_conv_tc_grid(int max_ctas);
  * release the operand-ring stages in groups of `stages` (1, 2 or 3; 3 falls back to 2 where the ring has four slots)
  * with one tcgen05.commit per group instead of one per stage.  Process-wide. */
 int btc_sparse_conv_tc_commit_group(int stages);
+/* EXPERIMENTAL (not verified on hardware in round 1; default 0): launch the tile with programmatic stream serialisation —
+ * prologue, first index tile and weight prefetch of a layer run under the tail of the previous kernel in the stream; the
+ * first gather waits for it (griddepcontrol.wait).  Applies to the default tile (3-MMA k-steps, commit group 1). */
+int btc_sparse_conv_tc_pdl(int on);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
 int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,

@@ -349,6 +349,41 @@ def test_tensor_core_commit_groups_experimental(cuda, cg, npw, n_out, K, cin, co
         ops.tc_config(16, 0, 1)
 
 
+@pytest.mark.skipif(os.environ.get("BTC_TEST_EXPERIMENTAL") != "1",
+                    reason="programmatic dependent launch is not verified on hardware yet (DESIGN.md §8.1); set BTC_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("npw", [16, 8])
+def test_tensor_core_pdl_chain_experimental(cuda, npw):
+    """Four dependent layers launched back to back with programmatic stream serialisation: every layer's first gather
+    must wait for the previous layer (griddepcontrol.wait) — results identical to ordinary launches, repeatedly."""
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(5)
+    n, K, c = 60000, 27, 64
+    valid = rng.random((n, K)) < 0.3
+    valid[:, K // 2] = True
+    nbr = torch.from_numpy(np.where(valid, rng.integers(0, n, (n, K)), -1).astype(np.int32)).cuda()
+    x0 = torch.from_numpy(rng.standard_normal((n, c)).astype(np.float32)).cuda()
+    ws = [ops.tc_pack_weight(torch.from_numpy((rng.standard_normal((K, c, c)) * 0.05).astype(np.float32)).cuda())
+          for _ in range(4)]
+
+    def chain():
+        x = x0
+        for pk in ws:
+            x = ops.sparse_conv_fwd_tc(x, nbr, pk, c, c, relu=True)
+        return x
+    try:
+        ops.tc_config(npw, 0, 1)
+        ref = chain()
+        torch.cuda.synchronize()
+        ops.tc_pdl(True)
+        for rep in range(3):
+            got = chain()
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref)
+    finally:
+        ops.tc_pdl(False)
+        ops.tc_config(16, 0, 1)
+
+
 @pytest.mark.parametrize("n,K", [(1, 27), (127, 27), (2048, 27), (2049, 8), (9000, 27), (5000, 64), (3000, 3), (4100, 33)])
 def test_rulebook_sort_rows(cuda, n, K):
     """btc_rulebook_sort_rows: a permutation inside 2048-row windows, ordered by (valid-offset mask, original row)."""

@@ -51,3 +51,14 @@ timeout 200 python tools/train_step.py --steps 10 > gpurun_out/battery_train_ste
 tail -1 gpurun_out/battery_train_step.json
 timeout 120 python -m pytest tests/test_mask_timings_gpu.py tests/test_stress_properties_gpu.py -m gpu -x -q > gpurun_out/battery_masks_stress.log 2>&1
 tail -3 gpurun_out/battery_masks_stress.log
+# 7. programmatic dependent launch of the conv tile (prologue of layer l+1 under the tail of layer l)
+BTC_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_parity_gpu.py -k pdl_chain -x -q --timeout 120 > gpurun_out/battery_pdl_test.log 2>&1
+tail -3 gpurun_out/battery_pdl_test.log
+if grep -q " passed" gpurun_out/battery_pdl_test.log; then
+    timeout 120 python tools/step_breakdown.py --pdl --reps 10 > gpurun_out/battery_breakdown_pdl.json 2> gpurun_out/battery_breakdown_pdl.err
+    python - <<PY
+import json
+d = json.loads(open("gpurun_out/battery_breakdown_pdl.json").read().strip().splitlines()[-1])
+print("PDL: conv chain %.0f us, graph %.0f us" % (d["conv_chain_us"], d["graph_us"]))
+PY
+fi

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--diag", action="store_true", help="also time the conv chain with parts of the tcgen05 tile skipped "
                     "(btc_sparse_conv_tc_diag masks; wrong results, timing only)")
     ap.add_argument("--commit-group", type=int, default=1, help="EXPERIMENTAL: stages per tcgen05.commit (1, 2, 3)")
+    ap.add_argument("--pdl", action="store_true", help="EXPERIMENTAL: programmatic dependent launch of the conv tile")
     ap.add_argument("--grids", default="", help="comma-separated caps on the conv grid: only the captured graph is timed per cap")
     ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
                     "(one JSON line each), e.g. '16,1,1;16,0,1;16,1,0'")
@@ -79,6 +80,7 @@ def run(args, npw, cat, dyn):
     from btcdet_b200 import ops
     ops.tc_config(npw, cat, dyn)
     ops.tc_commit_group(args.commit_group)
+    ops.tc_pdl(args.pdl)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, N = args.batch, 20000
