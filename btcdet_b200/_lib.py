@@ -35,6 +35,7 @@ SIGNATURES = {
     "btc_sparse_conv_tc_supported": (_i, [_i, _i, _i]),
     "btc_sparse_conv_tc_config": (_i, [_i, _i, _i]),
     "btc_sparse_conv_tc_diag": (_i, [_i]),
+    "btc_sparse_conv_tc_trace": (_i, [_p]),
     "btc_sparse_conv_tc_grid": (_i, [_i]),
     "btc_sparse_conv_tc_commit_group": (_i, [_i]),
     "btc_sparse_conv_tc_pdl": (_i, [_i]),

@@ -210,8 +210,8 @@ extern "C" {
 
 int btc_maxpool_fwd(const float* feat_in, const int* nbr_out, float* feat_out, int n_out_cap, const int* n_out_dev,
                     int K, int c, void* stream) {
+    if (n_out_cap <= 0) return BTC_OK;   // empty output (null data pointers of 0-row tensors are fine)
     if (!nbr_out || !feat_out) return badarg("btc_maxpool_fwd: null argument");
-    if (n_out_cap <= 0) return BTC_OK;
     if (!feat_in) return badarg("btc_maxpool_fwd: null feat_in");
     maxpool_fwd_kernel<<<grid_for((int64_t)n_out_cap * c, 256), 256, 0, (cudaStream_t)stream>>>(
         feat_in, nbr_out, feat_out, n_out_cap, n_out_dev, K, c);
@@ -221,7 +221,8 @@ int btc_maxpool_fwd(const float* feat_in, const int* nbr_out, float* feat_out, i
 
 int btc_maxpool_bwd(const float* feat_in, const float* feat_out, const float* d_out, const int* nbr_out, float* d_in,
                     int n_in, int n_out_cap, const int* n_out_dev, int K, int c, void* stream) {
-    if (!nbr_out || !d_in) return badarg("btc_maxpool_bwd: null argument");
+    if (n_in <= 0) return BTC_OK;
+    if (!d_in || (n_out_cap > 0 && !nbr_out)) return badarg("btc_maxpool_bwd: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_in > 0) BTC_CUDA(cudaMemsetAsync(d_in, 0, (size_t)n_in * c * 4, st), "maxpool_bwd memset");
     if (n_out_cap <= 0 || n_in <= 0) return BTC_OK;

@@ -353,8 +353,9 @@ extern "C" {
 int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out, const float* weight, const float* bias,
                         const float* scale, const float* shift, int relu, float* feat_out, int n_out_cap,
                         const int* n_out_dev, int K, int c_in, int c_out, int algo, void* stream) {
-    if (!nbr_out || !weight || !feat_out) return badarg("btc_sparse_conv_fwd: null argument");
     if (K < 1 || K > 256 || c_in < 1 || c_out < 1 || n_out_cap < 0) return badarg("btc_sparse_conv_fwd: bad sizes");
+    if (n_out_cap == 0) return BTC_OK;   // empty output (torch hands out null data pointers for 0-row tensors): nothing to do
+    if (!nbr_out || !weight || !feat_out) return badarg("btc_sparse_conv_fwd: null argument");
     if ((scale == nullptr) != (shift == nullptr)) return badarg("btc_sparse_conv_fwd: scale/shift must come together");
     if (n_out_cap > 0 && !feat_in) return badarg("btc_sparse_conv_fwd: null feat_in");
     cudaStream_t st = (cudaStream_t)stream;
@@ -371,9 +372,9 @@ int64_t btc_sparse_conv_bwd_workspace_bytes(int K, int c_in, int c_out) {
 int btc_sparse_conv_bwd_data(const float* d_out, const int* table, int mirror, const float* weight, float* d_in,
                              int n_in_cap, const int* n_in_dev, int K, int c_in, int c_out, void* workspace,
                              int64_t workspace_bytes, void* stream) {
+    if (n_in_cap <= 0) return BTC_OK;    // no input rows: no gradient rows
     if (!table || !weight || !d_in || !workspace) return badarg("btc_sparse_conv_bwd_data: null argument");
     if (workspace_bytes < btc_sparse_conv_bwd_workspace_bytes(K, c_in, c_out)) return badarg("btc_sparse_conv_bwd_data: workspace too small");
-    if (n_in_cap <= 0) return BTC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     float* wt = (float*)workspace;
     int64_t total = (int64_t)K * c_in * c_out;
@@ -386,7 +387,7 @@ int btc_sparse_conv_bwd_data(const float* d_out, const int* table, int mirror, c
 int btc_sparse_conv_bwd_weight(const float* feat_in, const float* d_out, const int* nbr_out, float* d_weight,
                                float* d_bias, int n_out_cap, const int* n_out_dev, int K, int c_in, int c_out,
                                void* stream) {
-    if (!nbr_out || !d_weight) return badarg("btc_sparse_conv_bwd_weight: null argument");
+    if (!d_weight || (n_out_cap > 0 && !nbr_out)) return badarg("btc_sparse_conv_bwd_weight: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     BTC_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)K * c_in * c_out * 4, st), "bwd_weight memset");
     if (d_bias) BTC_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)c_out * 4, st), "bwd_bias memset");

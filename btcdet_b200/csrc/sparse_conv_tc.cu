@@ -279,7 +279,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
-                   const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag) {
+                   const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag,
+                   unsigned long long* __restrict__ trace) {
     constexpr int STAGES = TcAStages<N, CAT>::value;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
@@ -315,6 +316,14 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     const int n = live_count(n_cap, n_dev);
     if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Timeline diagnostics (btc_sparse_conv_tc_trace): 16 u64 slots per CTA, see tools/tc_timeline.py for the legend.
+    unsigned long long* tr = trace ? trace + (size_t)blockIdx.x * 16 : nullptr;
+    if (tr && tid == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        tr[0] = g;
+        tr[1] = (unsigned long long)clock64();
+    }
     const int num_tiles = (n + TC_BM - 1) / TC_BM;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int E = K * c_in;                         // flattened (offset, channel) reduction length
@@ -347,6 +356,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tr && tid == 0) tr[2] = (unsigned long long)clock64();
 
     if (warp < TC_PRODUCER_WARPS) {
         // ================= producers =================
@@ -432,11 +442,15 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");   // feat_in is the previous layer's output
         int s = group % STAGES, ph = 0, slot = 0, islot = 0;   // consume-side stage slot / phase, staging slots
         bool located = false;
+        const bool tr_me = tr && warp == 0 && lane == 0;
+        bool tr_first_issue = true, tr_first_arrive = true;
+        long long tr_wait_empty = 0;
         while (true) {
             // issue ahead: up to TC_DEPTH gathers in flight, never blocking while some are
             while (!it_done && inflight < TC_DEPTH) {
                 if (!located) located = locate(inflight == 0);
                 if (!located) break;
+                if (tr_me && tr_first_issue) { tr[4] = (unsigned long long)clock64(); tr_first_issue = false; }
                 issue(islot);
                 if (++islot == TC_DEPTH) islot = 0;
                 located = false;
@@ -460,7 +474,10 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();                          // everyone has read the slot before it is refilled
+            long long tw0 = 0;
+            if (tr_me) tw0 = clock64();
             mbar_wait_a(empty0 + 8u * (uint32_t)(s / CG), (uint32_t)(ph ^ 1));
+            if (tr_me) tr_wait_empty += clock64() - tw0;
             tc_fence_after();
             // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
             // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
@@ -488,11 +505,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive_a(full0 + 8u * (uint32_t)s);
+            if (tr_me && tr_first_arrive) { tr[5] = (unsigned long long)clock64(); tr_first_arrive = false; }
             // advance the consume-side counters by two global stages
             s += G; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
             if (++slot == TC_DEPTH) slot = 0;
         }
         if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);   // (not reached: the iterator releases as it leaves)
+        if (tr_me) tr[14] = (unsigned long long)tr_wait_empty;
     } else if (warp == TC_MMA_WARP) {
         // ================= MMA issuer =================
         // The whole warp runs the loop in warp-uniform control flow and one ELECTed lane issues: a divergent
@@ -507,13 +526,20 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = (uint32_t)desc0;
         uint32_t s = 0, ph = 0;   // ring slot / phase (A operand in TMEM and weight tile in smem share both)
+        long long tr_wait_full = 0, tr_wait_list = 0, tr_wait_acc = 0;
+        unsigned long long tr_stages = 0;
+        bool tr_first = true;
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
+            long long tw0 = 0;
+            if (tr) tw0 = clock64();
             mbar_wait(&list_full[buf], (tl >> 1) & 1);
+            if (tr) { const long long t = clock64(); tr_wait_list += t - tw0; tw0 = t; }
             const int tile = s_tile[buf];
             const int cnt = s_cnt[buf];
             __syncwarp();
             mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);    // epilogue drained this accumulator (and read its tile id)
+            if (tr) tr_wait_acc += clock64() - tw0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
             if (elect_one()) {
@@ -555,10 +581,19 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             for (; j + 1 < cnt; j += 2) {
                 uint32_t s1 = s + 1, ph1 = ph;
                 if (s1 == (uint32_t)STAGES) { s1 = 0; ph1 ^= 1u; }
+                long long tw1 = 0;
+                if (tr) tw1 = clock64();
                 mbar_wait_a(bfull0 + 8u * s, ph);
                 mbar_wait_a(full0 + 8u * s, ph);
                 mbar_wait_a(bfull0 + 8u * s1, ph1);
                 mbar_wait_a(full0 + 8u * s1, ph1);
+                if (tr) {
+                    const long long t = clock64();
+                    tr_wait_full += t - tw1;
+                    tr_stages += 2;
+                    if (tr_first && lane == 0) { tr[6] = (unsigned long long)t; }
+                    tr_first = false;
+                }
                 tc_fence_after();
                 if (elect_one()) {
                     issue_stage(s, j == 0);
@@ -569,8 +604,17 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 if (s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
             }
             for (; j < cnt; ++j) {
+                long long tw1 = 0;
+                if (tr) tw1 = clock64();
                 mbar_wait_a(bfull0 + 8u * s, ph);        // weight tile landed (requested STAGES stages ago)
                 mbar_wait_a(full0 + 8u * s, ph);         // A operand in TMEM
+                if (tr) {
+                    const long long t = clock64();
+                    tr_wait_full += t - tw1;
+                    tr_stages += 1;
+                    if (tr_first && lane == 0) { tr[6] = (unsigned long long)t; }
+                    tr_first = false;
+                }
                 tc_fence_after();
                 if (elect_one()) issue_stage(s, j == 0);
                 __syncwarp();
@@ -578,6 +622,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
             __syncwarp();
+            if (tr && lane == 0) tr[7] = (unsigned long long)clock64();
+        }
+        if (tr && lane == 0) {
+            tr[12] = (unsigned long long)tr_wait_full;
+            tr[13] = tr_stages;
+            tr[3] = (unsigned long long)tr_wait_list;     // waiting for the index loader's chunk lists
+            tr[15] = (unsigned long long)tr_wait_acc;      // waiting for the epilogue to drain an accumulator
         }
     } else if (warp == TC_BLD_WARP) {
         // ================= weight loader: one cp.async.bulk per stage, NB stages ahead of the MMAs =================
@@ -637,6 +688,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     s_tile[buf] = -1;
                     s_cnt[buf] = 0;
                     mbar_arrive(&list_full[buf]);
+                    if (tr) tr[11] = (unsigned long long)tl;
                 }
                 break;
             }
@@ -740,11 +792,18 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);           // this accumulator buffer may be overwritten
+            if (tr && warp == Roles::kEpi0 && lane == 0) tr[8] = (unsigned long long)clock64();
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (tr && tid == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        tr[9] = (unsigned long long)clock64();
+        tr[10] = g;
+    }
 }
 
 // Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter at zero again (see
@@ -753,6 +812,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
 static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM, g_tc_cg = 1, g_tc_pdl = 0;
+static unsigned long long* g_tc_trace = nullptr;   // timeline diagnostics buffer (device, 16 u64 per CTA) or null
 
 static int* next_tile_counter() {
     static int* base[64] = {nullptr};            // (benign race: every thread computes the same address)
@@ -785,10 +845,13 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
                   "tc_smem_bytes mirrors these");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
     auto kern = conv_fwd_tc_kernel<N, NPW, CAT, CG, PDL>;
-    static size_t attr_set = 0;   // opt in to > 48 KB dynamic smem once per instantiation (not a stream op)
-    if (attr_set < smem) {
+    // opt in to > 48 KB dynamic smem: the attribute is per device / context, so it is tracked per device (not a stream op)
+    static size_t attr_set[64] = {0};
+    int dev = 0;
+    BTC_CUDA(cudaGetDevice(&dev), "tc device");
+    if (dev < 0 || dev >= 64 || attr_set[dev] < smem) {
         BTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc smem attr");
-        attr_set = smem;
+        if (dev >= 0 && dev < 64) attr_set[dev] = smem;
     }
     int tiles = (n_cap + TC_BM - 1) / TC_BM;
     dim3 grid(tiles < g_tc_grid ? tiles : g_tc_grid);    // persistent: one CTA per SM (or fewer: btc_sparse_conv_tc_grid)
@@ -809,11 +872,11 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         BTC_CUDA(cudaLaunchKernelEx(&cfg, kern, feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
-                                    n_dev, K, c_in, c_out, ctr, g_tc_diag), "conv_fwd_tc (programmatic dependent launch)");
+                                    n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace), "conv_fwd_tc (programmatic dependent launch)");
         return BTC_OK;
     }
     kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
-                                                     n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag);
+                                                     n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
@@ -910,6 +973,11 @@ int btc_sparse_conv_tc_diag(int mask) {
     return BTC_OK;
 }
 
+int btc_sparse_conv_tc_trace(void* trace_u64) {
+    g_tc_trace = (unsigned long long*)trace_u64;   // device buffer of 148 * 16 u64, or null to switch the timeline off
+    return BTC_OK;
+}
+
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out) {
     if (!(K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 4 && c_out % 4 == 0 && tc_padded_n(c_out) != 0 &&
           (int64_t)K * c_in >= 32))
@@ -940,10 +1008,10 @@ static int fwd_tc(const char* who, const float* feat_in, const int* nbr_out, con
                   const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_out_cap,
                   const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
     (void)who;
-    if (!nbr_out || !packed_weight || !feat_out) return badarg("btc_sparse_conv_fwd_tc: null argument");
     if ((scale == nullptr) != (shift == nullptr)) return badarg("btc_sparse_conv_fwd_tc: scale/shift must come together");
     if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_fwd_tc: shape not supported", cudaSuccess);
-    if (n_out_cap <= 0) return BTC_OK;
+    if (n_out_cap <= 0) return BTC_OK;   // empty output (null data pointers of 0-row tensors are fine)
+    if (!nbr_out || !packed_weight || !feat_out) return badarg("btc_sparse_conv_fwd_tc: null argument");
     if (!feat_in) return badarg("btc_sparse_conv_fwd_tc: null feat_in");
     if (((uintptr_t)feat_in & 15) || ((uintptr_t)feat_out & 15) || ((uintptr_t)packed_weight & 15))
         return badarg("btc_sparse_conv_fwd_tc: pointers must be 16-byte aligned");

@@ -357,6 +357,7 @@ class BackbonePlan:
             "host_feat": [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(slots)],
             "host_coords": [torch.empty((rows, 4), dtype=torch.int32).pin_memory() for _ in range(slots)],
             "host_n": [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(slots)],
+            "host_levels": [torch.zeros(len(self.levels), dtype=torch.int32).pin_memory() for _ in range(slots)],
             "count_ready": [torch.cuda.Event() for _ in range(slots)],
             "d2h_done": [None] * slots,
             "copy_stream": torch.cuda.Stream(device=dev),
@@ -381,6 +382,7 @@ class BackbonePlan:
                                      min(self.out_lvl.cap, pl["rows"]), _ptr(self.out_lvl.n_dev), 16, st), "btc_copy_rows")
         pl["stage_n"][slot].copy_(self.out_lvl.n_dev, non_blocking=True)
         pl["host_n"][slot].copy_(pl["stage_n"][slot], non_blocking=True)
+        pl["host_levels"][slot].copy_(self.dev_counts[:len(self.levels)], non_blocking=True)   # every level, for the overflow check
         pl["count_ready"][slot].record(main)
         pl["pending"].append(slot)
         pl["k"] += 1
@@ -392,6 +394,11 @@ class BackbonePlan:
         slot = pl["pending"].pop(0)
         pl["count_ready"][slot].synchronize()          # the row count of that batch (the GPU is already busy with the next)
         n = int(pl["host_n"][slot][0])
+        # an intermediate level that overflowed its capacity clamps its rows silently inside the kernels: fail loudly here
+        for c, l in zip(pl["host_levels"][slot].tolist(), self.levels):
+            if c > l.cap:
+                raise _lib.BtcError("level capacity exceeded in a pipelined batch: %d sites > capacity %d — raise level_growth"
+                                    % (c, l.cap))
         if n > pl["rows"]:
             raise _lib.BtcError("result of %d rows exceeds the pipeline staging capacity %d" % (n, pl["rows"]))
         cs = pl["copy_stream"]

@@ -359,20 +359,11 @@ def sparse_conv_bwd_weight(features, d_out, nbr_out, weight_shape, want_bias):
     return d_w, d_b
 
 
-_PACK_CACHE = {}
-
-
 def _packed_weight(weight):
-    """tcgen05 operand image of a layer's weights, cached until the Parameter is modified in place or replaced."""
-    key = (weight.data_ptr(), tuple(weight.shape))
-    hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == weight._version:
-        return hit[1]
-    if len(_PACK_CACHE) > 256:
-        _PACK_CACHE.clear()
-    packed = tc_pack_weight(weight)
-    _PACK_CACHE[key] = (weight._version, packed)
-    return packed
+    """tcgen05 operand image of a layer's weights, re-packed on every eager forward: the pack kernel touches only
+    K*Cin*Cout elements, and any cache keyed on (data_ptr, _version) goes stale under `weight.data.fill_()` (the
+    reference's own idiom, spconv_backbone.py:48) or when the allocator recycles a freed Parameter's storage."""
+    return tc_pack_weight(weight)
 
 
 class SparseConvFunction(torch.autograd.Function):

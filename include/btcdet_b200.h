@@ -249,6 +249,11 @@ int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tile
  * MMAs per k-step, bit 3 the weight-tile copies — so the cost of each pipeline side can be read off a wall-clock difference.  RESULTS ARE WRONG
  * while the mask is non-zero; 0 (the default) restores the product path. */
 int btc_sparse_conv_tc_diag(int mask);
+/* Timeline diagnostics (tools/tc_timeline.py): with a non-null device buffer of 148 x 16 uint64 every CTA of the following
+ * tcgen05 launches records clock64 / globaltimer stamps of its roles (entry, set-up done, first gather, first operand
+ * stage, first MMA, last commit, last epilogue, exit) and the cycles its MMA issuer / producers / epilogue spent waiting.
+ * Results are unchanged; null (the default) switches it off.  Process-wide, not thread-safe. */
+int btc_sparse_conv_tc_trace(void* trace_u64);
 /* Cap on the persistent grid of the tcgen05 tile (default 148 = one CTA per SM): a smaller grid leaves whole SMs to
  * kernels running concurrently on other streams (the rulebook chain of the engine).  Process-wide. */
 int btc_sparse_conv_tc_grid(int max_ctas);

@@ -62,12 +62,14 @@ def make_inputs(seeds, n_points=6000, with_rot=False):
     return out, geo
 
 
-def run_reference(inp, geo):
-    mods = ref_loader.load_reference_modules()
+def run_reference(inp, geo, device="cpu", keep_all=False):
+    """device="cuda": the reference's code runs unchanged on the GPU (O3) — same CUDA libm, ATen kernels and
+    torch.inverse (batched LU) as a real BtcDet run."""
+    mods = ref_loader.load_reference_modules(device)
     with ref_loader.cuda_as_cpu():
         nx, ny, nz = geo.grid_size
-        vs = torch.tensor(geo.voxel_size, dtype=torch.float32)
-        centers = mods["coords_utils"].get_all_voxel_centers_zyx(1, torch.tensor([nx, ny, nz], dtype=torch.int32),
+        vs = torch.tensor(geo.voxel_size, dtype=torch.float32, device=device)
+        centers = mods["coords_utils"].get_all_voxel_centers_zyx(1, torch.tensor([nx, ny, nz], dtype=torch.int32, device=device),
                                                                  geo.point_cloud_range[:3], vs)[0]
         centers = mods["coords_utils"].uvd2absxyz(centers[2], centers[1], centers[0], "cylinder", dim=-1)
         vc = {"all_voxel_centers": centers, "all_voxel_centers_2d": torch.mean(centers[:, :, :, :2], dim=0).view(-1, 2)}
@@ -75,12 +77,14 @@ def run_reference(inp, geo):
                                                   point_cloud_range=geo.point_cloud_range,
                                                   data_cfg=ref_loader.Cfg.wrap(data_cfg(geo)), grid_size=geo.grid_size,
                                                   num_class=1, voxel_centers=vc)
-        bd = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp.items()}
+        bd = {k: (torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) else v) for k, v in inp.items()}
         bd["is_train"] = True
         out = tgt(bd)
     keep = ["voxelwise_mask", "vcc_mask", "occ_voxelwise_mask", "fore_voxelwise_mask", "general_cls_loss_mask", "pos_mask",
             "occ_fore_cls_mask", "occ_mirr_cls_mask", "occ_bm_cls_mask", "general_cls_loss_mask_float", "forebox_label",
             "res_mtrx", "general_reg_loss_mask"]
+    if keep_all:
+        keep = [k for k, v in out.items() if torch.is_tensor(v)]
     return {k: out[k].cpu().numpy() for k in keep if out.get(k) is not None}
 
 

@@ -19,7 +19,19 @@ import types
 import numpy as np
 import torch
 
-REF = "/root/reference"
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_STAGED = os.path.join(_ROOT, "oracle", "_ref", "reference_py")   # oracle/stage_reference.py (GPU box: O3 runs)
+
+
+def _find_ref():
+    for cand in (os.environ.get("BTC_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if cand and os.path.isdir(os.path.join(cand, "btcdet")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_ref()
+ON_CUDA = False        # set by load_reference_modules(device="cuda"): the reference code then runs unchanged on the GPU
 
 
 def available():
@@ -49,9 +61,12 @@ def _load(name, relpath):
     return mod
 
 
-def load_reference_modules():
-    """Returns a dict of the reference modules on the mask / re-voxelisation path."""
+def load_reference_modules(device="cpu"):
+    """Returns a dict of the reference modules on the mask / re-voxelisation path.  device="cuda": no rewriting at
+    all — the reference's constructors allocate on the GPU exactly as they do in the reference's own runs (O3)."""
+    global ON_CUDA
     assert available(), "reference checkout not present"
+    ON_CUDA = str(device).startswith("cuda")
     root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     if root not in sys.path:
         sys.path.insert(0, root)   # the drop-in `spconv` shim
@@ -96,7 +111,10 @@ _FACTORIES = ["zeros", "ones", "empty", "full", "tensor", "as_tensor", "arange",
 
 @contextlib.contextmanager
 def cuda_as_cpu():
-    """Rewrite device="cuda" to "cpu" in torch factory calls while reference code executes."""
+    """Rewrite device="cuda" to "cpu" in torch factory calls while reference code executes (no-op in O3 mode)."""
+    if ON_CUDA:
+        yield
+        return
     saved = {}
 
     def wrap(fn):

@@ -51,8 +51,12 @@ def test_host_only_queries(lib_path):
 def test_bad_arguments_return_status_not_crash(lib_path):
     from btcdet_b200 import _lib
     lib = _lib.load()
-    rc = lib.btc_sparse_conv_fwd(None, None, None, None, None, None, 0, None, 0, None, 27, 16, 16, 0, None)
+    rc = lib.btc_sparse_conv_fwd(None, None, None, None, None, None, 0, None, 5, None, 27, 16, 16, 0, None)
     assert rc == -1 and b"null" in lib.btc_last_error()
+    # an EMPTY output is not an error: torch hands out null data pointers for 0-row tensors (spconv handles empty inputs)
+    assert lib.btc_sparse_conv_fwd(None, None, None, None, None, None, 0, None, 0, None, 27, 16, 16, 0, None) == 0
+    assert lib.btc_maxpool_fwd(None, None, None, 0, None, 27, 2, None) == 0
+    assert lib.btc_sparse_conv_fwd_tc(None, None, None, None, None, None, 0, None, 0, None, 27, 32, 32, None) == 0
 
 
 def test_product_does_not_import_oracle():
