@@ -120,7 +120,7 @@ def layer_bytes_flops(plan, counts):
     for s in plan.steps:
         if s.kind != "conv":
             continue
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = s.args
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = s.args
         n_out = lvl_n[id(lout)]
         pairs = int((nbr[:n_out] >= 0).sum().item())
         out.append({"n_in": n_in, "n_out": n_out, "pairs": pairs, "K": K, "cin": cin, "cout": cout,
@@ -335,7 +335,7 @@ def run_ours(args, rank, world):
         tot_ms, reps = 0.0, 5
         per_layer = []
         for s, sp in zip(conv_steps, specs):
-            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = s.args
+            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = s.args
             ms_l = 0.0
             for r in range(reps + 1):
                 flush.fill_(float(r))

@@ -20,6 +20,7 @@ SIGNATURES = {
     "btc_last_error": (ctypes.c_char_p, []),
     "btc_voxelize_workspace_bytes": (_i64, [_i64, _i, _i, _i]),
     "btc_voxelize": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_points_to_cylinder": (_i, [_p, _i, _p, _i, _i, _p, _p]),
     "btc_index_entries": (_i64, [_i, _p]),
     "btc_index_workspace_bytes": (_i64, [_i64]),
     "btc_index_build": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _p, _p, _i64, _p]),
@@ -42,6 +43,8 @@ SIGNATURES = {
     "btc_sparse_conv_tc_packed_bytes": (_i64, [_i, _i, _i]),
     "btc_sparse_conv_tc_pack": (_i, [_p, _i, _i, _i, _p, _p]),
     "btc_sparse_conv_fwd_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "btc_rulebook_tile_meta": (_i, [_p, _i, _p, _i, _p, _p, _p]),
+    "btc_sparse_conv_fwd_tc_meta": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
     "btc_sparse_conv_fwd_tc_rows": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "btc_rulebook_sort_rows": (_i, [_p, _i, _p, _i, _p, _p, _p]),
     "btc_sparse_conv_bwd_workspace_bytes": (_i64, [_i, _i, _i]),
@@ -56,10 +59,13 @@ SIGNATURES = {
     "btc_occ_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_occ_select_workspace_bytes": (_i64, [_i, _p]),
     "btc_occ_select": (_i, [_p, _p, _i, _p, ctypes.c_float, _p, _p, _p, ctypes.c_float, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_occ_abs_mean_vfe": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p]),
     "btc_occ_vfe": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
     "btc_occ_box_targets_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "btc_occ_box_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i,
                                  _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_occ_box_targets_v2": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i,
+                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_occ_loss_maps": (_i, [_p] * 10 + [_i, _p] + [_p] * 11),
     "btc_revoxelize_workspace_bytes": (_i64, [_i, _i64]),
     "btc_revoxelize": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),

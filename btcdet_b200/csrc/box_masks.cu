@@ -10,12 +10,17 @@
 //   occ_targets_template.py  prepare_cls_loss_map :330-380, prepare_reg_loss_map :383-401
 // with four kernels and no host synchronisation.
 //
-// Numerics.  The reference maps points into box frames through torch.inverse (batched LU) of a 4x4 rigid transform;
-// here the inverse is analytic (R^T (p - c)), which is the better-conditioned evaluation but not the same rounding:
-// a point within ~1e-5 m of a box face, or a mirrored point within ~1e-5 of an occupancy-bin edge, may be classified
-// differently (tests exclude / bound exactly those).  Everything else follows the reference's fp32 op
-// order (no FMA contraction).  Per-cell means of scattered points are accumulated in 2^-24 fixed point with 64-bit
-// integer atomics, so the result does not depend on thread order (the reference's CUDA scatter_add does).
+// Numerics.  The reference maps points into box frames through torch.inverse of a 4x4 (3x3 for the 2-D pre-filter) rigid
+// transform followed by an einsum, i.e. on CUDA a batched LU solve and a K = 3 (2) GEMM.  Both were dumped on a B200
+// (tools/o3_reference_cuda.py, tests/golden/box_inverse_cuda.npz) and are reproduced here bit for bit:
+//   * inverse = LU with partial pivoting (first maximum), multipliers l = a * (1 / pivot), FMA updates, column-oriented
+//     forward / backward substitution with FMA and an IEEE division by the diagonal (lu_inverse below; 256 / 256 dumped
+//     matrices identical, tests/test_box_inverse_cpu.py);
+//   * box-frame coordinates q_i = fma(z, a_i2, fma(y, a_i1, x * a_i0)) + t_i (the GEMM's ascending-k FMA chain), and the
+//     same chain for the mirrored points' way back and for rotatez.
+// The in-box decisions, mirrored points and forebox labels are therefore the reference's own, including for points on a
+// box face.  Per-cell means of scattered points are accumulated in 2^-24 fixed point with 64-bit integer atomics, so the
+// result does not depend on thread order (the reference's CUDA scatter_add does: compared at 2e-5).
 #include "common.cuh"
 #include "occ_geom.cuh"
 
@@ -23,8 +28,57 @@ namespace btc {
 
 struct BoxRec {
     float cx, cy, cz, hx, hy, hz, cs, sn, r2;
+    float inv4[3][4];     // rows 0..2 of torch.inverse([[R, t], [0, 1]])   (3-D tests)
+    float inv2[2][3];     // rows 0..1 of torch.inverse of the 2-D transform  (forebox pre-filter)
     int label, mirr;
 };
+
+// torch.inverse on CUDA for small batched matrices (cuBLAS getrf / getrs path), reproduced operation by operation.
+template <int N>
+__device__ __forceinline__ void lu_inverse(float (&A)[N][N], float (&X)[N][N]) {
+    int piv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) piv[i] = i;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int p = k;
+        float best = fabsf(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i)
+            if (fabsf(A[i][k]) > best) { best = fabsf(A[i][k]); p = i; }
+        if (p != k) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const float t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
+            const int t = piv[k]; piv[k] = piv[p]; piv[p] = t;
+        }
+        const float r = __fdiv_rn(1.0f, A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) A[i][k] = __fmul_rn(A[i][k], r);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i)
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) A[i][j] = __fmaf_rn(-A[i][k], A[k][j], A[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) X[i][j] = piv[i] == j ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; ++k)                       // L y = P I, unit lower triangle, column oriented
+#pragma unroll
+        for (int i = k + 1; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) X[i][j] = __fmaf_rn(-A[i][k], X[k][j], X[i][j]);
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {                // U x = y
+#pragma unroll
+        for (int j = 0; j < N; ++j) X[k][j] = __fdiv_rn(X[k][j], A[k][k]);
+#pragma unroll
+        for (int i = 0; i < k; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) X[i][j] = __fmaf_rn(-A[i][k], X[k][j], X[i][j]);
+    }
+}
 
 // one thread per (scene, box)
 __global__ void box_prep_kernel(const float* __restrict__ boxes, int max_boxes, int box_dim, const int* __restrict__ box_num,
@@ -37,6 +91,22 @@ __global__ void box_prep_kernel(const float* __restrict__ boxes, int max_boxes, 
     r.cx = bx[0]; r.cy = bx[1]; r.cz = bx[2];
     r.hx = __fmul_rn(bx[3], 0.5f); r.hy = __fmul_rn(bx[4], 0.5f); r.hz = __fmul_rn(bx[5], 0.5f);
     r.cs = cosf(bx[6]); r.sn = sinf(bx[6]);
+    {   // torch_get_yaw_rotation + torch_get_transform + torch.inverse (point_box_utils.py:272-288, 310-329)
+        float T[4][4] = {{r.cs, -r.sn, 0.f, r.cx}, {r.sn, r.cs, 0.f, r.cy}, {0.f, 0.f, 1.f, r.cz}, {0.f, 0.f, 0.f, 1.f}};
+        float X[4][4];
+        lu_inverse<4>(T, X);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r.inv4[i][j] = X[i][j];
+        float T2[3][3] = {{r.cs, -r.sn, r.cx}, {r.sn, r.cs, r.cy}, {0.f, 0.f, 1.f}};
+        float X2[3][3];
+        lu_inverse<3>(T2, X2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r.inv2[i][j] = X2[i][j];
+    }
     const float rr = sqrtf(r.hx * r.hx + r.hy * r.hy) * 1.001f + 1e-3f;      // conservative xy reject radius
     r.r2 = rr * rr;
     const float lab = bx[box_dim - 1];
@@ -46,13 +116,21 @@ __global__ void box_prep_kernel(const float* __restrict__ boxes, int max_boxes, 
     rec[t] = r;
 }
 
+// einsum("nj,mij->nmi", points, inverse[:, :3, :3]) + inverse[:, :3, 3]: ascending-k FMA chain of the K = 3 GEMM
 __device__ __forceinline__ bool in_box(const BoxRec& r, float px, float py, float pz, float& qx, float& qy, float& qz) {
     const float dx = px - r.cx, dy = py - r.cy;
-    if (dx * dx + dy * dy > r.r2) return false;
-    qx = __fadd_rn(__fmul_rn(r.cs, dx), __fmul_rn(r.sn, dy));
-    qy = __fsub_rn(__fmul_rn(r.cs, dy), __fmul_rn(r.sn, dx));
-    qz = pz - r.cz;
+    if (dx * dx + dy * dy > r.r2) return false;     // conservative reject (radius 0.1 % + 1 mm beyond the half diagonal)
+    qx = __fadd_rn(__fmaf_rn(pz, r.inv4[0][2], __fmaf_rn(py, r.inv4[0][1], __fmul_rn(px, r.inv4[0][0]))), r.inv4[0][3]);
+    qy = __fadd_rn(__fmaf_rn(pz, r.inv4[1][2], __fmaf_rn(py, r.inv4[1][1], __fmul_rn(px, r.inv4[1][0]))), r.inv4[1][3]);
+    qz = __fadd_rn(__fmaf_rn(pz, r.inv4[2][2], __fmaf_rn(py, r.inv4[2][1], __fmul_rn(px, r.inv4[2][0]))), r.inv4[2][3]);
     return qx <= r.hx && qx >= -r.hx && qy <= r.hy && qy >= -r.hy && qz <= r.hz && qz >= -r.hz;
+}
+// torch_points_in_box_2d_mask (point_box_utils.py:332-365): 3x3 inverse, K = 2 chain
+__device__ __forceinline__ bool in_box_2d(const BoxRec& r, float px, float py) {
+    if (r.r2 < 0.f) return false;                   // padded box row
+    const float qx = __fadd_rn(__fmaf_rn(py, r.inv2[0][1], __fmul_rn(px, r.inv2[0][0])), r.inv2[0][2]);
+    const float qy = __fadd_rn(__fmaf_rn(py, r.inv2[1][1], __fmul_rn(px, r.inv2[1][0])), r.inv2[1][2]);
+    return qx <= r.hx && qx >= -r.hx && qy <= r.hy && qy >= -r.hy;
 }
 
 // ---- order-independent per-cell accumulator (open addressing, 64-bit fixed point) ---------------------------
@@ -136,8 +214,10 @@ __global__ void fore_mirror_kernel(const float* __restrict__ voxels, int P, int 
                     if (!in_box(r, x, y, z, qx, qy, qz)) continue;
                     label = max(label, r.label);
                     if (r.mirr) {   // reflect across the box's length axis (y -> -y in the box frame) and map back
-                        const float mx = __fadd_rn(__fsub_rn(__fmul_rn(r.cs, qx), __fmul_rn(r.sn, -qy)), r.cx);
-                        const float my = __fadd_rn(__fadd_rn(__fmul_rn(r.sn, qx), __fmul_rn(r.cs, -qy)), r.cy);
+                        // einsum("nmj,mij->nmi", (qx, -qy, qz), R) + center: the GEMM's FMA chain; the zero / one entries of
+                        // R contribute exact no-ops
+                        const float mx = __fadd_rn(__fmaf_rn(-qy, -r.sn, __fmul_rn(qx, r.cs)), r.cx);
+                        const float my = __fadd_rn(__fmaf_rn(-qy, r.cs, __fmul_rn(qx, r.sn)), r.cy);
                         const float mz = __fadd_rn(qz, r.cz);
                         const long long cell = cyl_cell(g, c.x, mx, my, mz, rot_z);
                         if (cell >= 0) acc_add(mirr, cell, mx, my, mz, status);
@@ -209,7 +289,7 @@ __global__ void acc_finalize_kernel(CellAcc a, const float* __restrict__ rot_z, 
 
 // a11: one thread per (scene, phi bin, rho bin) column; z walked inside (stores coalesce along rho)
 __global__ void forebox_kernel(const BoxRec* __restrict__ rec, int max_boxes, const float* __restrict__ rot_z, OccGeom g,
-                               signed char* __restrict__ forebox) {
+                               const float* __restrict__ centers2d, signed char* __restrict__ forebox) {
     extern __shared__ unsigned char s_raw[];
     BoxRec* s_rec = reinterpret_cast<BoxRec*>(s_raw);
     const int b = blockIdx.y;
@@ -226,16 +306,28 @@ __global__ void forebox_kernel(const BoxRec* __restrict__ rec, int max_boxes, co
         const int cx = col % g.g[0], cy = col / g.g[0];
         float ctr[3];
         cell_center(g, 0, 0, cy, cx, nullptr, ctr);       // stored centres are unrotated; the rotation is applied below
-        const float x = rot_z ? __fsub_rn(__fmul_rn(ctr[0], cr), __fmul_rn(ctr[1], sr)) : ctr[0];
-        const float y = rot_z ? __fadd_rn(__fmul_rn(ctr[0], sr), __fmul_rn(ctr[1], cr)) : ctr[1];
+        // rotatez = torch.matmul(points, R(yaw)^T): FMA chain over k (point_box_utils.py:241-250)
+        const float x = rot_z ? __fmaf_rn(ctr[1], -sr, __fmul_rn(ctr[0], cr)) : ctr[0];
+        const float y = rot_z ? __fmaf_rn(ctr[1], cr, __fmul_rn(ctr[0], sr)) : ctr[1];
+        // 2-D pre-filter of the column (occ_targets_3d.py:79): on all_voxel_centers_2d = the mean over z of the centres'
+        // xy as torch computed it at model build (detector3d_template.py:62; passed in so that its rounding is torch's)
+        float x2 = x, y2 = y;
+        if (centers2d) {
+            const float ux = __ldg(centers2d + 2 * col), uy = __ldg(centers2d + 2 * col + 1);
+            x2 = rot_z ? __fmaf_rn(uy, -sr, __fmul_rn(ux, cr)) : ux;
+            y2 = rot_z ? __fmaf_rn(uy, cr, __fmul_rn(ux, sr)) : uy;
+        }
+        bool hit2d = false;
+        for (int j = 0; j < max_boxes && !hit2d; ++j) hit2d = in_box_2d(s_rec[j], x2, y2);
         signed char* out = forebox + (int64_t)b * scene_cells + col;
         for (int z = 0; z < g.g[2]; ++z) {
             const float zc = __fadd_rn(__fmul_rn(__fadd_rn((float)z, 0.5f), g.vs[2]), g.lo[2]);
             int label = 0;
-            for (int j = 0; j < max_boxes; ++j) {
-                float qx, qy, qz;
-                if (in_box(s_rec[j], x, y, zc, qx, qy, qz)) label = max(label, s_rec[j].label);
-            }
+            if (hit2d)
+                for (int j = 0; j < max_boxes; ++j) {
+                    float qx, qy, qz;
+                    if (in_box(s_rec[j], x, y, zc, qx, qy, qz)) label = max(label, s_rec[j].label);
+                }
             out[(int64_t)z * cols] = (signed char)label;
         }
     }
@@ -330,6 +422,19 @@ int btc_occ_box_targets(const float* voxels, int P, int C, const int* voxel_coor
                         float* fore_res, uint8_t* mirr_mask, float* mirr_res, uint8_t* bm_mask, float* bm_res,
                         int8_t* forebox_label, int8_t* point_label, int* status, void* workspace, int64_t workspace_bytes,
                         void* stream) {
+    return btc_occ_box_targets_v2(voxels, P, C, voxel_coords, num_points, m_cap, m_dev, batch, gt_boxes, max_boxes, box_dim,
+                                  gt_boxes_num, mirr_flag, bm_points, n_bm, rot_z, geom_f, geom_i, num_class, mirr_cap, bm_cap,
+                                  nullptr, fore_mask, fore_res, mirr_mask, mirr_res, bm_mask, bm_res, forebox_label, point_label,
+                                  status, workspace, workspace_bytes, stream);
+}
+
+int btc_occ_box_targets_v2(const float* voxels, int P, int C, const int* voxel_coords, const int* num_points, int m_cap,
+                           const int* m_dev, int batch, const float* gt_boxes, int max_boxes, int box_dim,
+                           const int* gt_boxes_num, const float* mirr_flag, const float* bm_points, int n_bm,
+                           const float* rot_z, const float* geom_f, const int* geom_i, int num_class, int mirr_cap, int bm_cap,
+                           const float* centers2d, uint8_t* fore_mask, float* fore_res, uint8_t* mirr_mask, float* mirr_res,
+                           uint8_t* bm_mask, float* bm_res, int8_t* forebox_label, int8_t* point_label, int* status,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
     OccGeom g;
     if (parse_geom(g, batch, geom_f, geom_i)) return badarg("btc_occ_box_targets: bad geometry");
     if (!fore_mask || !fore_res || !mirr_mask || !mirr_res || !status || !workspace)
@@ -380,7 +485,11 @@ int btc_occ_box_targets(const float* voxels, int P, int C, const int* voxel_coor
         if (max_boxes > 0) {
             const int cols = g.g[0] * g.g[1];
             dim3 grid((cols + 127) / 128, batch);
-            forebox_kernel<<<grid, 128, max_boxes * sizeof(BoxRec), st>>>(rec, max_boxes, rot_z, g, (signed char*)forebox_label);
+            if (max_boxes * sizeof(BoxRec) > 48 * 1024)
+                BTC_CUDA(cudaFuncSetAttribute(forebox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(max_boxes * sizeof(BoxRec))), "forebox smem attr");
+            forebox_kernel<<<grid, 128, max_boxes * sizeof(BoxRec), st>>>(rec, max_boxes, rot_z, g, centers2d,
+                                                                          (signed char*)forebox_label);
         } else {
             BTC_CUDA(cudaMemsetAsync(forebox_label, 0, cells, st), "box memset");
         }

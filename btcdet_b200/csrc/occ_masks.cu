@@ -69,6 +69,35 @@ __global__ void occ_dilate_kernel(const int4* __restrict__ coords, const int* __
     }
 }
 
+// MeanVFE of the occupancy branch on absolute coordinates (occ_targets_3d.py:45-47 with USE_ABSXYZ rewrites
+// batch_dict['voxels'] to cylinder_uvd2absxyz(voxels) + extra columns for EVERY slot, padding included; mean_vfe.py:27-44
+// then sums all P slots and divides by clamp_min(count, 1)).  One thread per (voxel, column); the slot sum runs in slot
+// order (torch's reduction order over a 12-element strided axis is an implementation detail: compared at 1e-6).
+__global__ void occ_abs_vfe_kernel(const float* __restrict__ voxels, int P, int C, const int* __restrict__ num_points, int m_cap,
+                                   const int* __restrict__ m_dev, float* __restrict__ voxels_abs, float* __restrict__ mean) {
+    const int m_live = live_count(m_cap, m_dev);
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < m_live; m += gridDim.x * blockDim.x) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int p = 0; p < P; ++p) {
+            const float* v = voxels + ((int64_t)m * P + p) * C;
+            const float rho = __ldg(v), phi = __ldg(v + 1);
+            const float u = deg2rad_like_torch(phi);
+            float o[8];
+            o[0] = __fmul_rn(rho, cosf(u));
+            o[1] = __fmul_rn(-rho, sinf(u));
+            for (int j = 2; j < C; ++j) o[j] = __ldg(v + j);
+            for (int j = 0; j < C; ++j) acc[j] = __fadd_rn(acc[j], o[j]);
+            if (voxels_abs)
+                for (int j = 0; j < C; ++j) voxels_abs[((int64_t)m * P + p) * C + j] = o[j];
+        }
+        const int cnt = __ldg(num_points + m);
+        const float norm = cnt > 1 ? (float)cnt : 1.0f;
+        for (int j = 0; j < C; ++j) mean[(int64_t)m * C + j] = __fdiv_rn(acc[j], norm);
+    }
+}
+
 // per (b, el, az) column of the sphere map: number of returns and first return at range bin >= 1
 __global__ void sphere_columns_kernel(const unsigned char* __restrict__ sphere_map, OccGeom g, int* __restrict__ counts,
                                       int* __restrict__ first1) {
@@ -397,6 +426,17 @@ int btc_occ_vfe(const float* voxels, const int* num_points, int m_cap, const int
     occ_vfe_kernel<<<grid_for(m_cap, 128), 128, 0, (cudaStream_t)stream>>>(voxels, num_points, m_cap, m_dev, P, C, num_raw, feats,
                                                                           occ_feats);
     BTC_CHECK_LAUNCH("occ_vfe");
+    return BTC_OK;
+}
+
+int btc_occ_abs_mean_vfe(const float* voxels, int max_points, int n_feat, const int* num_points, int m_cap, const int* m_dev,
+                         float* voxels_abs, float* voxel_mean, void* stream) {
+    if (m_cap < 0 || max_points < 1 || n_feat < 3 || n_feat > 8) return badarg("btc_occ_abs_mean_vfe: bad sizes");
+    if (m_cap == 0) return BTC_OK;
+    if (!voxels || !num_points || !voxel_mean) return badarg("btc_occ_abs_mean_vfe: null argument");
+    occ_abs_vfe_kernel<<<grid_for(m_cap, 128), 128, 0, (cudaStream_t)stream>>>(voxels, max_points, n_feat, num_points, m_cap, m_dev,
+                                                                              voxels_abs, voxel_mean);
+    BTC_CHECK_LAUNCH("occ_abs_vfe");
     return BTC_OK;
 }
 

@@ -280,7 +280,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                    float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
                    const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag,
-                   unsigned long long* __restrict__ trace) {
+                   unsigned long long* __restrict__ trace, const unsigned long long* __restrict__ tile_mask,
+                   const int* __restrict__ tile_order) {
     constexpr int STAGES = TcAStages<N, CAT>::value;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
@@ -681,6 +682,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                         if (t == num_tiles - 1) atomicExch(tile_ctr, 0);
                     }
                 }
+                // heaviest-first hand-out (btc_rulebook_tile_meta): position in the sequence -> tile id, so that the last
+                // tiles of a launch are its cheapest and the CTAs finish together
+                if (tile >= 0 && tile_order) tile = __ldg(tile_order + tile);
             }
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile < 0) {                            // publish the end marker and leave
@@ -706,17 +710,23 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 mbar_arrive(&nbr_full[buf]);
             }
             __syncwarp();
-            mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
-            // offsets with at least one valid neighbour among the tile's live rows
-            const int rows_live = n - row0 < TC_BM ? n - row0 : TC_BM;
+            // offsets with at least one valid neighbour among the tile's live rows: precomputed with the rulebook
+            // (btc_rulebook_tile_meta), else scanned here from the staged index tile (~2.5 us per tile on one warp)
             unsigned long long m = 0;
-            for (int r = lane; r < rows_live; r += 32) {
-                const uint32_t rp = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + r * K);
-                for (int k = 0; k < K; ++k) m |= (unsigned long long)(lds_i32(rp + 4u * (uint32_t)k) >= 0) << k;
+            if (tile_mask) {
+                m = __ldg(tile_mask + tile);
+                mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
+            } else {
+                mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
+                const int rows_live = n - row0 < TC_BM ? n - row0 : TC_BM;
+                for (int r = lane; r < rows_live; r += 32) {
+                    const uint32_t rp = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + r * K);
+                    for (int k = 0; k < K; ++k) m |= (unsigned long long)(lds_i32(rp + 4u * (uint32_t)k) >= 0) << k;
+                }
+                const uint32_t m_lo = __reduce_or_sync(0xffffffffu, (uint32_t)m);
+                const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
+                m = (unsigned long long)m_lo | ((unsigned long long)m_hi << 32);
             }
-            const uint32_t m_lo = __reduce_or_sync(0xffffffffu, (uint32_t)m);
-            const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
-            m = (unsigned long long)m_lo | ((unsigned long long)m_hi << 32);
             int cnt = 0;
             for (int c0 = 0; c0 < T; c0 += 32) {
                 const int c = c0 + lane;
@@ -806,6 +816,50 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     }
 }
 
+// ---- per-tile metadata of a neighbour table (btc_rulebook_tile_meta) ------------------------------------------------
+// tile_mask[t]: bit k set iff some live row of tile t (rows [128 t, 128 t + 128)) has a neighbour through offset k.
+// One CTA per tile, coalesced sweep over the tile's [128 x K] block of the table.
+__global__ void __launch_bounds__(128) tile_mask_kernel(const int* __restrict__ table, int n_cap, const int* __restrict__ n_dev,
+                                                        int K, unsigned long long* __restrict__ tile_mask) {
+    __shared__ unsigned long long s_m[4];
+    const int n = live_count(n_cap, n_dev);
+    const int row0 = blockIdx.x * TC_BM;
+    unsigned long long m = 0;
+    if (row0 < n) {
+        const int rows = n - row0 < TC_BM ? n - row0 : TC_BM;
+        const int total = rows * K;
+        const int* src = table + (int64_t)row0 * K;
+        for (int i = threadIdx.x; i < total; i += 128)
+            if (__ldg(src + i) >= 0) m |= 1ull << (i % K);
+    }
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)m), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_mask[blockIdx.x] = s_m[0] | s_m[1] | s_m[2] | s_m[3];
+}
+
+// tile_order: the live tiles sorted by descending number of active offsets (counting sort in one CTA; the order inside
+// a cost class is unspecified — it only decides which CTA runs which tile, never a result).
+__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned long long* __restrict__ tile_mask, int n_cap,
+                                                          const int* __restrict__ n_dev, int* __restrict__ tile_order) {
+    __shared__ int s_cnt[65], s_start[65];
+    const int n = live_count(n_cap, n_dev);
+    const int tiles = (n + TC_BM - 1) / TC_BM;
+    if (threadIdx.x < 65) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += 1024) atomicAdd(&s_cnt[__popcll(tile_mask[t])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 64; c >= 0; --c) { s_start[c] = acc; acc += s_cnt[c]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += 1024) {
+        const int c = __popcll(tile_mask[t]);
+        tile_order[atomicAdd(&s_start[c], 1)] = t;
+    }
+}
+
 // Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter at zero again (see
 // the scheduler warp).  Launches rotate through the slots, so kernels that overlap on different streams (or a captured
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
@@ -840,7 +894,8 @@ constexpr size_t kTcMaxSmem = 227 * 1024;
 template <int N, int NPW, bool CAT, int CG = 1, bool PDL = false>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
-                         const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
+                         const int* n_dev, int K, int c_in, int c_out, cudaStream_t st,
+                         const unsigned long long* tile_mask, const int* tile_order) {
     static_assert(TcBStages<N>::value == (N <= 32 ? 6 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
                   "tc_smem_bytes mirrors these");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
@@ -872,11 +927,13 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         BTC_CUDA(cudaLaunchKernelEx(&cfg, kern, feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
-                                    n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace), "conv_fwd_tc (programmatic dependent launch)");
+                                    n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace, tile_mask, g_tc_dyn ? tile_order : nullptr),
+                 "conv_fwd_tc (programmatic dependent launch)");
         return BTC_OK;
     }
     kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
-                                                     n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace);
+                                                     n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace, tile_mask,
+                                                     g_tc_dyn ? tile_order : nullptr);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
@@ -904,10 +961,11 @@ static void tc_config_init() {
 template <int N>
 static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                      const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
-                     const int* n_dev, int K, int c_in, int c_out, cudaStream_t st) {
+                     const int* n_dev, int K, int c_in, int c_out, cudaStream_t st,
+                     const unsigned long long* tile_mask, const int* tile_order) {
     tc_config_init();
     constexpr int NS = N <= 64 ? N : 64;   // instantiation guard for the N <= 64 only variants
-#define BTC_TC_ARGS feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in, c_out, st
+#define BTC_TC_ARGS feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in, c_out, st, tile_mask, tile_order
     if (g_tc_pdl && !g_tc_cat && g_tc_cg == 1) {   // experimental programmatic dependent launch (default tile only)
         if (N <= 64 && g_tc_npw == 16) return launch_tc_npw<NS, 16, false, 1, true>(BTC_TC_ARGS);
         return launch_tc_npw<N, 8, false, 1, true>(BTC_TC_ARGS);
@@ -1006,7 +1064,8 @@ int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, voi
 
 static int fwd_tc(const char* who, const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
                   const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_out_cap,
-                  const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
+                  const int* n_out_dev, int K, int c_in, int c_out, void* stream,
+                  const unsigned long long* tile_mask = nullptr, const int* tile_order = nullptr) {
     (void)who;
     if ((scale == nullptr) != (shift == nullptr)) return badarg("btc_sparse_conv_fwd_tc: scale/shift must come together");
     if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_fwd_tc: shape not supported", cudaSuccess);
@@ -1018,9 +1077,9 @@ static int fwd_tc(const char* who, const float* feat_in, const int* nbr_out, con
     cudaStream_t st = (cudaStream_t)stream;
     const float* pw = (const float*)packed_weight;
     switch (tc_padded_n(c_out)) {
-        case 32: return launch_tc<32>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 64: return launch_tc<64>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st);
-        case 128: return launch_tc<128>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st);
+        case 32: return launch_tc<32>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order);
+        case 64: return launch_tc<64>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order);
+        case 128: return launch_tc<128>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order);
     }
     return BTC_E_UNSUPPORTED;
 }
@@ -1030,6 +1089,30 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
                            const int* n_out_dev, int K, int c_in, int c_out, void* stream) {
     return fwd_tc("btc_sparse_conv_fwd_tc", feat_in, nbr_out, packed_weight, bias, scale, shift, relu, feat_out, nullptr,
                   n_out_cap, n_out_dev, K, c_in, c_out, stream);
+}
+
+int btc_sparse_conv_fwd_tc_meta(const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
+                                const float* scale, const float* shift, int relu, float* feat_out, int n_out_cap,
+                                const int* n_out_dev, int K, int c_in, int c_out, const uint64_t* tile_mask,
+                                const int* tile_order, void* stream) {
+    return fwd_tc("btc_sparse_conv_fwd_tc_meta", feat_in, nbr_out, packed_weight, bias, scale, shift, relu, feat_out, nullptr,
+                  n_out_cap, n_out_dev, K, c_in, c_out, stream, (const unsigned long long*)tile_mask, tile_order);
+}
+
+int btc_rulebook_tile_meta(const int* nbr_out, int n_out_cap, const int* n_out_dev, int K, uint64_t* tile_mask,
+                           int* tile_order, void* stream) {
+    if (K < 1 || K > 64 || n_out_cap < 0) return badarg("btc_rulebook_tile_meta: bad sizes");
+    if (n_out_cap == 0) return BTC_OK;
+    if (!nbr_out || !tile_mask) return badarg("btc_rulebook_tile_meta: null argument");
+    const int tiles = (n_out_cap + TC_BM - 1) / TC_BM;
+    cudaStream_t st = (cudaStream_t)stream;
+    tile_mask_kernel<<<tiles, 128, 0, st>>>(nbr_out, n_out_cap, n_out_dev, K, (unsigned long long*)tile_mask);
+    BTC_CHECK_LAUNCH("tile_mask");
+    if (tile_order) {
+        tile_order_kernel<<<1, 1024, 0, st>>>((const unsigned long long*)tile_mask, n_out_cap, n_out_dev, tile_order);
+        BTC_CHECK_LAUNCH("tile_order");
+    }
+    return BTC_OK;
 }
 
 int btc_sparse_conv_fwd_tc_rows(const float* feat_in, const int* nbr_sorted, const int* out_rows, const void* packed_weight,

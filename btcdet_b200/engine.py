@@ -58,7 +58,8 @@ class BackbonePlan:
     """
 
     def __init__(self, layer_specs, sparse_shape, batch, max_points_total, voxel_size, point_range, max_points=5,
-                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=False, side_priority=0):
+                 max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=False, side_priority=0,
+                 tile_meta=True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.batch = int(batch)
@@ -72,6 +73,9 @@ class BackbonePlan:
         # sort launches add 0.55 ms to the rulebook chain and save 0.07 ms of convolution
         self.sort_rows = bool(sort_rows)
         self._sorted = {}
+        # per-rulebook tile masks + heaviest-first tile order for the tcgen05 tile (btc_rulebook_tile_meta)
+        self.tile_meta = bool(tile_meta)
+        self._meta = {}
         dev = self.device
         B = self.batch
         # ---- static input + voxelisation buffers ------------------------------------------
@@ -136,6 +140,14 @@ class BackbonePlan:
             if self.algo != 1 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
                 packed = ops.tc_pack_weight(w)
             self.params.append((w, bias, scale, shift, packed))
+            meta = None
+            if packed is not None and self.tile_meta and not self.sort_rows and K <= 64:
+                meta = self._meta.get(id(nbr))
+                if meta is None:
+                    tiles = (nbr.shape[0] + 127) // 128
+                    meta = (torch.zeros(tiles, dtype=torch.int64, device=dev), torch.zeros(tiles, dtype=torch.int32, device=dev))
+                    self._meta[id(nbr)] = meta
+                    self.steps.append(_Step("tile_meta", (nbr, out_lvl, meta[0], meta[1])))
             rows = None
             if packed is not None and self.sort_rows:
                 rows = self._sorted.get(id(nbr))
@@ -144,7 +156,7 @@ class BackbonePlan:
                     self._sorted[id(nbr)] = rows
                     self.steps.append(_Step("sort_rb", (nbr, out_lvl, rows[0], rows[1])))
             self.steps.append(_Step("conv", (cur_feat, nbr, w, bias, scale, shift, bn is not None, out_feat, out_lvl, K,
-                                             conv.in_channels, conv.out_channels, packed, rows)))
+                                             conv.in_channels, conv.out_channels, packed, rows, meta)))
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
         self.graph = None
@@ -256,6 +268,11 @@ class BackbonePlan:
                                         _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
                   "btc_rulebook_conv")
             return 8
+        if s.kind == "tile_meta":
+            nbr, lvl, tmask, torder = s.args
+            check(lib.btc_rulebook_tile_meta(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(tmask), _ptr(torder), st),
+                  "btc_rulebook_tile_meta")
+            return 2
         if s.kind == "sort_rb":
             nbr, lvl, nbr_sorted, out_rows = s.args
             check(lib.btc_rulebook_sort_rows(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(nbr_sorted),
@@ -265,8 +282,13 @@ class BackbonePlan:
 
     def launch_conv(self, args, st):
         """One sparse-conv layer: tcgen05 tile when the weights were packed, fp32 FFMA tile otherwise."""
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = args
-        if packed is not None and rows is not None:
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = args
+        if packed is not None and meta is not None:
+            check(self.lib.btc_sparse_conv_fwd_tc_meta(_ptr(fin), _ptr(nbr), _ptr(packed), _ptr(bias), _ptr(scale),
+                                                       _ptr(shift), int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K,
+                                                       cin, cout, _ptr(meta[0]), _ptr(meta[1]), st),
+                  "btc_sparse_conv_fwd_tc_meta")
+        elif packed is not None and rows is not None:
             check(self.lib.btc_sparse_conv_fwd_tc_rows(_ptr(fin), _ptr(rows[0]), _ptr(rows[1]), _ptr(packed), _ptr(bias),
                                                        _ptr(scale), _ptr(shift), int(relu), _ptr(fout), lout.cap,
                                                        _ptr(lout.n_dev), K, cin, cout, st), "btc_sparse_conv_fwd_tc_rows")

@@ -501,6 +501,29 @@ def voxelize(points: torch.Tensor, scene_offsets: torch.Tensor, voxel_size, coor
     return voxels, coords, num_points, mean, n_voxels
 
 
+def points_to_cylinder(points: torch.Tensor, sphere=False, n_dev=None, out=None):
+    """absxyz_2_cylinxyz_np / absxyz_2_spherexyz_np (btcdet/utils/coords_utils.py:268-292) on device points [N, C>=3]:
+    (rho, phi_deg, z, extra...) or (r, az_deg, el_deg, extra...), numpy's float32 op order."""
+    _require_cuda(points)
+    assert points.dtype == torch.float32 and points.dim() == 2 and points.is_contiguous()
+    n, c = points.shape
+    out = torch.empty_like(points) if out is None else out
+    check(_lib.load().btc_points_to_cylinder(_ptr(points), n, _ptr(n_dev), c, int(bool(sphere)), _ptr(out), _stream()),
+          "btc_points_to_cylinder")
+    return out
+
+
+def voxelize_occ_and_det(points, scene_offsets, occ_voxel_size, occ_range, occ_max_points, occ_max_voxels,
+                         det_voxel_size, det_range, det_max_points, det_max_voxels, want_mean=True):
+    """GPU-resident input pipeline: raw points feed BOTH voxelisers of data_processor.py:105-190 without
+    leaving the device — the cylindrical occupancy voxeliser (a2 transform + VoxelGeneratorV2, :128-136) and the Cartesian
+    detection voxeliser (:176-177).  Returns (occ, det), each the tuple voxelize() returns."""
+    cyl = points_to_cylinder(points)
+    occ = voxelize(cyl, scene_offsets, occ_voxel_size, occ_range, occ_max_points, occ_max_voxels, want_mean=want_mean)
+    det = voxelize(points, scene_offsets, det_voxel_size, det_range, det_max_points, det_max_voxels, want_mean=False)
+    return occ, det
+
+
 def voxel_grid_size(voxel_size, coors_range):
     """grid = round((max - min) / voxel_size) with float32 operands, as VoxelGeneratorV2.__init__ computes it."""
     import numpy as np
@@ -592,6 +615,34 @@ DEFAULT_LOSS_WEIGHTS = {"occ_fore_cls_weight": 1.0, "occ_mirr_cls_weight": 1.0, 
                         "occ_bm_res_weight": 0.0}
 
 
+_CENTERS2D = {}
+
+
+def occ_voxel_centers_2d(geom_f, geom_i, device):
+    """The reference's `voxel_centers["all_voxel_centers_2d"]` (detector3d_template.py:52-63): cylinder voxel centres ->
+    Cartesian -> mean over z of (x, y), flattened [ny * nx, 2].  Computed with the same torch ops as the reference at model
+    build (so every rounding, including the 9-term mean, is torch's) and cached per geometry and device."""
+    key = (tuple(float(v) for v in geom_f[:6]), tuple(int(v) for v in geom_i[:3]), str(device))
+    hit = _CENTERS2D.get(key)
+    if hit is None:
+        import numpy as np
+        nx, ny, nz = (int(v) for v in geom_i[:3])
+        vs = torch.tensor([float(geom_f[2]), float(geom_f[1]), float(geom_f[0])], dtype=torch.float32, device=device)
+        org = torch.tensor([float(geom_f[5]), float(geom_f[4]), float(geom_f[3])], dtype=torch.float32, device=device)
+        # ^ get_all_voxel_centers_zyx (coords_utils.py:166-178): float32 tensors built from python floats
+        z, y, x = torch.meshgrid(torch.arange(nz, device=device), torch.arange(ny, device=device),
+                                 torch.arange(nx, device=device), indexing="ij")
+        c = (0.5 + torch.stack([z, y, x], dim=0).to(torch.float32)) * vs.view(3, 1, 1, 1) + org.view(3, 1, 1, 1)
+        rho, phi = c[2], c[1]                                                          # cylinder_uvd2absxyz (:198-204)
+        cx = rho * torch.cos(phi * np.pi / 180.)
+        cy = -rho * torch.sin(phi * np.pi / 180.)
+        centers = torch.stack([cx, cy, c[0]], dim=-1)          # [nz, ny, nx, 3], the layout the reference reduces over
+        hit = torch.mean(centers[:, :, :, :2], dim=0).view(-1, 2).contiguous()
+        assert hit.dtype == torch.float32
+        _CENTERS2D[key] = hit
+    return hit
+
+
 def occ_box_targets(voxels, voxel_coords, voxel_num_points, batch_size, gt_boxes, gt_boxes_num, geom_f, geom_i,
                     box_mirr_flag=None, bm_points=None, rot_z=None, num_class=1, want_forebox=True, want_point_label=False,
                     mirr_cap=None, bm_cap=None):
@@ -631,9 +682,10 @@ def occ_box_targets(voxels, voxel_coords, voxel_num_points, batch_size, gt_boxes
     ws_bytes = int(lib.btc_occ_box_targets_workspace_bytes(B, max_boxes, mirr_cap, bm_cap))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rz = None if rot_z is None else rot_z.to(torch.float32).contiguous()
-    check(lib.btc_occ_box_targets(_ptr(voxels), P, C, _ptr(coords), _ptr(nump), m, None, B, _ptr(boxes), max_boxes, box_dim,
+    c2d = occ_voxel_centers_2d(geom_f, geom_i, dev) if want_forebox else None
+    check(lib.btc_occ_box_targets_v2(_ptr(voxels), P, C, _ptr(coords), _ptr(nump), m, None, B, _ptr(boxes), max_boxes, box_dim,
                                   _ptr(bnum), _ptr(flag), _ptr(bm), n_bm, _ptr(rz), gf, gi, int(num_class), mirr_cap, bm_cap,
-                                  _ptr(out["fore_voxelwise_mask"]), _ptr(out["fore_res_mtrx"]),
+                                  _ptr(c2d), _ptr(out["fore_voxelwise_mask"]), _ptr(out["fore_res_mtrx"]),
                                   _ptr(out["mirr_fore_voxelwise_mask"]), _ptr(out["mirr_res_mtrx"]),
                                   _ptr(out["bm_voxelwise_mask"]), _ptr(out["bm_res_mtrx"]), _ptr(out["forebox_label"]),
                                   _ptr(out["point_label"]), _ptr(out["status"]), _ptr(ws), ws_bytes, _stream()),

@@ -95,6 +95,19 @@ int btc_voxelize(const float* points, int n_points, int n_feat,
                  int* n_voxels,
                  void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Dataset-side coordinate transform of the occupancy branch: absxyz_2_cylinxyz_np / absxyz_2_spherexyz_np
+ * (btcdet/utils/coords_utils.py:268-292, called at btcdet/datasets/processor/data_processor.py:128-131) on device points,
+ * numpy's float32 op order (norm = sqrt(x*x + y*y), angle = (atan2 * 180) / pi: two roundings).
+ *   points [n_cap, n_feat] f32 -> out [n_cap, n_feat] f32: (rho, phi_deg, z, extra...) or, sphere = 1,
+ *   (r, azimuth_deg, elevation_deg, extra...).  n_dev [1] i32 device live count or NULL.
+ * The output feeds btc_voxelize with the cylindrical voxel size / range (the occ voxeliser).  (The augmentation-only
+ * SAVE_PRE_ROT branch, data_processor.py:149-150, subtracts rot_z from the voxel CONTENTS after grouping and is not part
+ * of this call.)
+ */
+int btc_points_to_cylinder(const float* points, int n_cap, const int* n_dev, int n_feat, int sphere, float* out,
+                           void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Coordinate index ("rank bitmap")                                            */
 /* Replaces the dense int32 `grid` / cuckoo hash of spconv 1.2.1              */
@@ -283,6 +296,21 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
  */
 int btc_rulebook_sort_rows(const int* nbr_out, int n_cap, const int* n_dev, int K, int* nbr_sorted, int* out_rows,
                            void* stream);
+/*
+ * Per-tile metadata of a neighbour table for the tcgen05 tile (tiles = 128 consecutive rows):
+ *   tile_mask  [ceil(n_out_cap / 128)] u64: bit k set iff a live row of the tile has a neighbour through offset k
+ *              (the block-skipping mask the tile otherwise derives from its staged index block, ~2.5 us per tile);
+ *   tile_order [ceil(n_out_cap / 128)] i32 or NULL: the live tiles by descending number of active offsets — the dynamic
+ *              tile scheduler hands tiles out in this order, so a launch ends on its cheapest tiles (no long tail).
+ * Built once per rulebook (2 launches), shared by every layer that uses the table.  K <= 64.
+ * btc_sparse_conv_fwd_tc_meta = btc_sparse_conv_fwd_tc with the two arrays (either may be NULL); results are identical.
+ */
+int btc_rulebook_tile_meta(const int* nbr_out, int n_out_cap, const int* n_out_dev, int K, uint64_t* tile_mask,
+                           int* tile_order, void* stream);
+int btc_sparse_conv_fwd_tc_meta(const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
+                                const float* scale, const float* shift, int relu, float* feat_out, int n_out_cap,
+                                const int* n_out_dev, int K, int c_in, int c_out, const uint64_t* tile_mask,
+                                const int* tile_order, void* stream);
 int btc_sparse_conv_fwd_tc_rows(const float* feat_in, const int* nbr_sorted, const int* out_rows,
                                 const void* packed_weight, const float* bias, const float* scale,
                                 const float* shift, int relu, float* feat_out, int n_out_cap,
@@ -413,6 +441,12 @@ int btc_occ_select(const float* probs, const float* residuals, int batch, const 
                    int* counts, void* workspace, int64_t workspace_bytes, void* stream);
 int btc_occ_vfe(const float* voxels, const int* num_points, int m_cap, const int* m_dev, int P, int C,
                 int num_raw, float* feats, float* occ_feats, void* stream);
+/* MeanVFE of the occupancy branch (occ side): occ_targets_3d.py:45-47 (USE_ABSXYZ) rewrites every slot of
+ * the cylindrical occ voxels to cylinder_uvd2absxyz(rho, phi, z) + extra columns, mean_vfe.py:27-44 then averages all
+ * slots / clamp_min(count, 1).  voxels [m_cap, max_points, n_feat] (rho, phi_deg, z, ...) -> voxels_abs (same shape, may
+ * be NULL) and voxel_mean [m_cap, n_feat] — the input features of VoxelBackBoneDeconv. */
+int btc_occ_abs_mean_vfe(const float* voxels, int max_points, int n_feat, const int* num_points, int m_cap, const int* m_dev,
+                         float* voxels_abs, float* voxel_mean, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Box-driven occupancy targets                        */
@@ -451,6 +485,17 @@ int btc_occ_box_targets(const float* voxels, int P, int C, const int* voxel_coor
                         int mirr_cap, int bm_cap, uint8_t* fore_mask, float* fore_res, uint8_t* mirr_mask,
                         float* mirr_res, uint8_t* bm_mask, float* bm_res, int8_t* forebox_label,
                         int8_t* point_label, int* status, void* workspace, int64_t workspace_bytes, void* stream);
+/* Same call with the reference's `voxel_centers["all_voxel_centers_2d"]` table (detector3d_template.py:52-63: the mean
+ * over z of the voxel centres' xy, [ny * nx, 2] f32 device, computed by torch at model build) for the 2-D pre-filter of
+ * the forebox label (occ_targets_3d.py:78-79).  With the table the forebox label is the reference's bit for bit; NULL uses
+ * the un-averaged centre (differs from torch's 9-term mean by at most one ulp on a few columns). */
+int btc_occ_box_targets_v2(const float* voxels, int P, int C, const int* voxel_coords, const int* num_points,
+                           int m_cap, const int* m_dev, int batch, const float* gt_boxes, int max_boxes, int box_dim,
+                           const int* gt_boxes_num, const float* mirr_flag, const float* bm_points, int n_bm,
+                           const float* rot_z, const float* geom_f, const int* geom_i, int num_class,
+                           int mirr_cap, int bm_cap, const float* centers2d, uint8_t* fore_mask, float* fore_res,
+                           uint8_t* mirr_mask, float* mirr_res, uint8_t* bm_mask, float* bm_res, int8_t* forebox_label,
+                           int8_t* point_label, int* status, void* workspace, int64_t workspace_bytes, void* stream);
 int btc_occ_loss_maps(const uint8_t* voxelwise_mask, const uint8_t* general_mask, const uint8_t* fore_mask,
                       const uint8_t* mirr_mask, const uint8_t* bm_mask, const int8_t* forebox_label,
                       const float* fore_res, const float* mirr_res, const float* bm_res, const float* weights,

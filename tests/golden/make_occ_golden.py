@@ -76,7 +76,7 @@ def run_reference(inp, geo, device="cpu", keep_all=False):
         tgt = mods["occ_targets_3d"].OccTargets3D(ref_loader.Cfg.wrap(MODEL_OCC_CFG), voxel_size=geo.voxel_size,
                                                   point_cloud_range=geo.point_cloud_range,
                                                   data_cfg=ref_loader.Cfg.wrap(data_cfg(geo)), grid_size=geo.grid_size,
-                                                  num_class=1, voxel_centers=vc)
+                                                  num_class=1, voxel_centers=vc).to(device)   # as model.cuda() does
         bd = {k: (torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) else v) for k, v in inp.items()}
         bd["is_train"] = True
         out = tgt(bd)

@@ -1,12 +1,14 @@
 """GPU parity of the box-driven occupancy targets (btc_occ_box_targets / btc_occ_loss_maps).
 
 Checker: oracle/box_masks.py (pinned bit-for-bit to the reference's create_voxel_res_label on CPU by
-tests/test_box_masks_cpu.py) executed with torch on the SAME device.  The reference maps points into box frames through
-torch.inverse (LU); the kernel uses the analytic rigid inverse, so the comparison is
-  * exact for every point / cell whose box-frame margin to a box face exceeds MARGIN (1e-4 m),
-  * bounded (<= 1 % of the set cells) for the masks that depend on re-quantised mirrored / template points and on
-    voxel centres, whose bin-edge cases flip with one ulp,
-  * exact for the loss-map algebra (a12), which is evaluated on identical inputs."""
+tests/test_box_masks_cpu.py) executed with torch on the SAME device, i.e. through the same torch.inverse (CUDA batched LU)
+and einsum / matmul (K = 3 GEMM) the reference itself runs.  The kernels reproduce both operation by operation
+(csrc/box_masks.cu lu_inverse + FMA chains; pinned to B200 dumps in tests/test_box_inverse_cpu.py), so
+  * point labels, fore / mirrored / best-match masks and the forebox label are BIT-EXACT — including points on a box face
+    and mirrored points on a bin edge (tests/test_reference_on_gpu.py shows the same against OccTargets3D.forward itself);
+  * the per-cell mean residuals agree to 2e-5: the reference accumulates them with float atomics (scatter_add_, order
+    dependent), the kernel in order-independent 2^-24 fixed point;
+  * the loss-map algebra (a12) is exact on identical inputs."""
 import os
 import sys
 
@@ -85,34 +87,21 @@ def _frac_diff(a, b):
 def test_box_targets_match_oracle_on_device(cuda, oracle, seeds, n, with_rot, with_bm):
     inp, geo = _case(seeds, n, with_rot, with_bm)
     t, occ, got, ref_occ, want, margin = _run(inp, geo)
-    vc = ref_occ["valid_coords"]
-    # a9 point labels: exact away from box faces
+    # a9 point labels: exact for every point, the ones within rounding distance of a box face included
     mask = ref_occ["voxel_point_mask"]
-    got_label = got["point_label"][mask]
-    safe = margin > MARGIN
-    assert torch.equal(got_label[safe], want["point_label"][safe])
-    assert int((got_label != want["point_label"]).sum()) <= int((~safe).sum())
+    assert torch.equal(got["point_label"][mask], want["point_label"])
     assert int((want["point_label"] > 0).sum()) > 30
-    # fore mask / residual: exact on cells that hold no ambiguous point
-    amb = torch.zeros_like(want["fore_voxelwise_mask"], dtype=torch.bool)
-    ac = vc[~safe]
-    amb[ac[:, 0], ac[:, 1], ac[:, 2], ac[:, 3]] = True
-    ok = ~amb
-    assert torch.equal(got["fore_voxelwise_mask"][ok], want["fore_voxelwise_mask"][ok])
-    ok3 = ok.unsqueeze(1).expand(-1, 3, -1, -1, -1)
-    torch.testing.assert_close(got["fore_res_mtrx"][ok3], want["fore_res_mtrx"][ok3], rtol=0, atol=2e-5)
+    assert torch.equal(got["fore_voxelwise_mask"], want["fore_voxelwise_mask"])
+    torch.testing.assert_close(got["fore_res_mtrx"], want["fore_res_mtrx"], rtol=0, atol=2e-5)
     assert int(want["fore_voxelwise_mask"].sum()) > 50
-    # mirrored / template cells: bounded bin-edge flips, residuals agree where the same points landed
+    # mirrored / template cells: the same cells; residuals up to the accumulation order
     for mk, rk in (("mirr_fore_voxelwise_mask", "mirr_res_mtrx"),) + ((("bm_voxelwise_mask", "bm_res_mtrx"),) if with_bm else ()):
-        d, tot = _frac_diff(got[mk], want[mk])
-        assert tot > 10 and d <= max(2, int(0.01 * tot)), (mk, d, tot)
-        both = (got[mk].bool() & want[mk].bool()).unsqueeze(1).expand(-1, 3, -1, -1, -1)
-        err = (got[rk][both] - want[rk][both]).abs()
-        assert float((err > 1e-4).float().mean()) <= 0.02, (rk, float(err.max()))
-        assert float(err.median()) < 1e-5
-    # a11 forebox label
-    d, tot = _frac_diff(got["forebox_label"] > 0, want["forebox_label"] > 0)
-    assert tot > 100 and d <= max(2, int(0.01 * tot)), ("forebox", d, tot)
+        assert torch.equal(got[mk], want[mk]), mk
+        assert int(want[mk].sum()) > 10
+        torch.testing.assert_close(got[rk], want[rk], rtol=0, atol=2e-5)
+    # a11 forebox label (2-D pre-filter on the z-mean centres + 3-D test): exact
+    assert torch.equal(got["forebox_label"], want["forebox_label"])
+    assert int((want["forebox_label"] > 0).sum()) > 100
 
 
 def test_loss_maps_exact(cuda, oracle):
@@ -173,14 +162,11 @@ def test_box_targets_edge_cases(cuda, oracle):
     t, occ, got, ref_occ, want, margin = _run(inp, geo, num_class=3)
     assert int(got["fore_voxelwise_mask"][0].sum()) == 0 and int(got["forebox_label"][0].abs().sum()) == 0
     assert int(got["mirr_fore_voxelwise_mask"][0].sum()) == 0
-    safe = margin > MARGIN
     mask = ref_occ["voxel_point_mask"]
-    assert torch.equal(got["point_label"][mask][safe], want["point_label"][safe])
+    assert torch.equal(got["point_label"][mask], want["point_label"])
     assert int(want["point_label"].max()) >= 2                                   # multi-class labels survive
-    d, tot = _frac_diff(got["mirr_fore_voxelwise_mask"], want["mirr_fore_voxelwise_mask"])
-    assert d <= max(2, int(0.01 * tot))
-    lab_g, lab_w = got["forebox_label"], want["forebox_label"]
-    assert int((lab_g != lab_w).sum()) <= max(2, int(0.01 * int((lab_w > 0).sum())))
+    assert torch.equal(got["mirr_fore_voxelwise_mask"], want["mirr_fore_voxelwise_mask"])
+    assert torch.equal(got["forebox_label"], want["forebox_label"])
     gf, gi = ops.occ_geometry_arrays(geo.voxel_size, geo.point_cloud_range, geo.support_sphere_range, geo.dist_kern,
                                      geo.half_x, geo.empt_sur_thresh, geo.det_point_cloud_range)
     out = ops.occ_box_targets(t["voxels"][:0], t["voxel_coords"][:0], t["voxel_num_points"][:0], 2, t["gt_boxes"],

@@ -100,9 +100,33 @@ def section_inverse(report):
     inv_1 = torch.stack([torch.inverse(T[i]) for i in range(16)])
     pts = torch.from_numpy(rng.uniform(-1, 1, (512, 3)).astype(np.float32) * 40 + np.array([35, 0, -1], np.float32)).cuda()
     q = torch.einsum("nj,mij->nmi", pts, inv_12[:, :3, :3]) + inv_12[:, :3, 3]
+    # 2-D transforms of torch_points_in_box_2d_mask (point_box_utils.py:332-365), the mirrored points' way back
+    # (einsum "nmj,mij->nmi", :295-301) and rotatez (torch.matmul, :241-250): the remaining GEMM shapes of rows a9-a11
+    c2, s2 = torch.cos(b[:, 6]), torch.sin(b[:, 6])
+    rot2 = torch.stack([torch.stack([c2, -1.0 * s2], dim=-1), torch.stack([s2, c2], dim=-1)], dim=-2)
+    t2 = torch.cat([rot2, b[:, :2].unsqueeze(-1)], dim=-1)
+    last = torch.cat([torch.zeros_like(b[:, :2]), torch.ones_like(b[:, 0:1])], dim=-1)
+    T2 = torch.cat([t2, last.unsqueeze(-2)], dim=-2)
+    inv2_all = torch.inverse(T2)
+    q2 = torch.einsum("nj,mij->nmi", pts[:, :2].contiguous(), inv2_all[:12, :2, :2]) + inv2_all[:12, :2, 2]
+    qm = q.clone()
+    qm[:, :, 1] = -qm[:, :, 1]
+    back = torch.einsum("nmj,mij->nmi", qm, rot[:12]) + b[:12, :3]
+    yaw = torch.tensor(7.5, device="cuda") * np.pi / 180.
+    cy_, sy_ = torch.cos(yaw), torch.sin(yaw)
+    r3 = torch.transpose(torch.stack([torch.stack([cy_, -1.0 * sy_, torch.zeros_like(yaw)], dim=-1),
+                                      torch.stack([sy_, cy_, torch.zeros_like(yaw)], dim=-1),
+                                      torch.stack([torch.zeros_like(yaw), torch.zeros_like(yaw), torch.ones_like(yaw)], dim=-1)],
+                                     dim=-2), 0, 1)
+    r2 = torch.transpose(torch.stack([torch.stack([cy_, -1.0 * sy_], dim=-1), torch.stack([sy_, cy_], dim=-1)], dim=-2), 0, 1)
+    rot3_pts = torch.matmul(pts, r3)
+    rot2_pts = torch.matmul(pts[:, :2].contiguous(), r2)
     np.savez_compressed(os.path.join(OUT, "box_inverse_cuda.npz"), boxes=boxes, T=T.cpu().numpy(), inv_all=inv_all.cpu().numpy(),
                         inv_12=inv_12.cpu().numpy(), inv_1=inv_1.cpu().numpy(), pts=pts.cpu().numpy(), q=q.cpu().numpy(),
-                        cos=torch.cos(b[:, 6]).cpu().numpy(), sin=torch.sin(b[:, 6]).cpu().numpy())
+                        cos=torch.cos(b[:, 6]).cpu().numpy(), sin=torch.sin(b[:, 6]).cpu().numpy(),
+                        T2=T2.cpu().numpy(), inv2_all=inv2_all.cpu().numpy(), q2=q2.cpu().numpy(), back=back.cpu().numpy(),
+                        rot_cos=cy_.cpu().numpy(), rot_sin=sy_.cpu().numpy(), rot3_pts=rot3_pts.cpu().numpy(),
+                        rot2_pts=rot2_pts.cpu().numpy())
     report["inverse"] = {"batched_eq_first12": bool(torch.equal(inv_all[:12], inv_12)),
                          "batched_eq_single": bool(torch.equal(inv_all[:16], inv_1)),
                          "cpu_eq_cuda": bool(torch.equal(torch.inverse(T.cpu()), inv_all.cpu()))}

@@ -30,6 +30,7 @@ def main():
                     "(btc_sparse_conv_tc_diag masks; wrong results, timing only)")
     ap.add_argument("--commit-group", type=int, default=1, help="EXPERIMENTAL: stages per tcgen05.commit (1, 2, 3)")
     ap.add_argument("--pdl", action="store_true", help="EXPERIMENTAL: programmatic dependent launch of the conv tile")
+    ap.add_argument("--no-tile-meta", action="store_true", help="A/B: without the per-rulebook tile masks / heaviest-first order")
     ap.add_argument("--grids", default="", help="comma-separated caps on the conv grid: only the captured graph is timed per cap")
     ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
                     "(one JSON line each), e.g. '16,1,1;16,0,1;16,1,0'")
@@ -58,7 +59,8 @@ def grid_sweep(args):
         model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
         plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                    max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                                   device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority).capture()
+                                   device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority,
+                               tile_meta=not args.no_tile_meta).capture()
         plan.load_points(pts_d, offs_d)
         ms = []
         for r in range(args.reps + 3):
@@ -88,7 +90,8 @@ def run(args, npw, cat, dyn):
     model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                               device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority).capture()
+                               device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority,
+                               tile_meta=not args.no_tile_meta).capture()
     pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
     plan.load_points(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     plan.step()
@@ -134,7 +137,7 @@ def run(args, npw, cat, dyn):
             if s.kind == "conv":
                 plan.launch_conv(s.args, st)
 
-    res = {"batch": B, "sorted_rows": args.sort, "variant": {"producer_warps": npw, "concat_b": cat, "dynamic_tiles": dyn},
+    res = {"batch": B, "sorted_rows": args.sort, "tile_meta": not args.no_tile_meta, "variant": {"producer_warps": npw, "concat_b": cat, "dynamic_tiles": dyn},
            "steps": rows,
            "sum_index_us": round(sum(r["us"] for r in rows if not r["step"].startswith("conv ")), 1),
            "sum_conv_us": round(sum(r["us"] for r in rows if r["step"].startswith("conv ")), 1),

@@ -23,6 +23,7 @@ import torch  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--no-tile-meta", action="store_true")
     args = ap.parse_args()
     from btcdet_b200 import _lib, backbones, engine, synthetic as S
     lib = _lib.load()
@@ -31,7 +32,7 @@ def main():
     model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
     B = args.batch
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
-                               max_points=5, max_voxels=16000, device=dev, use_graph=False).capture()
+                               max_points=5, max_voxels=16000, device=dev, use_graph=False, tile_meta=not args.no_tile_meta).capture()
     pts, offs = S.batch_points([S.lidar_like(20000, seed=1000 + i) for i in range(B)])
     plan.forward(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     torch.cuda.synchronize()
@@ -43,7 +44,7 @@ def main():
     for s in plan.steps:
         if s.kind != "conv":
             continue
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows = s.args
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = s.args
         if packed is None:
             continue
         rec = {"layer": "%d->%d K=%d" % (cin, cout, K), "rows": int(lout.n_dev.item())}
@@ -86,7 +87,7 @@ def main():
             "cycles_per_stage_med": round(float(np.median((t[:, 7] - t[:, 6]) / np.maximum(t[:, 13], 1))), 1),
         })
         out.append(rec)
-    print(json.dumps({"batch": B, "layers": out}, indent=1))
+    print(json.dumps({"batch": B, "tile_meta": not args.no_tile_meta, "layers": out}, indent=1))
 
 
 if __name__ == "__main__":
