@@ -27,7 +27,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 N_POINTS = 20000
-N_SCENE_POOL = 24          # pre-generated scenes per rank; batches of B are cut from them (one batch at B = 16)
+N_SCENE_POOL = 48          # pre-generated scenes per rank; batches of B are cut from them (three distinct batches at B = 16)
+N_REPEATS = 9              # further repetitions of the K-step timed block (median / spread reported beside `value`)
 
 
 def parse():
@@ -44,6 +45,10 @@ def parse():
     ap.add_argument("--overlap", action="store_true", help="EXPERIMENTAL: also measure e2e through engine.OverlappedBackbone "
                     "(reported under the separate key e2e_overlapped; the e2e key stays the verified path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the gpu_native_baseline / train / chain / stress legs")
+    ap.add_argument("--conv-grid", type=int, default=0, help="cap on the persistent conv grid (0 = one CTA per SM); with "
+                    "--overlap a smaller grid leaves whole SMs to the rulebook chain of the next batch")
+    ap.add_argument("--no-tile-meta", action="store_true", help="A/B: without per-rulebook tile masks / heaviest-first order")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the bounded CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -184,9 +189,12 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(dev)
     B = args.batch
     model = build_model()
+    if args.conv_grid:
+        _lib.check(_lib.load().btc_sparse_conv_tc_grid(int(args.conv_grid)), "btc_sparse_conv_tc_grid")
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
-                               device=dev, use_graph=not args.no_graph, sort_rows=args.sort).capture()
+                               device=dev, use_graph=not args.no_graph, sort_rows=args.sort,
+                               tile_meta=not args.no_tile_meta).capture()
     scenes = make_scenes(rank, N_SCENE_POOL)
     # batches: host pinned (for e2e) and device resident (for value)
     n_batches = N_SCENE_POOL // B if N_SCENE_POOL >= B else 1
@@ -259,6 +267,8 @@ def run_ours(args, rank, world):
         sampler.start()
     ms_dev = timed(step_dev, args.steps, args.warmup)
     counts = plan.read_counts()
+    # further repetitions of the same K-step block (the contract's number is the block above): median and spread
+    rep_ms = [ms_dev / args.steps] + [timed(step_dev, args.steps, 0) / args.steps for _ in range(N_REPEATS)]
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region -----------------------------------
     # The host-facing call is a 2-deep software pipeline (engine.submit / retrieve): while batch i computes, the
@@ -294,7 +304,8 @@ def run_ours(args, rank, world):
             def make_plan():
                 return engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE,
                                            S.KITTI_RANGE, max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"],
-                                           algo=args.algo, device=dev, use_graph=False, sort_rows=args.sort)
+                                           algo=args.algo, device=dev, use_graph=False, sort_rows=args.sort,
+                                           tile_meta=not args.no_tile_meta)
             ov = engine.OverlappedBackbone(make_plan, slots=2).capture()
             ov_out, ov_last = [0], [None]
 
@@ -357,6 +368,9 @@ def run_ours(args, rank, world):
         "metric": "scenes/sec (KITTI-range 20k-pt clouds, voxel 0.05 m)", "value": round(scenes_total / (ms_dev * 1e-3), 2),
         "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "repeats": {"blocks": len(rep_ms), "steps_per_block": args.steps, "ms_per_step_median": round(float(np.median(rep_ms)), 4),
+                    "ms_per_step_min": round(min(rep_ms), 4), "ms_per_step_max": round(max(rep_ms), 4),
+                    "value_median": round(world * B / (float(np.median(rep_ms)) * 1e-3), 2)},
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: VoxelBackBone8x forward (voxelize+MeanVFE+rulebooks+12 sparse convs) on "
                                "lidar_like 20k-pt KITTI-range clouds, voxel [0.05,0.05,0.1], C_in=4",
@@ -376,6 +390,35 @@ def run_ours(args, rank, world):
         res["e2e_overlapped"] = e2e_ov
     if roof:
         res["roofline"] = roof
+    # ---- further legs (north_star items the headline metric does not cover) ---------------------------
+    if not args.no_extra:
+        from tools import bench_legs
+        if rank == 0:
+            try:   # spconv-1.2.1 Native re-created on the GPU: the denominator of ">= 10x the spconv CUDA backbone"
+                nat, nat_out = bench_legs.native_gpu_leg(model, scenes, B, dev)
+                sel = [scenes[j % N_SCENE_POOL] for j in range(B)]
+                pts, offs = S.batch_points(sel)
+                feat, coords, n_dev = plan.forward(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
+                n = int(n_dev.item())
+                err = float((feat[:n] - nat_out).abs().max() / nat_out.abs().max()) if n == nat_out.shape[0] else None
+                nat["max_rel_diff_vs_ours"] = err
+                nat["ours_over_native"] = round(res["value"] / world / nat["value"], 2)
+                res["gpu_native_baseline"] = nat
+            except Exception as exc:
+                res["gpu_native_baseline"] = {"error": repr(exc)}
+            for key, fn in (("chain", lambda: bench_legs.chain_leg(dev)),
+                            ("stress", lambda: bench_legs.stress_leg(dev, float(roof["peak"]) if roof else 6552.0))):
+                try:
+                    res[key] = fn()
+                except Exception as exc:
+                    res[key] = {"error": repr(exc)}
+        try:       # config 4: every rank takes part (DDP gradient all-reduce over NCCL)
+            tr = bench_legs.train_leg(rank, world, dev)
+            if rank == 0:
+                res["train"] = tr
+        except Exception as exc:
+            if rank == 0:
+                res["train"] = {"error": repr(exc)}
     return res, scenes
 
 
@@ -463,7 +506,7 @@ def main():
             "config": {"workload": "configs[1]: VoxelBackBone8x forward on lidar_like 20k-pt KITTI-range clouds "
                                    "(CPU oracle port of spconv-1.2.1 Native: C rulebooks + per-offset gather/torch.mm/"
                                    "scatter-add)", "scenes_per_step": per_step, "points_per_scene": N_POINTS},
-            "cpu_baseline": {"value": round(val, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": round(val, 4), "unit": "scenes/s", "cores": os.cpu_count(), "threads": cores, "kind": "port",
                              "sample": "%d scenes of 20k points, full voxelize+backbone forward each" % done},
             "e2e": {"value": round(val, 4), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -477,7 +520,7 @@ def main():
         if not args.no_cpu_baseline:
             n_cpu = args.cpu_scenes or 6
             val, cores, dt = run_cpu(scenes, n_cpu)
-            res["cpu_baseline"] = {"value": round(val, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+            res["cpu_baseline"] = {"value": round(val, 4), "unit": "scenes/s", "cores": os.cpu_count(), "threads": cores, "kind": "port",
                                    "sample": "%d scenes of 20k points (%.1f s of CPU work), full voxelize+backbone "
                                              "forward on the oracle port" % (n_cpu, dt)}
         print(json.dumps(res))

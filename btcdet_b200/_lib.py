@@ -30,6 +30,11 @@ SIGNATURES = {
     "btc_rulebook_subm_hash": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "btc_rulebook_subm": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "btc_rulebook_conv": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _i, _p, _p, _p, _p, _i64, _p]),
+    "btc_rulebook_tile_order": (_i, [_p, _i, _p, _p, _p]),
+    "btc_index_summary_words": (_i64, [_i64]),
+    "btc_rulebook_conv_sparse_workspace_bytes": (_i64, [_i64]),
+    "btc_rulebook_conv_sparse": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _p, _i, _p, _p, _p, _p, _i64, _p]),
+    "btc_index_clear_sparse": (_i, [_p, _i, _p, _i, _p, _p, _i64, _p, _p]),
     "btc_rulebook_pairs_workspace_bytes": (_i64, [_i, _i]),
     "btc_rulebook_pairs": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i64, _p]),
     "btc_sparse_conv_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),

@@ -1,0 +1,127 @@
+"""BtcNet's data-parallel hot path composed end to end on the CUDA library (BASELINE config 3).
+
+Modules 1-8 of BtcNet.forward (btcdet/models/detectors/btcnet.py:32-56, module order detector3d_template.py:28-34):
+  1 OccTargets3D.forward            -> ops.occ_training_targets          (3 C-ABI calls, no host sync)
+  2 MeanVFE on absolute coordinates -> btc_occ_abs_mean_vfe              (occ_targets_3d.py:45-47 + mean_vfe.py:27-44)
+  3 VoxelBackBoneDeconv.forward     -> backbones.OccBackbone on the spconv shim
+  4 OccHead3D.forward               -> backbones.OccHead (SubM + dense + softmax x mask)
+  5 PassOccVox.forward              -> ops.pass_occ_vox                  (select + pseudo points + sorted re-voxelisation)
+  6 OccVFE.forward                  -> btc_occ_vfe
+  7 VoxelBackBone8xOcc.forward      -> backbones.DetBackboneOcc on the spconv shim
+  8 HeightCompression.forward       -> dense() + view                    (height_compression.py:21-23)
+The batch_dict keys follow the reference's contract, so the reference's own BEV backbone / heads can
+consume the result unchanged.  Any module 3 / 4 / 7 implementation with the reference's forward(batch_dict) signature
+can be passed in — in particular the reference's own classes (tests/test_reference_on_gpu.py does exactly that).
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib, backbones, ops, synthetic as S
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def occ_abs_mean_vfe(voxels, voxel_num_points, want_abs=True):
+    """(voxels rewritten to absolute xyz [M,P,C] or None, MeanVFE features [M,C]) of cylindrical occ voxels."""
+    lib = _lib.load()
+    voxels = voxels.to(torch.float32).contiguous()
+    nump = voxel_num_points.to(torch.int32).contiguous()
+    m, P, C = voxels.shape
+    vabs = torch.empty_like(voxels) if want_abs else None
+    mean = torch.empty((m, C), dtype=torch.float32, device=voxels.device)
+    _lib.check(lib.btc_occ_abs_mean_vfe(_ptr(voxels), P, C, _ptr(nump), m, None, _ptr(vabs), _ptr(mean),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "btc_occ_abs_mean_vfe")
+    return vabs, mean
+
+
+class BtcHotPath(nn.Module):
+    """occ net (targets -> backbone -> head) -> pseudo-point injection -> det backbone -> BEV features."""
+
+    def __init__(self, occ_backbone=None, occ_head=None, det_backbone=None, occ_voxel_size=S.OCC_VOXEL_SIZE,
+                 occ_range=S.OCC_RANGE, det_voxel_size=S.DET_VOXEL_SIZE, det_range=S.KITTI_RANGE,
+                 support_sphere_range=(2.24, -40.6944, -16.5953125, 70.72, 40.6944, 4.0, 0.4203125), dist_kern=(5, 9, 5), half_x=True,
+                 empt_sur_thresh=1, occ_thresh=0.3, max_occ_points=(2048, 40000), num_class=1, box_weight=0.2,
+                 loss_weights=None):
+        super().__init__()
+        self.occ_backbone = occ_backbone if occ_backbone is not None else backbones.OccBackbone(4)
+        self.occ_head = occ_head if occ_head is not None else backbones.OccHead(32)
+        self.det_backbone = det_backbone if det_backbone is not None else backbones.DetBackboneOcc(6, 4)
+        self.occ_voxel_size, self.occ_range = list(occ_voxel_size), list(occ_range)
+        self.det_voxel_size, self.det_range = list(det_voxel_size), list(det_range)
+        self.det_grid = ops.voxel_grid_size(det_voxel_size, det_range)
+        self.geom = ops.occ_geometry_arrays(occ_voxel_size, occ_range, list(support_sphere_range), list(dist_kern), half_x,
+                                            empt_sur_thresh, det_range)
+        self.occ_thresh, self.max_occ_points = float(occ_thresh), tuple(max_occ_points)
+        self.num_class, self.box_weight, self.loss_weights = num_class, box_weight, loss_weights
+
+    def forward(self, bd):
+        gf, gi = self.geom
+        B = int(bd["batch_size"])
+        rot = bd.get("rot_z")
+        # 1 occupancy / occlusion training targets (also needed at inference: the head's probabilities are masked)
+        tg = ops.occ_training_targets(bd["voxels"], bd["voxel_coords"], bd["voxel_num_points"], B, bd["gt_boxes"],
+                                      bd["gt_boxes_num"], gf, gi, box_mirr_flag=bd.get("box_mirr_flag"),
+                                      bm_points=bd.get("bm_points"), rot_z=rot, num_class=self.num_class,
+                                      weights=self.loss_weights, box_weight=self.box_weight)
+        bd.update(tg)
+        # 2 USE_ABSXYZ + MeanVFE
+        bd["voxels"], bd["voxel_features"] = occ_abs_mean_vfe(bd["voxels"], bd["voxel_num_points"])
+        # 3, 4 occupancy backbone and head
+        bd = self.occ_head(self.occ_backbone(bd))
+        # 5 pseudo points + sorted re-voxelisation on the detection grid
+        max_pts = self.max_occ_points[0] if bd.get("is_train", self.training) else self.max_occ_points[1]
+        res = ops.pass_occ_vox(bd["batch_pred_occ_prob"].detach(), bd["pred_sem_residuals"].detach(), bd["det_voxels"],
+                               bd["det_voxel_num_points"], bd["det_voxel_coords"], B, self.occ_thresh, max_pts,
+                               self.occ_voxel_size, self.occ_range[:3], self.det_voxel_size, self.det_range, self.det_grid,
+                               rot_z=rot)
+        if res is None:    # no occupancy cell above threshold: raw det voxels with two zero code channels (pass_occ_vox.py:50-55)
+            v = bd["det_voxels"]
+            voxels = torch.cat((v, torch.zeros_like(v[..., :2])), dim=-1)
+            counts, coords = bd["det_voxel_num_points"], bd["det_voxel_coords"]
+            bd["added_occ_xyz"] = torch.zeros((1, 3), device=v.device)
+        else:
+            voxels, counts, coords, sel = res
+            bd["added_occ_xyz"], bd["added_occ_b_ind"] = sel["occ_xyz"], sel["occ_coords"][:, 0].long()
+            bd["occ_pnts"] = torch.cat([sel["occ_xyz"], sel["occ_probs"].unsqueeze(-1)], dim=-1)
+        bd["voxels"], bd["voxel_num_points"], bd["voxel_coords"] = voxels, counts, coords
+        # 6 OccVFE
+        bd["voxel_features"], bd["occ_voxel_features"] = ops.occ_vfe(voxels, counts, 4)
+        # 7 detection backbone
+        bd = self.det_backbone(bd)
+        # 8 HeightCompression
+        d = bd["encoded_spconv_tensor"].dense()
+        n, c, dd, h, w = d.shape
+        bd["spatial_features"] = d.view(n, c * dd, h, w)
+        bd["spatial_features_stride"] = bd["encoded_spconv_tensor_stride"]
+        return bd
+
+
+def synthetic_batch(seeds, n_points=20000, device="cuda", with_rot=False, mode="train"):
+    """A config-3 batch_dict from seeded lidar_like scenes with everything produced on the device: a2 + cylindrical
+    occupancy voxels, detection voxels, gt boxes (the generator's), mirror flags."""
+    import numpy as np
+    scenes, boxes = [], []
+    for s in seeds:
+        p, bx = S.lidar_like(n_points, seed=s, return_boxes=True)
+        scenes.append(p)
+        boxes.append(bx[:12])
+    pts, offs = S.batch_points(scenes)
+    pts_d, offs_d = torch.from_numpy(pts).to(device), torch.from_numpy(offs).to(device)
+    occ, det = ops.voxelize_occ_and_det(pts_d, offs_d, S.OCC_VOXEL_SIZE, S.OCC_RANGE, S.OCC_MAX_POINTS, S.OCC_MAX_VOXELS[mode],
+                                        S.DET_VOXEL_SIZE, S.KITTI_RANGE, S.DET_MAX_POINTS, S.DET_MAX_VOXELS[mode],
+                                        want_mean=False)
+    m_occ, m_det = int(occ[4][-1].item()), int(det[4][-1].item())
+    gt = torch.from_numpy(np.stack(boxes).astype(np.float32)).to(device)
+    bd = {"voxels": occ[0][:m_occ], "voxel_coords": occ[1][:m_occ], "voxel_num_points": occ[2][:m_occ],
+          "det_voxels": det[0][:m_det], "det_voxel_coords": det[1][:m_det], "det_voxel_num_points": det[2][:m_det],
+          "gt_boxes": gt, "gt_boxes_num": [gt.shape[1]] * len(seeds), "box_mirr_flag": torch.ones(gt.shape[:2], device=device),
+          "batch_size": len(seeds), "is_train": mode == "train",
+          "points": torch.cat([torch.repeat_interleave(torch.arange(len(seeds), device=device),
+                                                       torch.from_numpy(np.diff(offs)).to(device)).float().unsqueeze(1), pts_d], 1)}
+    if with_rot:
+        bd["rot_z"] = torch.tensor([7.5, -11.25, 3.0, -2.0][:len(seeds)], device=device)
+    return bd

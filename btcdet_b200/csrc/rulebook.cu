@@ -102,25 +102,64 @@ subm_table_sym_kernel(const int4* __restrict__ coords, int n_cap, const int* __r
     const int n = live_count(n_cap, n_dev);
     const int K = g.K, half = K >> 1;
     const int sub = threadIdx.x >> 4, k = threadIdx.x & 15;
-    for (int i = (blockIdx.x * kSubmSites + threadIdx.y) * 2 + sub; i < n; i += gridDim.x * kSubmSites * 2) {
-        const int4 c = __ldg(coords + i);
-        if (k == 0) nbr_out[(int64_t)i * K + half] = i;          // centre tap: the site itself
-        if (k < half) {
-            const int tap = s_tap[k];
-            const int z = c.y + (tap & 255) - 64, y = c.z + ((tap >> 8) & 255) - 64, x = c.w + ((tap >> 16) & 255) - 64;
-            if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w) {
-                const int64_t key = flat_key(c.x, z, y, x, g.in);
-                int j = -1;
-                if (HASH) {
-                    j = hash_lookup(keys, vals, hmask, key);
-                } else {
-                    int r = index_lookup(index, key);
-                    if (r >= 0 && r < n_cap) j = perm ? __ldg(perm + r) : r;   // rank >= capacity: site not materialised
+    const int tap = k < half ? s_tap[k] : 0;
+    const int dz = (tap & 255) - 64, dy = ((tap >> 8) & 255) - 64, dx = ((tap >> 16) & 255) - 64;
+    // kSubmUnroll sites per thread and trip: their coordinate loads, then their index / hash probes, are issued together
+    // (one probe whose result is used right away costs a full L2 round trip; the kernel is bound by exactly that)
+    constexpr int U = 4;
+    const int stride = gridDim.x * kSubmSites * 2;
+    for (int i0 = (blockIdx.x * kSubmSites + threadIdx.y) * 2 + sub; i0 < n; i0 += stride * U) {
+        int4 c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * stride;
+            c[u] = i < n ? __ldg(coords + i) : make_int4(-1, -1, -1, -1);
+        }
+        int64_t key[U];
+        bool ok[U];
+        uint2 e[U];
+        uint32_t h[U];
+        long long hk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * stride;
+            const int z = c[u].y + dz, y = c[u].z + dy, x = c[u].w + dx;
+            ok[u] = i < n && k < half && (unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h &&
+                    (unsigned)x < (unsigned)g.in.w;
+            key[u] = ok[u] ? flat_key(c[u].x, z, y, x, g.in) : 0;
+            if (HASH) {
+                h[u] = hash_key64((unsigned long long)key[u]) & hmask;
+                hk[u] = ok[u] ? __ldg(keys + h[u]) : -1LL;
+            } else {
+                e[u] = ok[u] ? __ldg(index + (key[u] >> 5)) : make_uint2(0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * stride;
+            if (i >= n) continue;
+            if (k == 0) nbr_out[(int64_t)i * K + half] = i;          // centre tap: the site itself
+            if (!ok[u]) continue;
+            int j = -1;
+            if (HASH) {
+                long long kk = hk[u];
+                uint32_t hh = h[u];
+                while (true) {                                       // linear probing (first slot already fetched)
+                    if (kk == key[u]) { j = __ldg(vals + hh); break; }
+                    if (kk == -1LL) break;
+                    hh = (hh + 1) & hmask;
+                    kk = __ldg(keys + hh);
                 }
-                if (j >= 0 && j < n) {
-                    nbr_out[(int64_t)i * K + k] = j;
-                    nbr_out[(int64_t)j * K + (K - 1 - k)] = i;
+            } else {
+                const unsigned bit = 1u << (unsigned)(key[u] & 31);
+                if (e[u].x & bit) {
+                    const int r = (int)(e[u].y + __popc(e[u].x & (bit - 1u)));
+                    if (r < n_cap) j = perm ? __ldg(perm + r) : r;   // rank >= capacity: site not materialised
                 }
+            }
+            if (j >= 0 && j < n) {
+                nbr_out[(int64_t)i * K + k] = j;
+                nbr_out[(int64_t)j * K + (K - 1 - k)] = i;
             }
         }
     }
@@ -230,6 +269,174 @@ __global__ void conv_tables_kernel(const int4* __restrict__ coords, int n_cap, c
                     if (nbr_in) nbr_in[(int64_t)i * K + k] = o;
                     if (nbr_out && o >= 0) nbr_out[(int64_t)o * K + k] = i;
                 }
+    }
+}
+
+// ---- strided / transposed, sparse two-level build (round 2) -------------------------------------------------------
+// The dense build above streams the whole rank bitmap of the output grid four times (zero, popcount, rank write, decode:
+// 47 MB each at batch 16 on the [21,800,704] level, 92 MB on the stress grid) to compact ~2e5 sites, in 8 dependent
+// launches.  Here a SUMMARY bitmap (one bit per 32-cell index word, 1/1024 of the grid in bits) records which words were
+// touched, so that ONE kernel — a single-pass scan with decoupled look-back over the summary words — ranks the touched
+// words, writes their ranks and decodes the output coordinates, touching only occupied words; both bitmaps are cleared
+// sparsely from the coordinate list after their last reader (btc_index_clear_sparse) instead of a memset per step.
+// Bytes moved per build: ~16 B per input tap + the summary (0.7 MB at batch 16) + 24 B per output site.
+__global__ void conv_mark2_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
+                                  unsigned* __restrict__ out_index_words, unsigned* __restrict__ summary) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        int kz_l[kMaxAxisTaps], oz_l[kMaxAxisTaps], ky_l[kMaxAxisTaps], oy_l[kMaxAxisTaps], kx_l[kMaxAxisTaps], ox_l[kMaxAxisTaps];
+        const int nz = axis_taps(c.y, g.k[0], g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, kz_l, oz_l);
+        const int ny = axis_taps(c.z, g.k[1], g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, ky_l, oy_l);
+        const int nx = axis_taps(c.w, g.k[2], g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, kx_l, ox_l);
+        for (int a = 0; a < nz; ++a)
+            for (int b = 0; b < ny; ++b)
+                for (int d = 0; d < nx; ++d) {
+                    const int64_t key = flat_key(c.x, oz_l[a], oy_l[b], ox_l[d], g.out);
+                    // two fire-and-forget reductions (RED.OR, results unused): the thread never waits for the L2
+                    const int64_t w = key >> 5;
+                    atomicOr(out_index_words + 2 * w, 1u << (unsigned)(key & 31));
+                    atomicOr(summary + (w >> 5), 1u << (unsigned)(w & 31));
+                }
+    }
+}
+
+// Single-pass ranking scan over the summary words (decoupled look-back).  A tile is kSrWarps x kSrWordsPerWarp = 256
+// summary words (8 Ki index words = 256 Ki cells), handed out by an atomic counter so that a tile only ever waits on
+// tiles that already run; tiles are chained through `status` (high word: 1 = tile aggregate, 2 = inclusive prefix) with a
+// warp-wide look-back (32 predecessors per round trip).  A warp owns 16 consecutive summary words; lane l owns index
+// word l of each: the (at most 16) loads of a lane are independent and issued together — only flagged words are read —
+// and a word's rank (occupied cells before it) is written in place.  The output coordinates are written by
+// conv_tables2 (which knows them without decoding a flat key).
+constexpr int kSrWarps = 16;
+constexpr int kSrWordsPerWarp = 16;
+constexpr int kSeThreads = kSrWarps * 32;
+constexpr int kSeTile = kSrWarps * kSrWordsPerWarp;      // summary words per tile
+__global__ void __launch_bounds__(kSeThreads)
+scan_rank_kernel(uint2* __restrict__ index, const unsigned* __restrict__ summary, int n_sum,
+                 unsigned long long* __restrict__ status, int* __restrict__ tile_ctr, int* __restrict__ total) {
+    __shared__ int s_wtot[kSrWarps];
+    __shared__ int s_tile, s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_ctr, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sw0 = tile * kSeTile + warp * kSrWordsPerWarp;            // first summary word of this warp
+    const unsigned mine = (lane < kSrWordsPerWarp && sw0 + lane < n_sum) ? __ldg(summary + sw0 + lane) : 0u;
+    int pc[kSrWordsPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSrWordsPerWarp; ++j) {                         // independent loads, all in flight together
+        const unsigned sw = __shfl_sync(0xffffffffu, mine, j);
+        pc[j] = ((sw >> lane) & 1u) ? __popc(index[(int64_t)(sw0 + j) * 32 + lane].x) : 0;
+    }
+    int ex[kSrWordsPerWarp];
+    int running = 0;
+#pragma unroll
+    for (int j = 0; j < kSrWordsPerWarp; ++j) {                         // exclusive ranks in (summary word, lane) order
+        const int inc = warp_inclusive_scan(pc[j]);
+        ex[j] = running + inc - pc[j];
+        running += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_wtot[warp] = running;
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < kSrWarps ? s_wtot[lane] : 0;
+        const int inc = warp_inclusive_scan(v);
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane < kSrWarps) s_wtot[lane] = inc - v;                    // exclusive warp bases
+        volatile unsigned long long* st = status;
+        int base = 0;
+        if (tile > 0) {
+            if (lane == 0) st[tile] = (1ull << 32) | (unsigned)tot;      // this tile's aggregate
+            int p_hi = tile - 1;                                          // nearest predecessor not yet accounted for
+            while (true) {
+                const int p = p_hi - lane;
+                unsigned long long pv = (2ull << 32);                     // before tile 0: inclusive prefix 0
+                if (p >= 0) {
+                    do { pv = st[p]; } while ((pv >> 32) == 0ull);        // predecessors run already: bounded wait
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (pv >> 32) == 2ull);
+                const int first = incl ? __ffs(incl) - 1 : 31;            // nearest predecessor with an inclusive prefix
+                int c = lane <= first ? (int)(unsigned)pv : 0;
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                base += c;
+                if (incl) break;
+                p_hi -= 32;
+            }
+        }
+        if (lane == 0) {
+            st[tile] = (2ull << 32) | (unsigned)(base + tot);
+            s_base = base;
+            if (tile == (int)gridDim.x - 1 && total) *total = base + tot;
+        }
+    }
+    __syncthreads();
+    const int row0 = s_base + s_wtot[warp];
+#pragma unroll
+    for (int j = 0; j < kSrWordsPerWarp; ++j) {
+        const unsigned sw = __shfl_sync(0xffffffffu, mine, j);
+        if ((sw >> lane) & 1u) index[(int64_t)(sw0 + j) * 32 + lane].y = (unsigned)(row0 + ex[j]);
+    }
+}
+
+// conv_tables + the output coordinate rows: every (input, tap) pair knows its output cell (b, oz, oy, ox) and, through
+// the rank bitmap, its row — so the coordinate list needs no decode pass over the bitmap (pairs that share an output
+// store the same 16 bytes).
+__global__ void conv_tables2_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
+                                    const uint2* __restrict__ out_index, int out_cap, int* __restrict__ nbr_out,
+                                    int* __restrict__ nbr_in, int4* __restrict__ out_coords) {
+    const int n = live_count(n_cap, n_dev);
+    const int K = g.K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        if (nbr_in)
+            for (int k = 0; k < K; ++k) nbr_in[(int64_t)i * K + k] = -1;
+        int kz_l[kMaxAxisTaps], oz_l[kMaxAxisTaps], ky_l[kMaxAxisTaps], oy_l[kMaxAxisTaps], kx_l[kMaxAxisTaps], ox_l[kMaxAxisTaps];
+        const int nz = axis_taps(c.y, g.k[0], g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, kz_l, oz_l);
+        const int ny = axis_taps(c.z, g.k[1], g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, ky_l, oy_l);
+        const int nx = axis_taps(c.w, g.k[2], g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, kx_l, ox_l);
+        // taps in batches of 8 (all of a k3 s2 site's): the rank-bitmap loads of a batch are issued together, then used
+        const int taps = nz * ny * nx;
+        for (int t0 = 0; t0 < taps; t0 += 8) {
+            uint2 e[8];
+            int64_t key[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int t = t0 + j < taps ? t0 + j : t0;
+                const int d = t % nx, b = (t / nx) % ny, a = t / (nx * ny);
+                key[j] = flat_key(c.x, oz_l[a], oy_l[b], ox_l[d], g.out);
+                e[j] = __ldg(out_index + (key[j] >> 5));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (t0 + j >= taps) break;
+                const int t = t0 + j;
+                const int d = t % nx, b = (t / nx) % ny, a = t / (nx * ny);
+                const int k = (kz_l[a] * g.k[1] + ky_l[b]) * g.k[2] + kx_l[d];
+                const unsigned bit = 1u << (unsigned)(key[j] & 31);
+                int o = (e[j].x & bit) ? (int)(e[j].y + __popc(e[j].x & (bit - 1u))) : -1;
+                if (o >= out_cap) o = -1;
+                if (nbr_in) nbr_in[(int64_t)i * K + k] = o;
+                if (o >= 0) {
+                    if (nbr_out) nbr_out[(int64_t)o * K + k] = i;
+                    if (out_coords) out_coords[o] = make_int4(c.x, oz_l[a], oy_l[b], ox_l[d]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void index_clear2_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, Shape3 shape,
+                                    int batch, uint2* __restrict__ index, unsigned* __restrict__ summary) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)shape.d || (unsigned)c.z >= (unsigned)shape.h ||
+            (unsigned)c.w >= (unsigned)shape.w)
+            continue;
+        const int64_t w = flat_key(c.x, c.y, c.z, c.w, shape) >> 5;
+        index[w] = make_uint2(0u, 0u);
+        summary[w >> 5] = 0u;
     }
 }
 
@@ -408,7 +615,7 @@ int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch,
     cudaStream_t st = (cudaStream_t)stream;
     if ((g.K & 1) && g.K / 2 <= 16) {
         fill_table_kernel<<<grid_for((int64_t)n_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, n_cap, n_dev, g.K);
-        subm_table_sym_kernel<false><<<grid_for((n_cap + 2 * kSubmSites - 1) / (2 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
+        subm_table_sym_kernel<false><<<grid_for((n_cap + 8 * kSubmSites - 1) / (8 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
             (const int4*)coords, n_cap, n_dev, g, (const uint2*)index, perm, nullptr, nullptr, 0u, nbr_out);
     } else {
         subm_table_kernel<false><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, st>>>(
@@ -434,7 +641,7 @@ int btc_rulebook_subm_hash(const int* coords, int n_cap, const int* n_dev, int b
     cudaStream_t st = (cudaStream_t)stream;
     if ((g.K & 1) && g.K / 2 <= 16) {
         fill_table_kernel<<<grid_for((int64_t)n_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, n_cap, n_dev, g.K);
-        subm_table_sym_kernel<true><<<grid_for((n_cap + 2 * kSubmSites - 1) / (2 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
+        subm_table_sym_kernel<true><<<grid_for((n_cap + 8 * kSubmSites - 1) / (8 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
             (const int4*)coords, n_cap, n_dev, g, nullptr, nullptr, (const long long*)keys, vals, (uint32_t)(n_slots - 1),
             nbr_out);
     } else {
@@ -480,6 +687,67 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev, i
         conv_tables_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
                                                             (const uint2*)out_index, out_cap, nbr_out, nbr_in);
     BTC_CHECK_LAUNCH("conv rulebook");
+    return BTC_OK;
+}
+
+int64_t btc_index_summary_words(int64_t n_entries) { return (n_entries + 31) / 32; }
+
+int64_t btc_rulebook_conv_sparse_workspace_bytes(int64_t n_entries) {
+    const int64_t n_sum = (n_entries + 31) / 32;
+    const int64_t tiles = (n_sum + kSeTile - 1) / kSeTile;
+    return align_up(16 + tiles * 8, 256);
+}
+
+int btc_rulebook_conv_sparse(const int* coords_in, int n_in_cap, const int* n_in_dev, int batch, const int* in_shape,
+                             const int* out_shape, const int* ksize, const int* stride, const int* padding,
+                             const int* dilation, int transposed, uint64_t* out_index, int64_t out_entries,
+                             uint32_t* summary, int* out_coords, int out_cap, int* n_out, int* nbr_out, int* nbr_in,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!in_shape || !out_shape || !ksize || !out_index || !summary || !n_out || !workspace)
+        return badarg("btc_rulebook_conv_sparse: null argument");
+    if (n_in_cap > 0 && (!coords_in || !out_coords)) return badarg("btc_rulebook_conv_sparse: null coordinates");
+    if (out_entries != btc_index_entries(batch, out_shape)) return badarg("btc_rulebook_conv_sparse: out_entries mismatch");
+    if (workspace_bytes < btc_rulebook_conv_sparse_workspace_bytes(out_entries))
+        return badarg("btc_rulebook_conv_sparse: workspace too small");
+    ConvGeom g;
+    if (make_geom(g, batch, in_shape, out_shape, ksize, stride, padding, dilation, transposed))
+        return badarg("btc_rulebook_conv_sparse: bad geometry");
+    if (g.k[0] > kMaxAxisTaps || g.k[1] > kMaxAxisTaps || g.k[2] > kMaxAxisTaps)
+        return badarg("btc_rulebook_conv_sparse: kernel extent above 8 per axis");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_sum = (out_entries + 31) / 32;
+    const int tiles = (int)((n_sum + kSeTile - 1) / kSeTile);
+    int* tile_ctr = (int*)workspace;
+    unsigned long long* status = (unsigned long long*)((char*)workspace + 16);
+    BTC_CUDA(cudaMemsetAsync(workspace, 0, 16 + (size_t)tiles * 8, st), "conv_sparse memset");
+    const int64_t work = (int64_t)(n_in_cap > 0 ? n_in_cap : 1);
+    if (n_in_cap > 0) {
+        conv_mark2_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+                                                           (unsigned*)out_index, summary);
+        BTC_CHECK_LAUNCH("conv_mark2");
+    }
+    scan_rank_kernel<<<tiles, kSeThreads, 0, st>>>((uint2*)out_index, summary, (int)n_sum, status, tile_ctr, n_out);
+    BTC_CHECK_LAUNCH("scan_rank");
+    if (out_cap > 0 && nbr_out)
+        fill_table_kernel<<<grid_for((int64_t)out_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, out_cap, n_out, g.K);
+    if (n_in_cap > 0)
+        conv_tables2_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+                                                             (const uint2*)out_index, out_cap, nbr_out, nbr_in,
+                                                             (int4*)out_coords);
+    BTC_CHECK_LAUNCH("conv rulebook (sparse)");
+    return BTC_OK;
+}
+
+int btc_index_clear_sparse(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, uint64_t* index,
+                           int64_t n_entries, uint32_t* summary, void* stream) {
+    if (!index || !shape || !summary) return badarg("btc_index_clear_sparse: null argument");
+    if (n_entries != btc_index_entries(batch, shape)) return badarg("btc_index_clear_sparse: n_entries mismatch");
+    if (n_cap <= 0) return BTC_OK;
+    if (!coords) return badarg("btc_index_clear_sparse: null coordinates");
+    Shape3 s{shape[0], shape[1], shape[2]};
+    index_clear2_kernel<<<grid_for(n_cap, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, s, batch,
+                                                                              (uint2*)index, summary);
+    BTC_CHECK_LAUNCH("index_clear2");
     return BTC_OK;
 }
 

@@ -840,24 +840,73 @@ __global__ void __launch_bounds__(128) tile_mask_kernel(const int* __restrict__ 
 
 // tile_order: the live tiles sorted by descending number of active offsets (counting sort in one CTA; the order inside
 // a cost class is unspecified — it only decides which CTA runs which tile, never a result).
-__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned long long* __restrict__ tile_mask, int n_cap,
-                                                          const int* __restrict__ n_dev, int* __restrict__ tile_order) {
-    __shared__ int s_cnt[65], s_start[65];
-    const int n = live_count(n_cap, n_dev);
-    const int tiles = (n + TC_BM - 1) / TC_BM;
+__device__ __forceinline__ void tile_order_block(const unsigned long long* __restrict__ tile_mask, int tiles,
+                                                 int* __restrict__ tile_order, int* s_cnt, int* s_start) {
     if (threadIdx.x < 65) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += 1024) atomicAdd(&s_cnt[__popcll(tile_mask[t])], 1);
+    const volatile unsigned long long* tm = tile_mask;     // (tile_meta_kernel: written by other CTAs of the same launch)
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(&s_cnt[__popcll(tm[t])], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int c = 64; c >= 0; --c) { s_start[c] = acc; acc += s_cnt[c]; }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += 1024) {
-        const int c = __popcll(tile_mask[t]);
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const int c = __popcll(tm[t]);
         tile_order[atomicAdd(&s_start[c], 1)] = t;
     }
+}
+
+__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned long long* __restrict__ tile_mask, int n_cap,
+                                                          const int* __restrict__ n_dev, int* __restrict__ tile_order) {
+    __shared__ int s_cnt[65], s_start[65];
+    const int n = live_count(n_cap, n_dev);
+    tile_order_block(tile_mask, (n + TC_BM - 1) / TC_BM, tile_order, s_cnt, s_start);
+}
+
+// Masks and order in ONE launch: every CTA computes the mask of its tile; the CTA that finishes last (atomic ticket,
+// no CTA ever waits for another) sorts the tiles.  `ticket` is a zeroed device int that the kernel leaves at zero.
+__global__ void __launch_bounds__(128) tile_meta_kernel(const int* __restrict__ table, int n_cap, const int* __restrict__ n_dev,
+                                                        int K, unsigned long long* __restrict__ tile_mask,
+                                                        int* __restrict__ tile_order, int* __restrict__ ticket) {
+    __shared__ unsigned long long s_m[4];
+    __shared__ int s_cnt[65], s_start[65];
+    __shared__ int s_last;
+    const int n = live_count(n_cap, n_dev);
+    const int row0 = blockIdx.x * TC_BM;
+    unsigned long long m = 0;
+    if (row0 < n) {
+        const int rows = n - row0 < TC_BM ? n - row0 : TC_BM;
+        const int total = rows * K;
+        const int* src = table + (int64_t)row0 * K;
+        // coalesced sweep of the tile's [rows x K] block in batches of 16 independent loads per thread (a load whose
+        // value is tested right away costs a full L2 round trip each: 27 in a row made this kernel 25 us)
+        for (int i0 = threadIdx.x; i0 < total; i0 += 128 * 16) {
+            int v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = i0 + 128 * j < total ? __ldg(src + i0 + 128 * j) : -1;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (v[j] >= 0) m |= 1ull << ((i0 + 128 * j) % K);
+        }
+    }
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)m), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tile_mask[blockIdx.x] = s_m[0] | s_m[1] | s_m[2] | s_m[3];
+        __threadfence();                                        // the mask is visible before the ticket is taken
+        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || !tile_order) {
+        if (s_last && threadIdx.x == 0) *ticket = 0;
+        return;
+    }
+    __threadfence();
+    tile_order_block((const unsigned long long*)tile_mask, (n + TC_BM - 1) / TC_BM, tile_order, s_cnt, s_start);
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter at zero again (see
@@ -876,6 +925,22 @@ static int* next_tile_counter() {
     if (!base[dev]) {
         void* p = nullptr;
         if (cudaGetSymbolAddress(&p, g_tc_tile_ctr) != cudaSuccess) return nullptr;
+        base[dev] = (int*)p;
+    }
+    return base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
+}
+
+// Tickets of tile_meta_kernel (zero at module load, every launch leaves its ticket at zero): rotating slots like the
+// tile counters, so launches that overlap on different streams do not share one.
+__device__ int g_tile_meta_ticket[kTcCtrSlots];
+static int* tile_meta_ticket() {
+    static int* base[64] = {nullptr};
+    static std::atomic<unsigned> next{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!base[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_tile_meta_ticket) != cudaSuccess) return nullptr;
         base[dev] = (int*)p;
     }
     return base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
@@ -1106,12 +1171,18 @@ int btc_rulebook_tile_meta(const int* nbr_out, int n_out_cap, const int* n_out_d
     if (!nbr_out || !tile_mask) return badarg("btc_rulebook_tile_meta: null argument");
     const int tiles = (n_out_cap + TC_BM - 1) / TC_BM;
     cudaStream_t st = (cudaStream_t)stream;
-    tile_mask_kernel<<<tiles, 128, 0, st>>>(nbr_out, n_out_cap, n_out_dev, K, (unsigned long long*)tile_mask);
-    BTC_CHECK_LAUNCH("tile_mask");
-    if (tile_order) {
-        tile_order_kernel<<<1, 1024, 0, st>>>((const unsigned long long*)tile_mask, n_out_cap, n_out_dev, tile_order);
-        BTC_CHECK_LAUNCH("tile_order");
-    }
+    int* ticket = tile_meta_ticket();
+    if (!ticket) return set_error(BTC_E_CUDA, "btc_rulebook_tile_meta: ticket symbol not available", cudaGetLastError());
+    tile_meta_kernel<<<tiles, 128, 0, st>>>(nbr_out, n_out_cap, n_out_dev, K, (unsigned long long*)tile_mask, tile_order, ticket);
+    BTC_CHECK_LAUNCH("tile_meta");
+    return BTC_OK;
+}
+
+int btc_rulebook_tile_order(const uint64_t* tile_mask, int n_out_cap, const int* n_out_dev, int* tile_order, void* stream) {
+    if (n_out_cap <= 0) return BTC_OK;
+    if (!tile_mask || !tile_order) return badarg("btc_rulebook_tile_order: null argument");
+    tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const unsigned long long*)tile_mask, n_out_cap, n_out_dev, tile_order);
+    BTC_CHECK_LAUNCH("tile_order");
     return BTC_OK;
 }
 

@@ -32,6 +32,7 @@ class _Level:
     coords: torch.Tensor     # [cap, 4] i32
     n_dev: torch.Tensor      # [1] i32 view
     index: Optional[torch.Tensor] = None   # rank bitmap (int64 entries) — sorted levels
+    summary: Optional[torch.Tensor] = None  # one bit per index word (sparse two-level build / clear)
     perm: Optional[torch.Tensor] = None
     hash_keys: Optional[torch.Tensor] = None   # coordinate hash — the unsorted voxeliser level
     hash_vals: Optional[torch.Tensor] = None
@@ -105,11 +106,16 @@ class BackbonePlan:
             key = conv.indice_key
             rb = self.rulebooks.get(key) if key is not None else None
             if rb is None:
+                want_meta = self.tile_meta and not self.sort_rows and K <= 64 and self.algo != 1 and \
+                    ops.tc_supported(K, conv.in_channels, conv.out_channels)
                 if conv.subm:
                     if cur_lvl.index is None and cur_lvl.hash_keys is None:
                         self._add_index(cur_lvl)
                     nbr = torch.empty((cur_lvl.cap, K), dtype=torch.int32, device=dev)
                     self.steps.append(_Step("subm_rb", (cur_lvl, conv.kernel_size, conv.dilation, nbr)))
+                    if want_meta:
+                        meta = self._new_meta(nbr)
+                        self.steps.append(_Step("tile_meta", (nbr, cur_lvl, meta[0], meta[1])))
                     rb = (nbr, cur_lvl)
                 else:
                     assert not conv.transposed, "planned engine covers the det backbone (no transposed convs)"
@@ -120,9 +126,14 @@ class BackbonePlan:
                     n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
                     out_lvl = _Level(out_shape, cap, torch.empty((cap, 4), dtype=torch.int32, device=dev), n_dev)
                     out_lvl.index = torch.zeros(ops.index_entries(B, out_shape), dtype=torch.int64, device=dev)
+                    out_lvl.summary = torch.zeros(int(self.lib.btc_index_summary_words(out_lvl.index.numel())),
+                                                  dtype=torch.int32, device=dev)
                     nbr = torch.empty((cap, K), dtype=torch.int32, device=dev)
                     self.steps.append(_Step("conv_rb", (cur_lvl, out_lvl, conv.kernel_size, conv.stride, conv.padding,
                                                         conv.dilation, nbr)))
+                    if want_meta:
+                        meta = self._new_meta(nbr)
+                        self.steps.append(_Step("tile_meta", (nbr, out_lvl, meta[0], meta[1])))
                     self.levels.append(out_lvl)
                     self.counts.append((n_dev, cap))
                     rb = (nbr, out_lvl)
@@ -140,14 +151,7 @@ class BackbonePlan:
             if self.algo != 1 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
                 packed = ops.tc_pack_weight(w)
             self.params.append((w, bias, scale, shift, packed))
-            meta = None
-            if packed is not None and self.tile_meta and not self.sort_rows and K <= 64:
-                meta = self._meta.get(id(nbr))
-                if meta is None:
-                    tiles = (nbr.shape[0] + 127) // 128
-                    meta = (torch.zeros(tiles, dtype=torch.int64, device=dev), torch.zeros(tiles, dtype=torch.int32, device=dev))
-                    self._meta[id(nbr)] = meta
-                    self.steps.append(_Step("tile_meta", (nbr, out_lvl, meta[0], meta[1])))
+            meta = self._meta.get(id(nbr)) if packed is not None else None
             rows = None
             if packed is not None and self.sort_rows:
                 rows = self._sorted.get(id(nbr))
@@ -159,6 +163,14 @@ class BackbonePlan:
                                              conv.in_channels, conv.out_channels, packed, rows, meta)))
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
+        # sparse clear of every sorted level's bitmaps right after their last reader (the rulebook that built them or a
+        # sub-manifold rulebook on that level): the next step starts from all-zero bitmaps without a memset of the grid
+        for lvl in self.levels:
+            if lvl.summary is None:
+                continue
+            last = max(i for i, st in enumerate(self.steps)
+                       if (st.kind == "conv_rb" and st.args[1] is lvl) or (st.kind == "subm_rb" and st.args[0] is lvl))
+            self.steps.insert(last + 1, _Step("index_clear", (lvl,)))
         self.graph = None
         # (a high-priority rulebook stream, side_priority=-1, was measured: no effect on the captured step, 1515 us both ways)
         self._side_stream = torch.cuda.Stream(device=dev, priority=side_priority)
@@ -173,6 +185,12 @@ class BackbonePlan:
         lvl.hash_keys = torch.empty(n_slots, dtype=torch.int64, device=self.device)
         lvl.hash_vals = torch.empty(n_slots, dtype=torch.int32, device=self.device)
         self.steps.append(_Step("hash_build", (lvl,)))
+
+    def _new_meta(self, nbr):
+        tiles = (nbr.shape[0] + 127) // 128
+        meta = (torch.zeros(tiles, dtype=torch.int64, device=self.device), torch.zeros(tiles, dtype=torch.int32, device=self.device))
+        self._meta[id(nbr)] = meta
+        return meta
 
     def _workspace(self, nbytes):
         ws = self._ws.get("ws")
@@ -260,19 +278,24 @@ class BackbonePlan:
             return 2 if (K % 2 == 1 and K // 2 <= 16) else 1   # -1 fill + symmetric half-probe kernel
         if s.kind == "conv_rb":
             lin, lout, ksize, stride, pad, dil, nbr = s.args
-            lout.index.zero_()
-            ws = self._workspace(lib.btc_index_workspace_bytes(lout.index.numel()))
-            check(lib.btc_rulebook_conv(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
-                                        int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
-                                        _ptr(lout.index), lout.index.numel(), _ptr(lout.coords), lout.cap,
-                                        _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
-                  "btc_rulebook_conv")
-            return 8
+            # sparse two-level build: both bitmaps are all-zero here (allocation / the previous step's index_clear)
+            ws = self._workspace(lib.btc_rulebook_conv_sparse_workspace_bytes(lout.index.numel()))
+            check(lib.btc_rulebook_conv_sparse(_ptr(lin.coords), lin.cap, _ptr(lin.n_dev), B, int3(lin.shape),
+                                               int3(lout.shape), int3(ksize), int3(stride), int3(pad), int3(dil), 0,
+                                               _ptr(lout.index), lout.index.numel(), _ptr(lout.summary), _ptr(lout.coords),
+                                               lout.cap, _ptr(lout.n_dev), _ptr(nbr), None, _ptr(ws), ws.numel(), st),
+                  "btc_rulebook_conv_sparse")
+            return 4
         if s.kind == "tile_meta":
             nbr, lvl, tmask, torder = s.args
             check(lib.btc_rulebook_tile_meta(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(tmask), _ptr(torder), st),
                   "btc_rulebook_tile_meta")
-            return 2
+            return 1
+        if s.kind == "index_clear":
+            (lvl,) = s.args
+            check(lib.btc_index_clear_sparse(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape), _ptr(lvl.index),
+                                             lvl.index.numel(), _ptr(lvl.summary), st), "btc_index_clear_sparse")
+            return 1
         if s.kind == "sort_rb":
             nbr, lvl, nbr_sorted, out_rows = s.args
             check(lib.btc_rulebook_sort_rows(_ptr(nbr), lvl.cap, _ptr(lvl.n_dev), nbr.shape[1], _ptr(nbr_sorted),
@@ -443,6 +466,8 @@ class BackbonePlan:
                 for lv in self.levels:   # rows past a capacity were never listed, so the sparse clear missed their bits
                     if getattr(lv, "index", None) is not None:
                         lv.index.zero_()
+                    if getattr(lv, "summary", None) is not None:
+                        lv.summary.zero_()
                 raise _lib.BtcError("level capacity exceeded: %d sites > capacity %d — raise level_growth" % (c, l.cap))
         return counts
 

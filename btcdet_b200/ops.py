@@ -208,16 +208,18 @@ def rulebook_conv(coords: torch.Tensor, batch: int, in_shape, ksize, stride=1, p
     cells = batch * out_shape[0] * out_shape[1] * out_shape[2]
     cap = out_cap if out_cap is not None else _out_bound(n_in, ksize, stride, transposed, cells)
     out_index = torch.zeros(out_entries, dtype=torch.int64, device=dev)
+    summary = torch.zeros(int(lib.btc_index_summary_words(out_entries)), dtype=torch.int32, device=dev)
     out_coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     nbr_out = torch.empty((cap, K), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((max(n_in, 1), K), dtype=torch.int32, device=dev)
     n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws_bytes = int(lib.btc_index_workspace_bytes(out_entries))
+    ws_bytes = int(lib.btc_rulebook_conv_sparse_workspace_bytes(out_entries))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.btc_rulebook_conv(_ptr(coords), n_in, None, int(batch), int3(in_shape), int3(out_shape), int3(ksize),
-                                int3(stride), int3(padding), int3(dilation), int(bool(transposed)), _ptr(out_index),
-                                out_entries, _ptr(out_coords), cap, _ptr(n_out_dev), _ptr(nbr_out), _ptr(nbr_in),
-                                _ptr(ws), ws_bytes, _stream()), "btc_rulebook_conv")
+    # sparse two-level build (freshly zeroed bitmaps; the rank bitmap stays populated for sub-manifold layers on this level)
+    check(lib.btc_rulebook_conv_sparse(_ptr(coords), n_in, None, int(batch), int3(in_shape), int3(out_shape), int3(ksize),
+                                       int3(stride), int3(padding), int3(dilation), int(bool(transposed)), _ptr(out_index),
+                                       out_entries, _ptr(summary), _ptr(out_coords), cap, _ptr(n_out_dev), _ptr(nbr_out),
+                                       _ptr(nbr_in), _ptr(ws), ws_bytes, _stream()), "btc_rulebook_conv_sparse")
     n_out = int(n_out_dev.item())  # the one host sync of a new rulebook (exact tensor shapes for torch)
     if n_out > cap:
         raise _lib.BtcError("rulebook capacity exceeded: %d output sites > capacity %d" % (n_out, cap))

@@ -197,6 +197,27 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev,
                       int* nbr_out, int* nbr_in,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Heaviest-first order of the live tiles from their masks (see btc_rulebook_tile_meta): one small launch. */
+int btc_rulebook_tile_order(const uint64_t* tile_mask, int n_out_cap, const int* n_out_dev, int* tile_order, void* stream);
+
+/*
+ * Sparse two-level build of a strided / transposed rulebook (same results as btc_rulebook_conv, bit for bit).
+ * `summary` [btc_index_summary_words(out_entries)] u32 holds one bit per 32-cell word of `out_index`; BOTH bitmaps must
+ * be all-zero on entry and are left populated (out_index is the rank bitmap of the output level, used by sub-manifold
+ * rulebooks on that level).  After the last reader, btc_index_clear_sparse zeroes exactly the touched words from the
+ * level's coordinate list, so no per-step memset of the grid is needed.  The build touches only occupied words:
+ * mark -> one single-pass ranking scan (decoupled look-back over the summary) -> table fill -> tables + coordinates.
+ */
+int64_t btc_index_summary_words(int64_t n_entries);
+int64_t btc_rulebook_conv_sparse_workspace_bytes(int64_t n_entries);
+int btc_rulebook_conv_sparse(const int* coords_in, int n_in_cap, const int* n_in_dev, int batch, const int* in_shape,
+                             const int* out_shape, const int* ksize, const int* stride, const int* padding,
+                             const int* dilation, int transposed, uint64_t* out_index, int64_t out_entries,
+                             uint32_t* summary, int* out_coords, int out_cap, int* n_out, int* nbr_out, int* nbr_in,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+int btc_index_clear_sparse(const int* coords, int n_cap, const int* n_dev, int batch, const int* shape, uint64_t* index,
+                           int64_t n_entries, uint32_t* summary, void* stream);
+
 /* Workspace bytes for btc_rulebook_pairs. */
 int64_t btc_rulebook_pairs_workspace_bytes(int n_in_cap, int K);
 

@@ -1,0 +1,239 @@
+"""Additional measurement legs of bench.py (imported by it; each returns a small dict for the JSON line).
+
+  native_gpu_leg   a GPU re-creation of spconv 1.2.1's Native algorithm: per layer
+                   the rulebook in spconv's pair format with the per-offset counts copied to the HOST (as spconv sizes
+                   its GEMMs), then per kernel offset {index_select gather, torch.mm (cuBLAS SGEMM), index_add_
+                   scatter-add} — 27 x 3 launches per 3x3x3 layer — on the same scenes, same weights, fp32.  The rulebooks
+                   themselves come from this library (spconv's own indice kernels are not available offline), which
+                   favours the baseline.  This is the denominator of the north-star ">= 10x the spconv CUDA backbone".
+  train_leg        BASELINE config 4: fwd + bwd + DDP gradient all-reduce (NCCL) + clip + Adam, 2 scenes per GPU.
+  chain_leg        BASELINE config 3: btcdet_b200.chain.BtcHotPath on 2 scenes (occ targets -> occ backbone -> head ->
+                   injection -> det backbone -> BEV features).
+  stress_leg       BASELINE config 5: 100k-point clouds at voxel 0.025 m; rulebook-build / gather-GEMM bytes per second
+                   against the measured HBM peak.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _events():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def native_gpu_leg(model, scenes, B, dev, steps=3, warmup=1):
+    from btcdet_b200 import ops, synthetic as S
+    model = model.to(dev).eval()
+    pts, offs = S.batch_points(scenes[:B])
+    v, c, n, mean, nv = ops.voxelize(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev), S.DET_VOXEL_SIZE,
+                                     S.KITTI_RANGE, S.DET_MAX_POINTS, S.DET_MAX_VOXELS["train"], want_mean=True)
+    m = int(nv[-1].item())
+    feats0, coords0 = mean[:m].contiguous(), c[:m].contiguous()
+    specs = model.layer_specs()
+    launches = [0]
+
+    def forward():
+        x, coords, shape = feats0, coords0, list(model.sparse_shape)
+        cache = {}
+        launches[0] = 0
+        for conv, bn in specs:
+            K = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
+            ent = cache.get(conv.indice_key)
+            if ent is None:
+                rb = ops.rulebook_subm(coords, B, shape, conv.kernel_size) if conv.subm else \
+                    ops.rulebook_conv(coords, B, shape, conv.kernel_size, conv.stride, conv.padding, conv.dilation)
+                pairs, pair_num = rb.pairs()
+                ent = (rb, pairs.long(), pair_num.cpu().tolist())      # host-synchronised counts, as spconv 1.2.1
+                cache[conv.indice_key] = ent
+            rb, pairs, counts = ent
+            W = conv.weight.reshape(K, conv.in_channels, conv.out_channels)
+            if conv.subm:
+                out = torch.mm(x, W[K // 2])                            # centre offset first (App. A.5)
+                launches[0] += 1
+            else:
+                out = torch.zeros((rb.n_out, conv.out_channels), dtype=torch.float32, device=dev)
+            for k in range(K):
+                nk = counts[k]
+                if nk == 0 or (conv.subm and k == K // 2):
+                    continue
+                buf = x.index_select(0, pairs[0, k, :nk])
+                out.index_add_(0, pairs[1, k, :nk], torch.mm(buf, W[k]))
+                launches[0] += 3
+            if bn is not None:
+                out = torch.relu(bn(out))
+            x, coords, shape = out, rb.out_coords, rb.out_shape
+        return x
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            ref_out = forward()
+        torch.cuda.synchronize()
+        e0, e1 = _events()
+        e0.record()
+        for _ in range(steps):
+            forward()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": round(B / (ms * 1e-3), 2), "unit": "scenes/s", "ms_per_step": round(ms, 3), "scenes_per_step": B,
+            "launches_per_step": launches[0], "rows_out": int(ref_out.shape[0]),
+            "what": "GPU re-creation of spconv-1.2.1 Native: per offset index_select -> torch.mm (cuBLAS SGEMM, fp32) -> "
+                    "index_add_, pair counts read on the host per rulebook; backbone only (voxel features already on the device), "
+                    "rulebooks from this library"}, ref_out
+
+
+class _TrainNet(torch.nn.Module):
+    """VoxelBackBone8x + HeightCompression-style dense() + a 1x1 BEV head standing in for the RPN."""
+
+    def __init__(self):
+        super().__init__()
+        from btcdet_b200 import backbones
+        self.backbone = backbones.VoxelBackBone8x(4)
+        self.head = torch.nn.Conv2d(256, 8, 1)
+
+    def forward(self, feats, coords, batch):
+        out = self.backbone({"voxel_features": feats, "voxel_coords": coords, "batch_size": batch})["encoded_spconv_tensor"]
+        d = out.dense()
+        n, c, dd, h, w = d.shape
+        return self.head(d.view(n, c * dd, h, w))
+
+
+def train_leg(rank, world, dev, steps=10, warmup=4, batch=2):
+    """Runs on EVERY rank (DDP all-reduce over NCCL when world > 1); returns the dict on every rank."""
+    from btcdet_b200 import ops, synthetic as S
+    torch.manual_seed(0)
+    net = _TrainNet().to(dev).train()
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index]) if world > 1 else net
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    batches = []
+    for i in range(3):
+        sc = [S.lidar_like(20000, seed=7000 + 100 * rank + 10 * i + b) for b in range(batch)]
+        pts, offs = S.batch_points(sc)
+        batches.append((torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)))
+
+    def step(i):
+        pts, offs = batches[i % len(batches)]
+        v, c, n, mean, nv = ops.voxelize(pts, offs, S.DET_VOXEL_SIZE, S.KITTI_RANGE, 5, 16000, want_mean=True)
+        m = int(nv[-1].item())
+        loss = model(mean[:m], c[:m], batch).square().mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = _events()
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    n_param = sum(p.numel() for p in net.parameters())
+    return {"value": round(world * batch * steps / (ms * 1e-3), 2), "unit": "scenes/s", "ms_per_step": round(ms / steps, 3),
+            "scenes_per_gpu": batch, "steps": steps, "allreduce_bytes_per_step": 4 * n_param if world > 1 else 0,
+            "loss": float(loss.detach()),
+            "what": "config 4 shape: fwd + bwd (CUDA dX / dW / db kernels) + DDP bucketed NCCL all-reduce overlapped with "
+                    "backward + grad clip + Adam, VoxelBackBone8x + BEV 1x1 head, train-mode BatchNorm, eager spconv shim"}
+
+
+def chain_leg(dev, steps=5, warmup=2, batch=2):
+    from btcdet_b200 import backbones, chain
+    torch.manual_seed(0)
+    model = chain.BtcHotPath()
+    backbones.randomize_bn_(model, 0)
+    with torch.no_grad():
+        model.occ_head.conv_cls[0].bias.copy_(torch.tensor([1.2, -1.2]))
+    model = model.to(dev).eval()
+    bds = [chain.synthetic_batch([900 + 10 * i + b for b in range(batch)], n_points=20000, device=dev, with_rot=True, mode="test")
+           for i in range(2)]
+
+    def run(i):
+        bd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in bds[i % len(bds)].items()}
+        with torch.no_grad():
+            return model(bd)
+
+    for i in range(warmup):
+        out = run(i)
+    torch.cuda.synchronize()
+    e0, e1 = _events()
+    e0.record()
+    for i in range(steps):
+        out = run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": round(batch / (ms * 1e-3), 2), "unit": "scenes/s", "ms_per_step": round(ms, 3), "scenes_per_step": batch,
+            "occ_sites": int(out["general_cls_loss_mask"].sum()), "det_voxels": int(out["voxel_coords"].shape[0]),
+            "bev_rows": int(out["encoded_spconv_tensor"].features.shape[0]),
+            "what": "config 3 shape: occ targets -> MeanVFE -> VoxelBackBoneDeconv -> OccHead -> PassOccVox -> OccVFE -> "
+                    "VoxelBackBone8xOcc -> HeightCompression on 2 scenes of 20k points (eval mode, random-init weights, eager "
+                    "spconv shim: one host read per new rulebook)"}
+
+
+def stress_leg(dev, peak_gbs, reps=5):
+    """Config 5: 100k-point dense clouds, voxel [0.025, 0.025, 0.05] (721 M cells per scene): voxelise + level-1 SubM rulebook +
+    strided rulebook + one 16->16 SubM conv; algorithmic bytes per second against the measured HBM peak."""
+    from btcdet_b200 import ops, synthetic as S
+    vs, B = [0.025, 0.025, 0.05], 2
+    scenes = [S.lidar_like(100000, seed=50 + b, az_density=4.0) for b in range(B)]
+    pts, offs = S.batch_points(scenes)
+    p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
+    grid = ops.voxel_grid_size(vs, S.KITTI_RANGE)
+    shape = [grid[2] + 1, grid[1], grid[0]]
+
+    def timed(fn):
+        out = fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            e0, e1 = _events()
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms)), out
+
+    ms_v, vox = timed(lambda: ops.voxelize(p, o, vs, S.KITTI_RANGE, 5, 150000, want_mean=True))
+    m = int(vox[4][-1].item())
+    coords, feats = vox[1][:m].contiguous(), vox[3][:m].contiguous()
+    ms_s, rb_s = timed(lambda: ops.rulebook_subm(coords, B, shape, 3))
+    ms_c, rb_c = timed(lambda: ops.rulebook_conv(coords, B, shape, 3, 2, 1))
+    w = torch.randn(27, 16, 16, device=dev) * 0.1
+    f16 = torch.randn(m, 16, device=dev)
+    packed = ops.tc_pack_weight(w)
+    ms_g, _ = timed(lambda: ops.sparse_conv_fwd_tc(f16, rb_s.nbr_out, packed, 16, 16))
+    pairs_s = int((rb_s.nbr_out >= 0).sum())
+    pairs_c = int((rb_c.nbr_out >= 0).sum())
+    n_pts = int(p.shape[0])
+
+    def row(ms, nbytes):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": round(ms, 4), "alg_bytes": int(nbytes), "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak_gbs, 4)}
+
+    return {"points": n_pts, "l1_sites": m, "strided_sites": int(rb_c.n_out), "subm_pairs": pairs_s, "strided_pairs": pairs_c,
+            "voxelize": row(ms_v, 16 * n_pts + (4 * 5 * 4 + 16) * m),
+            "rulebook_subm": row(ms_s, 16 * m + 8 * pairs_s + 16 * m),
+            "rulebook_strided": row(ms_c, 16 * m + 8 * pairs_c + 16 * rb_c.n_out),
+            "gather_gemm_16x16": row(ms_g, 4 * m * 16 * 2 + 8 * pairs_s + 4 * 27 * 16 * 16),
+            "what": "config 5 (stress): 2 x 100k-point clouds, voxel [0.025,0.025,0.05]; eager calls incl. their allocations and "
+                    "the one host read of a strided rulebook; bytes = SURVEY §8(d) algorithmic bytes"}
