@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--conv-grid", type=int, default=0, help="cap on the persistent conv grid (0 = one CTA per SM); with "
                     "--overlap a smaller grid leaves whole SMs to the rulebook chain of the next batch")
     ap.add_argument("--no-tile-meta", action="store_true", help="A/B: without per-rulebook tile masks / heaviest-first order")
+    ap.add_argument("--no-split", action="store_true", help="A/B: fp32 features between all layers (3xTF32 MMAs everywhere)")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the bounded CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -125,7 +126,7 @@ def layer_bytes_flops(plan, counts):
     for s in plan.steps:
         if s.kind != "conv":
             continue
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = s.args
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta, fmt = s.args
         n_out = lvl_n[id(lout)]
         pairs = int((nbr[:n_out] >= 0).sum().item())
         out.append({"n_in": n_in, "n_out": n_out, "pairs": pairs, "K": K, "cin": cin, "cout": cout,
@@ -194,7 +195,7 @@ def run_ours(args, rank, world):
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
                                device=dev, use_graph=not args.no_graph, sort_rows=args.sort,
-                               tile_meta=not args.no_tile_meta).capture()
+                               tile_meta=not args.no_tile_meta, split_format=not args.no_split).capture()
     scenes = make_scenes(rank, N_SCENE_POOL)
     # batches: host pinned (for e2e) and device resident (for value)
     n_batches = N_SCENE_POOL // B if N_SCENE_POOL >= B else 1
@@ -305,7 +306,7 @@ def run_ours(args, rank, world):
                 return engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE,
                                            S.KITTI_RANGE, max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"],
                                            algo=args.algo, device=dev, use_graph=False, sort_rows=args.sort,
-                                           tile_meta=not args.no_tile_meta)
+                                           tile_meta=not args.no_tile_meta, split_format=not args.no_split)
             ov = engine.OverlappedBackbone(make_plan, slots=2).capture()
             ov_out, ov_last = [0], [None]
 
@@ -346,7 +347,7 @@ def run_ours(args, rank, world):
         tot_ms, reps = 0.0, 5
         per_layer = []
         for s, sp in zip(conv_steps, specs):
-            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = s.args
+            fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta, fmt = s.args
             ms_l = 0.0
             for r in range(reps + 1):
                 flush.fill_(float(r))

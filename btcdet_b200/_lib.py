@@ -30,7 +30,7 @@ SIGNATURES = {
     "btc_rulebook_subm_hash": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "btc_rulebook_subm": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "btc_rulebook_conv": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _i, _p, _p, _p, _p, _i64, _p]),
-    "btc_rulebook_tile_order": (_i, [_p, _i, _p, _p, _p]),
+    "btc_rulebook_tile_order_ints": (_i64, [_i]),
     "btc_index_summary_words": (_i64, [_i64]),
     "btc_rulebook_conv_sparse_workspace_bytes": (_i64, [_i64]),
     "btc_rulebook_conv_sparse": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _p, _i, _p, _p, _p, _p, _i64, _p]),
@@ -43,8 +43,12 @@ SIGNATURES = {
     "btc_sparse_conv_tc_diag": (_i, [_i]),
     "btc_sparse_conv_tc_trace": (_i, [_p]),
     "btc_sparse_conv_tc_grid": (_i, [_i]),
-    "btc_sparse_conv_tc_commit_group": (_i, [_i]),
-    "btc_sparse_conv_tc_pdl": (_i, [_i]),
+    "btc_sparse_conv_tc_split_supported": (_i, [_i, _i, _i, _i, _i]),
+    "btc_sparse_conv_tc_split_packed_bytes": (_i64, [_i, _i, _i]),
+    "btc_sparse_conv_tc_pack_split": (_i, [_p, _i, _i, _i, _p, _p]),
+    "btc_features_to_split": (_i, [_p, _i, _p, _i, _p, _p]),
+    "btc_features_from_split": (_i, [_p, _i, _p, _i, _p, _p]),
+    "btc_sparse_conv_fwd_tc_split": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "btc_sparse_conv_tc_packed_bytes": (_i64, [_i, _i, _i]),
     "btc_sparse_conv_tc_pack": (_i, [_p, _i, _i, _i, _p, _p]),
     "btc_sparse_conv_fwd_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),

@@ -100,6 +100,28 @@ class BtcHotPath(nn.Module):
         return bd
 
 
+def calibrate_occ_head_bias(model, bd, fraction=0.03):
+    """Benchmark / test helper for random-init weights: shift the occupied-class bias of the head so that `fraction` of the
+    candidate cells (general_cls_loss_mask) of `bd` exceeds the occupancy threshold — an untrained head would otherwise pass
+    either nothing or everything, and the injection / re-voxelisation stages would not be exercised."""
+    import math
+    gf, gi = model.geom
+    with torch.no_grad():
+        b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in bd.items()}
+        tg = ops.occ_training_targets(b["voxels"], b["voxel_coords"], b["voxel_num_points"], int(b["batch_size"]), b["gt_boxes"],
+                                      b["gt_boxes_num"], gf, gi, box_mirr_flag=b.get("box_mirr_flag"), rot_z=b.get("rot_z"))
+        b.update(tg)
+        b["voxels"], b["voxel_features"] = occ_abs_mean_vfe(b["voxels"], b["voxel_num_points"])
+        b = model.occ_head(model.occ_backbone(b))
+        logit = b["pred_occ_logit"]
+        diff = (logit[:, 1] - logit[:, 0])[b["general_cls_loss_mask"].bool()]
+        q = torch.quantile(diff.float(), 1.0 - fraction)
+        target = math.log(model.occ_thresh / (1.0 - model.occ_thresh))
+        bias = model.occ_head.conv_cls[0].bias
+        bias[1] += float(target - q)
+    return model
+
+
 def synthetic_batch(seeds, n_points=20000, device="cuda", with_rot=False, mode="train"):
     """A config-3 batch_dict from seeded lidar_like scenes with everything produced on the device: a2 + cylindrical
     occupancy voxels, detection voxels, gt boxes (the generator's), mirror flags."""

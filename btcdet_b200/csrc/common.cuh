@@ -25,10 +25,11 @@ int set_error(int code, const char* what, cudaError_t e);
 
 inline int badarg(const char* what) { return set_error(BTC_E_BADARG, what, cudaSuccess); }
 
-// B200: 148 SMs.  Grids of streaming kernels are capped at a few waves and
-// grid-stride, so a launch sized by a *capacity* does not pay for empty tail.
+// B200: 148 SMs.  Grids of streaming kernels are capped at two waves of 8 CTAs per SM and grid-stride, so a launch
+// sized by a *capacity* (levels are planned at 2x growth; the live count is a fraction of it) does not pay for thousands
+// of CTAs that start only to find nothing to do (measured: ~1 us per wave of dead CTAs, profiles/r2_index_kernels.md).
 constexpr int kNumSM = 148;
-inline int grid_for(int64_t n, int threads, int max_waves = 8, int ctas_per_sm = 8) {
+inline int grid_for(int64_t n, int threads, int max_waves = 2, int ctas_per_sm = 8) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = (int64_t)kNumSM * ctas_per_sm * max_waves;
     if (b > cap) b = cap;

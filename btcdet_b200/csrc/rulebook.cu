@@ -102,64 +102,25 @@ subm_table_sym_kernel(const int4* __restrict__ coords, int n_cap, const int* __r
     const int n = live_count(n_cap, n_dev);
     const int K = g.K, half = K >> 1;
     const int sub = threadIdx.x >> 4, k = threadIdx.x & 15;
-    const int tap = k < half ? s_tap[k] : 0;
-    const int dz = (tap & 255) - 64, dy = ((tap >> 8) & 255) - 64, dx = ((tap >> 16) & 255) - 64;
-    // kSubmUnroll sites per thread and trip: their coordinate loads, then their index / hash probes, are issued together
-    // (one probe whose result is used right away costs a full L2 round trip; the kernel is bound by exactly that)
-    constexpr int U = 4;
-    const int stride = gridDim.x * kSubmSites * 2;
-    for (int i0 = (blockIdx.x * kSubmSites + threadIdx.y) * 2 + sub; i0 < n; i0 += stride * U) {
-        int4 c[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * stride;
-            c[u] = i < n ? __ldg(coords + i) : make_int4(-1, -1, -1, -1);
-        }
-        int64_t key[U];
-        bool ok[U];
-        uint2 e[U];
-        uint32_t h[U];
-        long long hk[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * stride;
-            const int z = c[u].y + dz, y = c[u].z + dy, x = c[u].w + dx;
-            ok[u] = i < n && k < half && (unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h &&
-                    (unsigned)x < (unsigned)g.in.w;
-            key[u] = ok[u] ? flat_key(c[u].x, z, y, x, g.in) : 0;
-            if (HASH) {
-                h[u] = hash_key64((unsigned long long)key[u]) & hmask;
-                hk[u] = ok[u] ? __ldg(keys + h[u]) : -1LL;
-            } else {
-                e[u] = ok[u] ? __ldg(index + (key[u] >> 5)) : make_uint2(0u, 0u);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * stride;
-            if (i >= n) continue;
-            if (k == 0) nbr_out[(int64_t)i * K + half] = i;          // centre tap: the site itself
-            if (!ok[u]) continue;
-            int j = -1;
-            if (HASH) {
-                long long kk = hk[u];
-                uint32_t hh = h[u];
-                while (true) {                                       // linear probing (first slot already fetched)
-                    if (kk == key[u]) { j = __ldg(vals + hh); break; }
-                    if (kk == -1LL) break;
-                    hh = (hh + 1) & hmask;
-                    kk = __ldg(keys + hh);
+    for (int i = (blockIdx.x * kSubmSites + threadIdx.y) * 2 + sub; i < n; i += gridDim.x * kSubmSites * 2) {
+        const int4 c = __ldg(coords + i);
+        if (k == 0) nbr_out[(int64_t)i * K + half] = i;          // centre tap: the site itself
+        if (k < half) {
+            const int tap = s_tap[k];
+            const int z = c.y + (tap & 255) - 64, y = c.z + ((tap >> 8) & 255) - 64, x = c.w + ((tap >> 16) & 255) - 64;
+            if ((unsigned)z < (unsigned)g.in.d && (unsigned)y < (unsigned)g.in.h && (unsigned)x < (unsigned)g.in.w) {
+                const int64_t key = flat_key(c.x, z, y, x, g.in);
+                int j = -1;
+                if (HASH) {
+                    j = hash_lookup(keys, vals, hmask, key);
+                } else {
+                    int r = index_lookup(index, key);
+                    if (r >= 0 && r < n_cap) j = perm ? __ldg(perm + r) : r;   // rank >= capacity: site not materialised
                 }
-            } else {
-                const unsigned bit = 1u << (unsigned)(key[u] & 31);
-                if (e[u].x & bit) {
-                    const int r = (int)(e[u].y + __popc(e[u].x & (bit - 1u)));
-                    if (r < n_cap) j = perm ? __ldg(perm + r) : r;   // rank >= capacity: site not materialised
+                if (j >= 0 && j < n) {
+                    nbr_out[(int64_t)i * K + k] = j;
+                    nbr_out[(int64_t)j * K + (K - 1 - k)] = i;
                 }
-            }
-            if (j >= 0 && j < n) {
-                nbr_out[(int64_t)i * K + k] = j;
-                nbr_out[(int64_t)j * K + (K - 1 - k)] = i;
             }
         }
     }
@@ -280,24 +241,51 @@ __global__ void conv_tables_kernel(const int4* __restrict__ coords, int n_cap, c
 // words, writes their ranks and decodes the output coordinates, touching only occupied words; both bitmaps are cleared
 // sparsely from the coordinate list after their last reader (btc_index_clear_sparse) instead of a memset per step.
 // Bytes moved per build: ~16 B per input tap + the summary (0.7 MB at batch 16) + 24 B per output site.
+// Output coordinate of one axis with the common strides resolved without an integer division.
+__device__ __forceinline__ bool out_coord_fast(int in, int kk, int s, int p, int d, int out_dim, int transposed, int& o) {
+    if (transposed) {
+        o = in * s - p + kk * d;
+    } else {
+        int t = in + p - kk * d;
+        if (t < 0) return false;
+        if (s == 2) {
+            if (t & 1) return false;
+            t >>= 1;
+        } else if (s != 1) {
+            if (t % s) return false;
+            t /= s;
+        }
+        o = t;
+    }
+    return o >= 0 && o < out_dim;
+}
+
+// One thread per input site; nested tap loops with the validity tests inline (no per-thread tap arrays: dynamically
+// indexed local arrays live in local memory).  Two fire-and-forget reductions per (site, tap) pair (RED.OR, results
+// unused: the thread never waits for the L2).  Measured alternatives (profiles/r2_index_kernels.md): a test-before-atomic
+// variant costs a dependent L2 round trip per tap (same time), warp-level aggregation of lanes that hit the same word
+// (match.any + redux) is 4.7x SLOWER — match.any serialises over the distinct values of a warp.
 __global__ void conv_mark2_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, ConvGeom g,
                                   unsigned* __restrict__ out_index_words, unsigned* __restrict__ summary) {
     const int n = live_count(n_cap, n_dev);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 c = __ldg(coords + i);
-        int kz_l[kMaxAxisTaps], oz_l[kMaxAxisTaps], ky_l[kMaxAxisTaps], oy_l[kMaxAxisTaps], kx_l[kMaxAxisTaps], ox_l[kMaxAxisTaps];
-        const int nz = axis_taps(c.y, g.k[0], g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, kz_l, oz_l);
-        const int ny = axis_taps(c.z, g.k[1], g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, ky_l, oy_l);
-        const int nx = axis_taps(c.w, g.k[2], g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, kx_l, ox_l);
-        for (int a = 0; a < nz; ++a)
-            for (int b = 0; b < ny; ++b)
-                for (int d = 0; d < nx; ++d) {
-                    const int64_t key = flat_key(c.x, oz_l[a], oy_l[b], ox_l[d], g.out);
-                    // two fire-and-forget reductions (RED.OR, results unused): the thread never waits for the L2
+        for (int kz = 0; kz < g.k[0]; ++kz) {
+            int oz;
+            if (!out_coord_fast(c.y, kz, g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, oz)) continue;
+            for (int ky = 0; ky < g.k[1]; ++ky) {
+                int oy;
+                if (!out_coord_fast(c.z, ky, g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, oy)) continue;
+                for (int kx = 0; kx < g.k[2]; ++kx) {
+                    int ox;
+                    if (!out_coord_fast(c.w, kx, g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, ox)) continue;
+                    const int64_t key = flat_key(c.x, oz, oy, ox, g.out);
                     const int64_t w = key >> 5;
                     atomicOr(out_index_words + 2 * w, 1u << (unsigned)(key & 31));
                     atomicOr(summary + (w >> 5), 1u << (unsigned)(w & 31));
                 }
+            }
+        }
     }
 }
 
@@ -391,37 +379,54 @@ __global__ void conv_tables2_kernel(const int4* __restrict__ coords, int n_cap, 
         const int4 c = __ldg(coords + i);
         if (nbr_in)
             for (int k = 0; k < K; ++k) nbr_in[(int64_t)i * K + k] = -1;
-        int kz_l[kMaxAxisTaps], oz_l[kMaxAxisTaps], ky_l[kMaxAxisTaps], oy_l[kMaxAxisTaps], kx_l[kMaxAxisTaps], ox_l[kMaxAxisTaps];
-        const int nz = axis_taps(c.y, g.k[0], g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, kz_l, oz_l);
-        const int ny = axis_taps(c.z, g.k[1], g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, ky_l, oy_l);
-        const int nx = axis_taps(c.w, g.k[2], g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, kx_l, ox_l);
-        // taps in batches of 8 (all of a k3 s2 site's): the rank-bitmap loads of a batch are issued together, then used
-        const int taps = nz * ny * nx;
-        for (int t0 = 0; t0 < taps; t0 += 8) {
+        // pass 1: issue the rank-bitmap loads of up to 8 valid taps (all of a k3 s2 site's) without using them;
+        // pass 2: resolve rows and write.  Sites with more valid taps (transposed / stride-1 kernels) take further rounds.
+        int done = 0;                                   // valid taps already handled
+        while (true) {
             uint2 e[8];
+            long long packed[8];                        // k | oz << 10 | oy << 24 | ox << 44
             int64_t key[8];
+            int cnt = 0, seen = 0;
+            for (int kz = 0; kz < g.k[0] && cnt < 8; ++kz) {
+                int oz;
+                if (!out_coord_fast(c.y, kz, g.s[0], g.p[0], g.dil[0], g.out.d, g.transposed, oz)) continue;
+                for (int ky = 0; ky < g.k[1] && cnt < 8; ++ky) {
+                    int oy;
+                    if (!out_coord_fast(c.z, ky, g.s[1], g.p[1], g.dil[1], g.out.h, g.transposed, oy)) continue;
+                    for (int kx = 0; kx < g.k[2] && cnt < 8; ++kx) {
+                        int ox;
+                        if (!out_coord_fast(c.w, kx, g.s[2], g.p[2], g.dil[2], g.out.w, g.transposed, ox)) continue;
+                        if (seen++ < done) continue;
+                        const int64_t kk = flat_key(c.x, oz, oy, ox, g.out);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int t = t0 + j < taps ? t0 + j : t0;
-                const int d = t % nx, b = (t / nx) % ny, a = t / (nx * ny);
-                key[j] = flat_key(c.x, oz_l[a], oy_l[b], ox_l[d], g.out);
-                e[j] = __ldg(out_index + (key[j] >> 5));
+                        for (int j = 0; j < 8; ++j)
+                            if (j == cnt) {             // static indices keep the batch in registers
+                                key[j] = kk;
+                                packed[j] = (long long)((kz * g.k[1] + ky) * g.k[2] + kx) | ((long long)oz << 10) |
+                                            ((long long)oy << 24) | ((long long)ox << 44);
+                                e[j] = __ldg(out_index + (kk >> 5));
+                            }
+                        ++cnt;
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (t0 + j >= taps) break;
-                const int t = t0 + j;
-                const int d = t % nx, b = (t / nx) % ny, a = t / (nx * ny);
-                const int k = (kz_l[a] * g.k[1] + ky_l[b]) * g.k[2] + kx_l[d];
+                if (j >= cnt) break;
+                const int k = (int)(packed[j] & 1023);
                 const unsigned bit = 1u << (unsigned)(key[j] & 31);
                 int o = (e[j].x & bit) ? (int)(e[j].y + __popc(e[j].x & (bit - 1u))) : -1;
                 if (o >= out_cap) o = -1;
                 if (nbr_in) nbr_in[(int64_t)i * K + k] = o;
                 if (o >= 0) {
                     if (nbr_out) nbr_out[(int64_t)o * K + k] = i;
-                    if (out_coords) out_coords[o] = make_int4(c.x, oz_l[a], oy_l[b], ox_l[d]);
+                    if (out_coords)
+                        out_coords[o] = make_int4(c.x, (int)((packed[j] >> 10) & 16383), (int)((packed[j] >> 24) & 1048575),
+                                                  (int)(packed[j] >> 44));
                 }
             }
+            done += cnt;
+            if (cnt < 8) break;
         }
     }
 }
@@ -615,7 +620,7 @@ int btc_rulebook_subm(const int* coords, int n_cap, const int* n_dev, int batch,
     cudaStream_t st = (cudaStream_t)stream;
     if ((g.K & 1) && g.K / 2 <= 16) {
         fill_table_kernel<<<grid_for((int64_t)n_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, n_cap, n_dev, g.K);
-        subm_table_sym_kernel<false><<<grid_for((n_cap + 8 * kSubmSites - 1) / (8 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
+        subm_table_sym_kernel<false><<<grid_for((n_cap + 2 * kSubmSites - 1) / (2 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
             (const int4*)coords, n_cap, n_dev, g, (const uint2*)index, perm, nullptr, nullptr, 0u, nbr_out);
     } else {
         subm_table_kernel<false><<<grid_for((n_cap + kSubmSites - 1) / kSubmSites, 1, 8, 8), blk, 0, st>>>(
@@ -641,7 +646,7 @@ int btc_rulebook_subm_hash(const int* coords, int n_cap, const int* n_dev, int b
     cudaStream_t st = (cudaStream_t)stream;
     if ((g.K & 1) && g.K / 2 <= 16) {
         fill_table_kernel<<<grid_for((int64_t)n_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, n_cap, n_dev, g.K);
-        subm_table_sym_kernel<true><<<grid_for((n_cap + 8 * kSubmSites - 1) / (8 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
+        subm_table_sym_kernel<true><<<grid_for((n_cap + 2 * kSubmSites - 1) / (2 * kSubmSites), 1, 8, 8), blk, 0, st>>>(
             (const int4*)coords, n_cap, n_dev, g, nullptr, nullptr, (const long long*)keys, vals, (uint32_t)(n_slots - 1),
             nbr_out);
     } else {

@@ -18,6 +18,7 @@
 //     ReLU and write the output rows while the next tile's main loop runs.
 #include <stdlib.h>
 #include <atomic>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace btc {
@@ -177,6 +178,63 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
     }
 }
 
+// byte offset of bf16 element (row r, element j of 64) inside a K-major SW128 tile
+__host__ __device__ __forceinline__ int sw128_offset_bf16(int r, int j) {
+    return (r >> 3) * 1024 + (r & 7) * 128 + ((((j >> 3) ^ (r & 7)) & 7) << 4) + (j & 7) * 2;
+}
+
+// Split-format weights: the reduction axis e = k*c_in + ci in tiles of 64; packed[tile] = { B_hi image [N x 128 B] of
+// bf16, B_lo image }, hi = bf16_rn(w), lo = bf16_rn(w - hi).  A 32-element stage (chunk c) uses half c & 1 of tile c >> 1.
+__global__ void tc_pack_weight_split_kernel(const float* __restrict__ w, int K, int c_in, int c_out, int N,
+                                            unsigned short* __restrict__ packed) {
+    const int E = K * c_in;
+    const int ntile = (E + 63) / 64;
+    const int64_t total = (int64_t)ntile * N * 64;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % 64);
+        const int64_t r = t / 64;
+        const int n = (int)(r % N);
+        const int tt = (int)(r / N);
+        const int e = tt * 64 + j;
+        const float v = (e < E && n < c_out) ? w[(int64_t)e * c_out + n] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        char* base = (char*)packed + (int64_t)tt * (2 * N * 128);
+        *(unsigned short*)(base + sw128_offset_bf16(n, j)) = __bfloat16_as_ushort(hi);
+        *(unsigned short*)(base + N * 128 + sw128_offset_bf16(n, j)) = __bfloat16_as_ushort(lo);
+    }
+}
+
+// fp32 rows <-> split rows (per 32 channels [32 x bf16 hi | 32 x bf16 lo]); c % 32 == 0.  One thread per channel pair.
+__global__ void features_to_split_kernel(const float* __restrict__ in, int n_cap, const int* __restrict__ n_dev, int c,
+                                         uint32_t* __restrict__ out) {
+    const int64_t work = (int64_t)live_count(n_cap, n_dev) * (c / 2);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / (c / 2);
+        const int pr = (int)(t % (c / 2));                 // channel pair (2 pr, 2 pr + 1)
+        const float2 x = *reinterpret_cast<const float2*>(in + row * c + 2 * pr);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1));
+        uint32_t* blk = out + row * c + (pr >> 4) * 32;    // 32 words per 32-channel block
+        blk[pr & 15] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        blk[16 + (pr & 15)] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+__global__ void features_from_split_kernel(const uint32_t* __restrict__ in, int n_cap, const int* __restrict__ n_dev, int c,
+                                           float* __restrict__ out) {
+    const int64_t work = (int64_t)live_count(n_cap, n_dev) * (c / 2);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / (c / 2);
+        const int pr = (int)(t % (c / 2));
+        const uint32_t* blk = in + row * c + (pr >> 4) * 32;
+        const uint32_t h = blk[pr & 15], l = blk[16 + (pr & 15)];
+        float2 x;
+        x.x = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+        x.y = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+        *reinterpret_cast<float2*>(out + row * c + 2 * pr) = x;
+    }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 // Persistent, warp-specialised: one CTA per SM walks 128-row output tiles handed out by a tile scheduler.
 //   producers  : NPW warps in NPW/4 groups (4 warps = 128 rows = the four TMEM lane quarters; thread == output row).
@@ -233,6 +291,17 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// bf16 operands (A: 16 values = 8 TMEM columns per lane, two per column, even element in the low half)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
@@ -260,20 +329,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// CAT: the hi and lo weight tiles of a stage are adjacent in shared memory, i.e. one K-major tile of 2N rows, so
-// A_hi x [B_hi | B_lo] is ONE MMA of width 2N into two accumulator column blocks (D1 | D2) and the 3xTF32 step is two
-// instructions (A_hi x [B_hi|B_lo], A_lo x B_hi -> D1) instead of three; the epilogue adds D1 + D2.  Same tensor-pipe
-// cycles, a third fewer instructions and half the descriptors on the single issuing thread, which the round-1 source-
-// level profile showed to be the critical path (~100 instructions, ~800 cycles per stage against 384 cycles of MMA).
-// Needs 4N + 64*STAGES <= 512 TMEM columns: N <= 64.
-// CG (commit group): the stages of a ring are released in groups of CG with ONE tcgen05.commit after the last stage of a
-// group (empty barrier per slot group).  CG = 1 is the measured round-1 default; CG = 2 / 3 is the experiment DESIGN.md
-// §8.1(0) calls for (a per-stage commit appears to drain the MMA pipeline) and is not yet verified on hardware.
-// PDL (programmatic dependent launch, EXPERIMENTAL, not verified on hardware in round 1): the kernel lets its dependents
-// be scheduled as soon as its own CTAs leave an SM (griddepcontrol.launch_dependents) and, launched with the
-// programmatic-serialisation attribute itself, runs its prologue, first index tile and weight prefetch under the tail of
-// the previous layer; only the producers' first gather waits for that layer to complete (griddepcontrol.wait).
-template <int N, int NPW, bool CAT, int CG, bool PDL = false>
+// Operand formats (round 2).  SIN / SOUT select the "split" feature format on the input / output side:
+//   fp32 format  : rows of C floats; the producers split every value into tf32 hi / lo in registers and the k-step is
+//                  three kind::tf32 MMAs of K = 8 (3xTF32) — 12 MMAs per 32-element stage;
+//   split format : the SAME 4 C bytes per row, but every value is stored by the producing layer's epilogue as two
+//                  bfloat16: x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi) (|x - hi - lo| <= 2^-17 |x|).  Per
+//                  32 channels the row holds [32 x hi | 32 x lo] (64 B + 64 B), so a stage's gather is byte-for-byte
+//                  the copy it was, the read-back registers ARE the packed A operands (no ALU work in the producers,
+//                  half the tcgen05.st) and the k-step is three kind::f16 (bf16) MMAs of K = 16: A_lo B_hi + A_hi B_lo
+//                  + A_hi B_hi — 6 MMAs per stage.  Weights are packed as bf16 hi / lo tiles of 64 reduction elements
+//                  (one 128-byte swizzle row); a stage uses the half its chunk parity names.
+// Both meet the 1e-4 parity bar (split: ~2^-16 per product, measured in tests/test_parity_gpu.py).  The experimental
+// variants of round 1 (concatenated [B_hi|B_lo] MMAs, commit groups, programmatic dependent launch) were measured on
+// hardware at the start of round 2 (profiles/r2_battery.json: no gain / slower) and removed.
+template <int N, int NPW, bool SIN, bool SOUT>
 __global__ void __launch_bounds__(TcRoles<NPW>::kThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ table,
                    const float* __restrict__ packed_w, const float* __restrict__ bias,
@@ -281,26 +350,25 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    float* __restrict__ feat_out, const int* __restrict__ out_rows, int n_cap,
                    const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag,
                    unsigned long long* __restrict__ trace, const unsigned long long* __restrict__ tile_mask,
-                   const int* __restrict__ tile_order) {
-    constexpr int STAGES = TcAStages<N, CAT>::value;
+                   const int* __restrict__ tile_order, int tiles_cap) {
+    constexpr int STAGES = TcAStages<N, false>::value;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
     constexpr int G = Roles::kGroups;               // producer groups; group g feeds the stages with gi % G == g
     constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx, TC_BLD_WARP = Roles::kBld;
     constexpr int NB = TcBStages<N>::value;         // weight-tile ring depth
-    static_assert(NB == TcAStages<N, CAT>::value, "the A ring and the weight ring share slot index, phase and the commit");
-    static_assert(CG >= 1 && STAGES % CG == 0, "commit groups tile the ring");
+    static_assert(NB == TcAStages<N, false>::value, "the A ring and the weight ring share slot index, phase and the commit");
     static_assert(G <= STAGES, "a group advances by G stages and may wrap the ring at most once per step");
     constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
     constexpr int STAGE_BYTES = 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = 512;
-    constexpr uint32_t ACC_COLS = CAT ? 2 * N : N;   // TMEM columns of one accumulator buffer
+    constexpr uint32_t ACC_COLS = N;              // TMEM columns of one accumulator buffer
     constexpr uint32_t A_COL0 = 2 * ACC_COLS;     // first A-operand column
-    // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // instruction descriptor: D=f32 (1<<4), A / B format at bits 7 / 10 (tf32 = 2, bf16 = 1), K-major both, N>>3 at bit 17,
+    // M>>4 at bit 24
+    constexpr uint32_t FMT = SIN ? 1u : 2u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     static_assert(2 * ACC_COLS + 64 * STAGES <= 512, "TMEM budget");
-    static_assert(!CAT || 2 * N <= 256, "UMMA N limit");
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* stages = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
@@ -313,6 +381,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     __shared__ int s_cnt[2];                        // active reduction chunks of the tile in each index buffer
     __shared__ int s_tile[2];                       // tile id in each index buffer (-1: no more tiles for this CTA)
     __shared__ int s_epi_tile[2];                   // tile id behind each accumulator buffer (MMA issuer -> epilogue)
+    __shared__ int s_cls_start[66];                 // heaviest-first prefix of the cost-class counts (tile_order lookup)
 
     const int n = live_count(n_cap, n_dev);
     if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
@@ -356,7 +425,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tr && tid == 0) tr[2] = (unsigned long long)clock64();
 
     if (warp < TC_PRODUCER_WARPS) {
@@ -414,9 +482,12 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + it_pos));
             // this lane's 4-float piece covers flattened elements e .. e+3 -> offset i_k = e / c_in, channel e % c_in
             // (c_in % 4 == 0, so a piece never straddles two offsets)
-            const uint32_t e = chunk * TC_KC + (uint32_t)q * 4u;
+            // fp32 rows: piece q = floats e .. e+3.  Split rows (c_in % 32 == 0): the chunk is one 128-byte block
+            // [32 hi | 32 lo] of its offset's row and piece q is its q-th 16 bytes.
+            const uint32_t e = SIN ? chunk * TC_KC : chunk * TC_KC + (uint32_t)q * 4u;
             const int i_k = (int)__umulhi(e, magic);
-            const uint32_t colbytes = (e - (uint32_t)i_k * (uint32_t)c_in) * 4u;
+            const uint32_t colbytes = SIN ? (e - (uint32_t)i_k * (uint32_t)c_in) * 4u + (uint32_t)q * 16u
+                                          : (e - (uint32_t)i_k * (uint32_t)c_in) * 4u;
             const bool col_ok = i_k < K;            // beyond the end of the reduction axis: zero fill
             const uint32_t nb = nbr_s32 + 4u * (uint32_t)(buf * TC_BM * K + (quarter * 32 + sub) * K + (col_ok ? i_k : 0));
             const uint32_t dbase = abuf + (uint32_t)slot * 4096u;
@@ -440,7 +511,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         };
         const uint32_t rd_base = abuf + (uint32_t)lane * 128u;
         const uint32_t x7 = (uint32_t)(lane & 7);
-        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");   // feat_in is the previous layer's output
         int s = group % STAGES, ph = 0, slot = 0, islot = 0;   // consume-side stage slot / phase, staging slots
         bool located = false;
         const bool tr_me = tr && warp == 0 && lane == 0;
@@ -477,11 +547,28 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             __syncwarp();                          // everyone has read the slot before it is refilled
             long long tw0 = 0;
             if (tr_me) tw0 = clock64();
-            mbar_wait_a(empty0 + 8u * (uint32_t)(s / CG), (uint32_t)(ph ^ 1));
+            mbar_wait_a(empty0 + 8u * (uint32_t)s, (uint32_t)(ph ^ 1));
             if (tr_me) tr_wait_empty += clock64() - tw0;
             tc_fence_after();
             // hi = low 13 mantissa bits cleared (exact tf32), lo = exact fp32 remainder; written in 16-column halves
             // to keep the live register set small (the 16-warp variant runs the producers at 96 registers)
+            if (SIN) {
+                // split rows: pieces 0..3 are the packed bf16 hi operand (32 values = 16 columns), 4..7 the lo operand
+                if (!(diag & 2)) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            w[4 * i + 0] = __float_as_uint(v[4 * h + i].x);
+                            w[4 * i + 1] = __float_as_uint(v[4 * h + i].y);
+                            w[4 * i + 2] = __float_as_uint(v[4 * h + i].z);
+                            w[4 * i + 3] = __float_as_uint(v[4 * h + i].w);
+                        }
+                        tmem_st16(lane_base + A_COL0 + (uint32_t)(s * 64 + 32 * h), w);
+                    }
+                }
+            } else
             if (!(diag & 2))                        // (bit 1 drops the smem read-back, the hi/lo split and the TMEM stores)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -551,20 +638,26 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             __syncwarp();
             if (tile < 0) break;
-            // one stage = 12 (8 with CAT) MMAs + the two commits that free its A and weight slots
-            auto issue_stage = [&](uint32_t sa, bool first) {
+            // one stage = 12 tf32 (6 bf16) MMAs + the commit that frees its A and weight slots.  `half`: split format only —
+            // which 32-element half of the 64-element weight tile the stage's chunk is (chunk parity).
+            const uint32_t list_s32 = smem_u32(s_list);
+            auto issue_stage = [&](uint32_t sa, bool first, uint32_t half) {
                 const uint32_t a_hi = tmem_base + A_COL0 + sa * 64u;
                 const uint32_t a_lo = a_hi + 32u;
-                const uint32_t dl = desc_lo0 + sa * (uint32_t)(STAGE_BYTES >> 4);
+                const uint32_t dl = desc_lo0 + sa * (uint32_t)(STAGE_BYTES >> 4) + (SIN ? half * 4u : 0u);
+                constexpr int KSTEPS = SIN ? TC_KC / 16 : TC_KC / 8;   // UMMA_K = 16 bf16 / 8 tf32 = 8 TMEM columns, 32 B of B
 #pragma unroll
-                for (int kk = 0; kk < TC_KC / 8; ++kk) {   // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
+                for (int kk = 0; kk < KSTEPS; ++kk) {
                     const uint64_t db_hi = desc_hi64 | (uint64_t)(dl + 2u * (uint32_t)kk);
                     const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-                    if (CAT) {
-                        umma_tf32_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC2, acc);   // D1 | D2
-                        umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, 1u);     // D1
+                    const uint64_t db_lo = desc_hi64 | (uint64_t)(dl + (uint32_t)(B_BYTES >> 4) + 2u * (uint32_t)kk);
+                    if (SIN) {
+                        umma_f16_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, acc);    // small terms first
+                        if (!(diag & 4)) {
+                            umma_f16_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
+                            umma_f16_ts(d_tmem, a_hi + kk * 8, db_hi, IDESC, 1u);
+                        }
                     } else {
-                        const uint64_t db_lo = desc_hi64 | (uint64_t)(dl + (uint32_t)(B_BYTES >> 4) + 2u * (uint32_t)kk);
                         umma_tf32_ts(d_tmem, a_lo + kk * 8, db_hi, IDESC, acc);   // small terms first
                         if (!(diag & 4)) {            // (bit 2: one MMA per k-step instead of three)
                             umma_tf32_ts(d_tmem, a_hi + kk * 8, db_lo, IDESC, 1u);
@@ -572,8 +665,10 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                         }
                     }
                 }
-                if (CG == 1 || sa % CG == CG - 1)   // last stage of its commit group
-                    umma_commit_a(empty0 + 8u * (sa / CG));   // frees the A and weight stages (of the group) once the MMAs retire
+                umma_commit_a(empty0 + 8u * sa);   // frees the A and weight stages once the MMAs retire
+            };
+            auto chunk_half = [&](int jj) -> uint32_t {
+                return SIN ? (lds_u16(list_s32 + 2u * (uint32_t)(buf * T + jj)) & 1u) : 0u;
             };
             // Two stages per trip where the list allows (diag bit 4 forces one): the wait -> fence -> elect -> issue ->
             // reconverge sequence has a fixed latency that a 12-MMA stage does not cover.
@@ -596,9 +691,10 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     tr_first = false;
                 }
                 tc_fence_after();
+                const uint32_t h0 = chunk_half(j), h1 = chunk_half(j + 1);
                 if (elect_one()) {
-                    issue_stage(s, j == 0);
-                    issue_stage(s1, false);
+                    issue_stage(s, j == 0, h0);
+                    issue_stage(s1, false, h1);
                 }
                 __syncwarp();
                 s = s1 + 1; ph = ph1;
@@ -617,7 +713,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     tr_first = false;
                 }
                 tc_fence_after();
-                if (elect_one()) issue_stage(s, j == 0);
+                const uint32_t h0 = chunk_half(j);
+                if (elect_one()) issue_stage(s, j == 0, h0);
                 __syncwarp();
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
             }
@@ -643,12 +740,14 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 const int cnt = s_cnt[buf];
                 for (int j = 0; j < cnt; ++j) {
                     const uint32_t chunk = lds_u16(list_s32 + 2u * (uint32_t)(buf * T + j));
-                    mbar_wait(&empty_bar[sb / CG], pb ^ 1u);   // the MMAs that read this slot (group) have retired
+                    mbar_wait(&empty_bar[sb], pb ^ 1u);   // the MMAs that read this slot have retired
                     tc_fence_after();
                     if (!(diag & 8)) {                         // (timing diagnostics: bit 3 drops the weight-tile copy)
                         mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
-                        bulk_copy_g2s(stages + sb * STAGE_BYTES, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES),
-                                      2 * B_BYTES, &b_full[sb]);
+                        // split format: the 64-element tile that holds this 32-element chunk (chunk >> 1)
+                        bulk_copy_g2s(stages + sb * STAGE_BYTES,
+                                      (const char*)packed_w + (int64_t)(SIN ? (chunk >> 1) : chunk) * (2 * B_BYTES), 2 * B_BYTES,
+                                      &b_full[sb]);
                     }
                     mbar_arrive(&b_full[sb]);
                     if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
@@ -665,6 +764,24 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // the fetch that returns num_tiles - 1 is the last one and resets the counter for the next launch.
         const int P = num_tiles < (int)gridDim.x ? num_tiles : (int)gridDim.x;
         const uint32_t nbr_s32 = smem_u32(nbr_s);
+        if (tile_order) {
+            // s_cls_start[r] = number of tiles in classes heavier than class (64 - r); s_cls_start[65] = all tiles
+            int c0 = __ldg(tile_order + (64 - lane)), c1 = __ldg(tile_order + (32 - lane >= 0 ? 32 - lane : 0));
+            if (lane > 32) c1 = 0;
+            const int i0 = warp_inclusive_scan(c0);
+            const int t0 = __shfl_sync(0xffffffffu, i0, 31);
+            const int i1 = warp_inclusive_scan(c1) + t0;
+            s_cls_start[lane] = i0 - c0;                       // r = lane        (classes 64 .. 33)
+            s_cls_start[32 + lane] = i1 - c1;                  // r = 32 + lane   (classes 32 .. 1)
+            if (lane == 0) s_cls_start[64] = 0;                // fixed below
+            __syncwarp();
+            if (lane == 0) {
+                const int c_last = __ldg(tile_order + 0);      // class 0 (cannot hold live tiles of a well-formed table)
+                s_cls_start[64] = s_cls_start[63] + __ldg(tile_order + 1);
+                s_cls_start[65] = s_cls_start[64] + c_last;
+            }
+            __syncwarp();
+        }
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
             int tile = -1;
@@ -682,9 +799,16 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                         if (t == num_tiles - 1) atomicExch(tile_ctr, 0);
                     }
                 }
-                // heaviest-first hand-out (btc_rulebook_tile_meta): position in the sequence -> tile id, so that the last
-                // tiles of a launch are its cheapest and the CTAs finish together
-                if (tile >= 0 && tile_order) tile = __ldg(tile_order + tile);
+                // heaviest-first hand-out (btc_rulebook_tile_meta): position in the sequence -> (cost class, slot) -> tile
+                // id, so that the last tiles of a launch are its cheapest and the CTAs finish together
+                if (tile >= 0 && tile_order) {
+                    int lo_r = 0, hi_r = 65;                    // largest r with s_cls_start[r] <= tile
+                    while (hi_r - lo_r > 1) {
+                        const int mid = (lo_r + hi_r) >> 1;
+                        if (s_cls_start[mid] <= tile) lo_r = mid; else hi_r = mid;
+                    }
+                    tile = __ldg(tile_order + 65 + (int64_t)(64 - lo_r) * tiles_cap + (tile - s_cls_start[lo_r]));
+                }
             }
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile < 0) {                            // publish the end marker and leave
@@ -768,12 +892,35 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             for (int c0 = 0; c0 < N; c0 += 16) {
                 uint32_t acc[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * ACC_COLS + (uint32_t)c0, acc);
-                if (CAT) {                             // D = D1 + D2 (the A_hi x B_lo terms)
-                    uint32_t acc2[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * ACC_COLS + (uint32_t)(N + c0), acc2);
+                if (SOUT) {
+                    // split format out: 16 channels -> 8 packed bf16 hi words + 8 lo words of the row's 128-byte block
+                    if (row < n && c0 < c_out) {
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
-                }
+                        for (int pp = 0; pp < 8; ++pp) {
+                            float x[2];
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                const int col = c0 + 2 * pp + jj;
+                                float t = __uint_as_float(acc[2 * pp + jj]);
+                                if (bias) t += __ldg(bias + col);
+                                if (scale) t = t * __ldg(scale + col) + __ldg(shift + col);
+                                if (relu) t = fmaxf(t, 0.f);
+                                x[jj] = t;
+                            }
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[0]), h1 = __float2bfloat16_rn(x[1]);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[0] - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(x[1] - __bfloat162float(h1));
+                            hi[pp] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[pp] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        char* blk = reinterpret_cast<char*>(dst) + (c0 >> 5) * 128 + ((c0 >> 4) & 1) * 32;
+                        *reinterpret_cast<uint4*>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(blk + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<uint4*>(blk + 64) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(blk + 80) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                } else
                 if (row < n && c0 < c_out) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -824,6 +971,8 @@ __global__ void __launch_bounds__(128) tile_mask_kernel(const int* __restrict__ 
     __shared__ unsigned long long s_m[4];
     const int n = live_count(n_cap, n_dev);
     const int row0 = blockIdx.x * TC_BM;
+    if (row0 >= n && blockIdx.x > 0) return;          // capacity-sized grid: dead tiles leave without taking a ticket
+    const int live_tiles = n > 0 ? (n + TC_BM - 1) / TC_BM : 1;
     unsigned long long m = 0;
     if (row0 < n) {
         const int rows = n - row0 < TC_BM ? n - row0 : TC_BM;
@@ -838,50 +987,23 @@ __global__ void __launch_bounds__(128) tile_mask_kernel(const int* __restrict__ 
     if (threadIdx.x == 0) tile_mask[blockIdx.x] = s_m[0] | s_m[1] | s_m[2] | s_m[3];
 }
 
-// tile_order: the live tiles sorted by descending number of active offsets (counting sort in one CTA; the order inside
-// a cost class is unspecified — it only decides which CTA runs which tile, never a result).
-__device__ __forceinline__ void tile_order_block(const unsigned long long* __restrict__ tile_mask, int tiles,
-                                                 int* __restrict__ tile_order, int* s_cnt, int* s_start) {
-    if (threadIdx.x < 65) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const volatile unsigned long long* tm = tile_mask;     // (tile_meta_kernel: written by other CTAs of the same launch)
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(&s_cnt[__popcll(tm[t])], 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int c = 64; c >= 0; --c) { s_start[c] = acc; acc += s_cnt[c]; }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-        const int c = __popcll(tm[t]);
-        tile_order[atomicAdd(&s_start[c], 1)] = t;
-    }
-}
-
-__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned long long* __restrict__ tile_mask, int n_cap,
-                                                          const int* __restrict__ n_dev, int* __restrict__ tile_order) {
-    __shared__ int s_cnt[65], s_start[65];
-    const int n = live_count(n_cap, n_dev);
-    tile_order_block(tile_mask, (n + TC_BM - 1) / TC_BM, tile_order, s_cnt, s_start);
-}
-
-// Masks and order in ONE launch: every CTA computes the mask of its tile; the CTA that finishes last (atomic ticket,
-// no CTA ever waits for another) sorts the tiles.  `ticket` is a zeroed device int that the kernel leaves at zero.
+// Masks and cost classes in ONE launch, no CTA waiting for another: every live CTA computes the mask of its tile, takes a
+// slot in the bucket of its cost class (number of active offsets, 0..64) with one atomic and stores its tile id there.
+// `tile_order` = [0, 65): class counts (zeroed by the caller), [65, 65 + 65 * tiles_cap): the buckets.  The conv kernel's
+// scheduler turns a position of the heaviest-first sequence into a tile id with a 65-entry prefix (tc_order_lookup).
 __global__ void __launch_bounds__(128) tile_meta_kernel(const int* __restrict__ table, int n_cap, const int* __restrict__ n_dev,
                                                         int K, unsigned long long* __restrict__ tile_mask,
-                                                        int* __restrict__ tile_order, int* __restrict__ ticket) {
+                                                        int* __restrict__ tile_order, int tiles_cap) {
     __shared__ unsigned long long s_m[4];
-    __shared__ int s_cnt[65], s_start[65];
-    __shared__ int s_last;
     const int n = live_count(n_cap, n_dev);
-    const int row0 = blockIdx.x * TC_BM;
-    unsigned long long m = 0;
-    if (row0 < n) {
+    for (int tile = blockIdx.x; tile * TC_BM < n; tile += gridDim.x) {     // grid-stride over the LIVE tiles
+        const int row0 = tile * TC_BM;
+        unsigned long long m = 0;
         const int rows = n - row0 < TC_BM ? n - row0 : TC_BM;
         const int total = rows * K;
         const int* src = table + (int64_t)row0 * K;
         // coalesced sweep of the tile's [rows x K] block in batches of 16 independent loads per thread (a load whose
-        // value is tested right away costs a full L2 round trip each: 27 in a row made this kernel 25 us)
+        // value is tested right away costs a full L2 round trip each)
         for (int i0 = threadIdx.x; i0 < total; i0 += 128 * 16) {
             int v[16];
 #pragma unroll
@@ -890,23 +1012,20 @@ __global__ void __launch_bounds__(128) tile_meta_kernel(const int* __restrict__ 
             for (int j = 0; j < 16; ++j)
                 if (v[j] >= 0) m |= 1ull << ((i0 + 128 * j) % K);
         }
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)m), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
+        if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long mm = s_m[0] | s_m[1] | s_m[2] | s_m[3];
+            tile_mask[tile] = mm;
+            if (tile_order) {
+                const int c = __popcll(mm);
+                const int pos = atomicAdd(tile_order + c, 1);
+                tile_order[65 + (int64_t)c * tiles_cap + pos] = tile;
+            }
+        }
+        __syncthreads();
     }
-    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)m), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
-    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tile_mask[blockIdx.x] = s_m[0] | s_m[1] | s_m[2] | s_m[3];
-        __threadfence();                                        // the mask is visible before the ticket is taken
-        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last || !tile_order) {
-        if (s_last && threadIdx.x == 0) *ticket = 0;
-        return;
-    }
-    __threadfence();
-    tile_order_block((const unsigned long long*)tile_mask, (n + TC_BM - 1) / TC_BM, tile_order, s_cnt, s_start);
-    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter at zero again (see
@@ -914,7 +1033,7 @@ __global__ void __launch_bounds__(128) tile_meta_kernel(const int* __restrict__ 
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
-static int g_tc_npw = 0, g_tc_cat = -1, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM, g_tc_cg = 1, g_tc_pdl = 0;
+static int g_tc_npw = 0, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM;
 static unsigned long long* g_tc_trace = nullptr;   // timeline diagnostics buffer (device, 16 u64 per CTA) or null
 
 static int* next_tile_counter() {
@@ -930,22 +1049,6 @@ static int* next_tile_counter() {
     return base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
 }
 
-// Tickets of tile_meta_kernel (zero at module load, every launch leaves its ticket at zero): rotating slots like the
-// tile counters, so launches that overlap on different streams do not share one.
-__device__ int g_tile_meta_ticket[kTcCtrSlots];
-static int* tile_meta_ticket() {
-    static int* base[64] = {nullptr};
-    static std::atomic<unsigned> next{0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!base[dev]) {
-        void* p = nullptr;
-        if (cudaGetSymbolAddress(&p, g_tile_meta_ticket) != cudaSuccess) return nullptr;
-        base[dev] = (int*)p;
-    }
-    return base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
-}
-
 // dynamic shared memory of one CTA: weight ring + cp.async staging + two index tiles + two chunk lists + alignment slack
 static size_t tc_smem_bytes(int N, int npw, int K, int c_in) {
     const int stage_bytes = 2 * N * 128;
@@ -956,7 +1059,7 @@ static size_t tc_smem_bytes(int N, int npw, int K, int c_in) {
 }
 constexpr size_t kTcMaxSmem = 227 * 1024;
 
-template <int N, int NPW, bool CAT, int CG = 1, bool PDL = false>
+template <int N, int NPW, bool SIN, bool SOUT>
 static int launch_tc_npw(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st,
@@ -964,7 +1067,7 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
     static_assert(TcBStages<N>::value == (N <= 32 ? 6 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
                   "tc_smem_bytes mirrors these");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
-    auto kern = conv_fwd_tc_kernel<N, NPW, CAT, CG, PDL>;
+    auto kern = conv_fwd_tc_kernel<N, NPW, SIN, SOUT>;
     // opt in to > 48 KB dynamic smem: the attribute is per device / context, so it is tracked per device (not a stream op)
     static size_t attr_set[64] = {0};
     int dev = 0;
@@ -980,42 +1083,21 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
         ctr = next_tile_counter();
         if (!ctr) return set_error(BTC_E_CUDA, "btc_sparse_conv_fwd_tc: tile counter symbol not available", cudaGetLastError());
     }
-    if (PDL) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(TcRoles<NPW>::kThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        BTC_CUDA(cudaLaunchKernelEx(&cfg, kern, feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap,
-                                    n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace, tile_mask, g_tc_dyn ? tile_order : nullptr),
-                 "conv_fwd_tc (programmatic dependent launch)");
-        return BTC_OK;
-    }
     kern<<<grid, TcRoles<NPW>::kThreads, smem, st>>>(feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows,
                                                      n_cap, n_dev, K, c_in, c_out, ctr, g_tc_diag, g_tc_trace, tile_mask,
-                                                     g_tc_dyn ? tile_order : nullptr);
+                                                     g_tc_dyn ? tile_order : nullptr, tiles);
     BTC_CHECK_LAUNCH("conv_fwd_tc");
     return BTC_OK;
 }
 
 // Tile variant knobs (A/B measurements and tests; defaults are the measured-best ones).  16 producer warps (four
-// groups) when shared memory allows (N <= 64), else 8; concatenated [B_hi|B_lo] MMAs (N <= 64) are off by default.
-// Dynamic tile scheduling (global counter) instead of a fixed round-robin.
-// Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_CAT=1, BTC_TC_DYN=0; btc_sparse_conv_tc_config() changes
-// them at run time.
+// groups) when shared memory allows (N <= 64), else 8.  Dynamic tile scheduling (global counter) instead of a fixed
+// round-robin.  Environment overrides at first use: BTC_TC_NPW=8, BTC_TC_DYN=0; btc_sparse_conv_tc_config() changes them
+// at run time.
 static void tc_config_init() {
     if (g_tc_npw == 0) {
         const char* e = getenv("BTC_TC_NPW");
         g_tc_npw = (e && atoi(e) == 8) ? 8 : 16;
-    }
-    if (g_tc_cat < 0) {
-        const char* e = getenv("BTC_TC_CAT");
-        g_tc_cat = (e && atoi(e) == 1) ? 1 : 0;   // measured: no gain from fewer MMA instructions (the issuer is not the limiter)
     }
     if (g_tc_dyn < 0) {
         const char* e = getenv("BTC_TC_DYN");
@@ -1023,30 +1105,16 @@ static void tc_config_init() {
     }
 }
 
-template <int N>
+template <int N, bool SIN, bool SOUT>
 static int launch_tc(const float* feat_in, const int* table, const float* packed_w, const float* bias,
                      const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                      const int* n_dev, int K, int c_in, int c_out, cudaStream_t st,
                      const unsigned long long* tile_mask, const int* tile_order) {
     tc_config_init();
-    constexpr int NS = N <= 64 ? N : 64;   // instantiation guard for the N <= 64 only variants
+    constexpr int NS = N <= 64 ? N : 64;   // instantiation guard for the N <= 64 only variant
 #define BTC_TC_ARGS feat_in, table, packed_w, bias, scale, shift, relu, feat_out, out_rows, n_cap, n_dev, K, c_in, c_out, st, tile_mask, tile_order
-    if (g_tc_pdl && !g_tc_cat && g_tc_cg == 1) {   // experimental programmatic dependent launch (default tile only)
-        if (N <= 64 && g_tc_npw == 16) return launch_tc_npw<NS, 16, false, 1, true>(BTC_TC_ARGS);
-        return launch_tc_npw<N, 8, false, 1, true>(BTC_TC_ARGS);
-    }
-    if (g_tc_cg > 1 && !g_tc_cat) {        // experimental commit groups (3-MMA k-steps only; 3 needs the six-stage ring)
-        constexpr int CG3 = TcAStages<N, false>::value % 3 == 0 ? 3 : 2;
-        if (N <= 64 && g_tc_npw == 16)
-            return g_tc_cg == 3 ? launch_tc_npw<NS, 16, false, CG3>(BTC_TC_ARGS) : launch_tc_npw<NS, 16, false, 2>(BTC_TC_ARGS);
-        return g_tc_cg == 3 ? launch_tc_npw<N, 8, false, CG3>(BTC_TC_ARGS) : launch_tc_npw<N, 8, false, 2>(BTC_TC_ARGS);
-    }
-    if (N <= 64 && g_tc_npw == 16) {
-        if (g_tc_cat) return launch_tc_npw<NS, 16, true>(BTC_TC_ARGS);
-        return launch_tc_npw<NS, 16, false>(BTC_TC_ARGS);
-    }
-    if (N <= 64 && g_tc_cat) return launch_tc_npw<NS, 8, true>(BTC_TC_ARGS);
-    return launch_tc_npw<N, 8, false>(BTC_TC_ARGS);
+    if (N <= 64 && g_tc_npw == 16) return launch_tc_npw<NS, 16, SIN, SOUT>(BTC_TC_ARGS);
+    return launch_tc_npw<N, 8, SIN, SOUT>(BTC_TC_ARGS);
 #undef BTC_TC_ARGS
 }
 
@@ -1065,23 +1133,13 @@ extern "C" {
 
 int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tiles) {
     tc_config_init();
+    if (concat_b > 0)
+        return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_tc_config: the concatenated [B_hi|B_lo] variant was measured (no gain) and removed", cudaSuccess);
     if (producer_warps >= 0) {
         if (producer_warps != 8 && producer_warps != 16) return badarg("btc_sparse_conv_tc_config: producer_warps must be 8 or 16");
         g_tc_npw = producer_warps;
     }
-    if (concat_b >= 0) g_tc_cat = concat_b ? 1 : 0;
     if (dynamic_tiles >= 0) g_tc_dyn = dynamic_tiles ? 1 : 0;
-    return BTC_OK;
-}
-
-int btc_sparse_conv_tc_commit_group(int stages) {
-    if (stages < 1 || stages > 3) return badarg("btc_sparse_conv_tc_commit_group: stages must be 1, 2 or 3");
-    g_tc_cg = stages;
-    return BTC_OK;
-}
-
-int btc_sparse_conv_tc_pdl(int on) {
-    g_tc_pdl = on ? 1 : 0;
     return BTC_OK;
 }
 
@@ -1127,13 +1185,63 @@ int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, voi
     return BTC_OK;
 }
 
+// ---- split (bf16 hi / lo) format ------------------------------------------------------------------------------------
+int btc_sparse_conv_tc_split_supported(int K, int c_in, int c_out, int in_split, int out_split) {
+    if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return 0;
+    if (in_split && c_in % 32 != 0) return 0;
+    if (out_split && c_out % 32 != 0) return 0;
+    return 1;
+}
+
+int64_t btc_sparse_conv_tc_split_packed_bytes(int K, int c_in, int c_out) {
+    if (!btc_sparse_conv_tc_split_supported(K, c_in, c_out, 1, 0)) return BTC_E_UNSUPPORTED;
+    const int N = tc_padded_n(c_out);
+    const int ntile = (K * c_in + 63) / 64;
+    return (int64_t)ntile * 2 * N * 128;
+}
+
+int btc_sparse_conv_tc_pack_split(const float* weight, int K, int c_in, int c_out, void* packed, void* stream) {
+    if (!weight || !packed) return badarg("btc_sparse_conv_tc_pack_split: null argument");
+    if (!btc_sparse_conv_tc_split_supported(K, c_in, c_out, 1, 0))
+        return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_tc_pack_split: shape not supported", cudaSuccess);
+    const int N = tc_padded_n(c_out);
+    const int ntile = (K * c_in + 63) / 64;
+    const int64_t total = (int64_t)ntile * N * 64;
+    tc_pack_weight_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, c_in, c_out, N,
+                                                                                       (unsigned short*)packed);
+    BTC_CHECK_LAUNCH("tc_pack_weight_split");
+    return BTC_OK;
+}
+
+int btc_features_to_split(const float* feat, int n_cap, const int* n_dev, int c, void* out, void* stream) {
+    if (n_cap < 0 || c < 32 || c % 32 != 0) return badarg("btc_features_to_split: channels must be a multiple of 32");
+    if (n_cap == 0) return BTC_OK;
+    if (!feat || !out) return badarg("btc_features_to_split: null argument");
+    features_to_split_kernel<<<grid_for((int64_t)n_cap * c / 2, 256), 256, 0, (cudaStream_t)stream>>>(feat, n_cap, n_dev, c,
+                                                                                                     (uint32_t*)out);
+    BTC_CHECK_LAUNCH("features_to_split");
+    return BTC_OK;
+}
+
+int btc_features_from_split(const void* feat_split, int n_cap, const int* n_dev, int c, float* out, void* stream) {
+    if (n_cap < 0 || c < 32 || c % 32 != 0) return badarg("btc_features_from_split: channels must be a multiple of 32");
+    if (n_cap == 0) return BTC_OK;
+    if (!feat_split || !out) return badarg("btc_features_from_split: null argument");
+    features_from_split_kernel<<<grid_for((int64_t)n_cap * c / 2, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint32_t*)feat_split, n_cap, n_dev, c, out);
+    BTC_CHECK_LAUNCH("features_from_split");
+    return BTC_OK;
+}
+
 static int fwd_tc(const char* who, const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
                   const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_out_cap,
                   const int* n_out_dev, int K, int c_in, int c_out, void* stream,
-                  const unsigned long long* tile_mask = nullptr, const int* tile_order = nullptr) {
+                  const unsigned long long* tile_mask = nullptr, const int* tile_order = nullptr, int in_split = 0,
+                  int out_split = 0) {
     (void)who;
     if ((scale == nullptr) != (shift == nullptr)) return badarg("btc_sparse_conv_fwd_tc: scale/shift must come together");
-    if (!btc_sparse_conv_tc_supported(K, c_in, c_out)) return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_fwd_tc: shape not supported", cudaSuccess);
+    if (!btc_sparse_conv_tc_split_supported(K, c_in, c_out, in_split, out_split))
+        return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_fwd_tc: shape not supported", cudaSuccess);
     if (n_out_cap <= 0) return BTC_OK;   // empty output (null data pointers of 0-row tensors are fine)
     if (!nbr_out || !packed_weight || !feat_out) return badarg("btc_sparse_conv_fwd_tc: null argument");
     if (!feat_in) return badarg("btc_sparse_conv_fwd_tc: null feat_in");
@@ -1141,11 +1249,22 @@ static int fwd_tc(const char* who, const float* feat_in, const int* nbr_out, con
         return badarg("btc_sparse_conv_fwd_tc: pointers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const float* pw = (const float*)packed_weight;
+#define BTC_TC_CALL(NN, SI, SO) \
+    launch_tc<NN, SI, SO>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order)
+#define BTC_TC_FMT(NN)                                              \
+    do {                                                            \
+        if (in_split && out_split) return BTC_TC_CALL(NN, true, true);   \
+        if (in_split) return BTC_TC_CALL(NN, true, false);          \
+        if (out_split) return BTC_TC_CALL(NN, false, true);         \
+        return BTC_TC_CALL(NN, false, false);                       \
+    } while (0)
     switch (tc_padded_n(c_out)) {
-        case 32: return launch_tc<32>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order);
-        case 64: return launch_tc<64>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order);
-        case 128: return launch_tc<128>(feat_in, nbr_out, pw, bias, scale, shift, relu, feat_out, out_rows, n_out_cap, n_out_dev, K, c_in, c_out, st, tile_mask, tile_order);
+        case 32: BTC_TC_FMT(32);
+        case 64: BTC_TC_FMT(64);
+        case 128: BTC_TC_FMT(128);
     }
+#undef BTC_TC_FMT
+#undef BTC_TC_CALL
     return BTC_E_UNSUPPORTED;
 }
 
@@ -1164,6 +1283,20 @@ int btc_sparse_conv_fwd_tc_meta(const float* feat_in, const int* nbr_out, const 
                   n_out_cap, n_out_dev, K, c_in, c_out, stream, (const unsigned long long*)tile_mask, tile_order);
 }
 
+int btc_sparse_conv_fwd_tc_split(const void* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
+                                 const float* scale, const float* shift, int relu, void* feat_out, int n_out_cap,
+                                 const int* n_out_dev, int K, int c_in, int c_out, int in_split, int out_split,
+                                 const uint64_t* tile_mask, const int* tile_order, void* stream) {
+    return fwd_tc("btc_sparse_conv_fwd_tc_split", (const float*)feat_in, nbr_out, packed_weight, bias, scale, shift, relu,
+                  (float*)feat_out, nullptr, n_out_cap, n_out_dev, K, c_in, c_out, stream, (const unsigned long long*)tile_mask,
+                  tile_order, in_split ? 1 : 0, out_split ? 1 : 0);
+}
+
+int64_t btc_rulebook_tile_order_ints(int n_out_cap) {
+    const int64_t tiles = (n_out_cap + TC_BM - 1) / TC_BM;
+    return 65 + 65 * (tiles > 0 ? tiles : 1);
+}
+
 int btc_rulebook_tile_meta(const int* nbr_out, int n_out_cap, const int* n_out_dev, int K, uint64_t* tile_mask,
                            int* tile_order, void* stream) {
     if (K < 1 || K > 64 || n_out_cap < 0) return badarg("btc_rulebook_tile_meta: bad sizes");
@@ -1171,18 +1304,10 @@ int btc_rulebook_tile_meta(const int* nbr_out, int n_out_cap, const int* n_out_d
     if (!nbr_out || !tile_mask) return badarg("btc_rulebook_tile_meta: null argument");
     const int tiles = (n_out_cap + TC_BM - 1) / TC_BM;
     cudaStream_t st = (cudaStream_t)stream;
-    int* ticket = tile_meta_ticket();
-    if (!ticket) return set_error(BTC_E_CUDA, "btc_rulebook_tile_meta: ticket symbol not available", cudaGetLastError());
-    tile_meta_kernel<<<tiles, 128, 0, st>>>(nbr_out, n_out_cap, n_out_dev, K, (unsigned long long*)tile_mask, tile_order, ticket);
+    if (tile_order) BTC_CUDA(cudaMemsetAsync(tile_order, 0, 65 * sizeof(int), st), "tile_meta memset");
+    const int grid = tiles < kNumSM * 16 ? tiles : kNumSM * 16;
+    tile_meta_kernel<<<grid, 128, 0, st>>>(nbr_out, n_out_cap, n_out_dev, K, (unsigned long long*)tile_mask, tile_order, tiles);
     BTC_CHECK_LAUNCH("tile_meta");
-    return BTC_OK;
-}
-
-int btc_rulebook_tile_order(const uint64_t* tile_mask, int n_out_cap, const int* n_out_dev, int* tile_order, void* stream) {
-    if (n_out_cap <= 0) return BTC_OK;
-    if (!tile_mask || !tile_order) return badarg("btc_rulebook_tile_order: null argument");
-    tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const unsigned long long*)tile_mask, n_out_cap, n_out_dev, tile_order);
-    BTC_CHECK_LAUNCH("tile_order");
     return BTC_OK;
 }
 

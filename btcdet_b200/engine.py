@@ -60,7 +60,7 @@ class BackbonePlan:
 
     def __init__(self, layer_specs, sparse_shape, batch, max_points_total, voxel_size, point_range, max_points=5,
                  max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=False, side_priority=0,
-                 tile_meta=True):
+                 tile_meta=True, split_format=True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.batch = int(batch)
@@ -77,6 +77,18 @@ class BackbonePlan:
         # per-rulebook tile masks + heaviest-first tile order for the tcgen05 tile (btc_rulebook_tile_meta)
         self.tile_meta = bool(tile_meta)
         self._meta = {}
+        # split (bf16 hi / lo) feature format between consecutive tcgen05 layers (include/btcdet_b200.h): a layer writes it
+        # when the next layer can gather it (c % 32 == 0 on both sides), the last layer always writes fp32
+        specs = list(layer_specs)
+        use_tc = [self.algo != 1 and not self.sort_rows and
+                  ops.tc_supported(c.kernel_size[0] * c.kernel_size[1] * c.kernel_size[2], c.in_channels, c.out_channels)
+                  for c, _ in specs]
+        self._fmt = []
+        for li, (c, _) in enumerate(specs):
+            in_split = bool(self._fmt and self._fmt[-1][1])
+            out_split = bool(split_format and use_tc[li] and li + 1 < len(specs) and use_tc[li + 1] and
+                             c.out_channels % 32 == 0 and specs[li + 1][0].in_channels == c.out_channels)
+            self._fmt.append((in_split, out_split))
         dev = self.device
         B = self.batch
         # ---- static input + voxelisation buffers ------------------------------------------
@@ -100,8 +112,9 @@ class BackbonePlan:
         self._ws = {}
         cur_feat, cur_lvl = self.feat0, lvl
         self.params = []  # keep folded tensors alive
-        for conv, bn in layer_specs:
+        for li, (conv, bn) in enumerate(specs):
             assert isinstance(conv, spconv.SparseConvolution) and conv.ndim == 3 and not conv.inverse
+            in_split, out_split = self._fmt[li]
             K = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
             key = conv.indice_key
             rb = self.rulebooks.get(key) if key is not None else None
@@ -149,7 +162,7 @@ class BackbonePlan:
             # wide layers run on the tcgen05 tile (weights packed once into the UMMA operand image)
             packed = None
             if self.algo != 1 and ops.tc_supported(K, conv.in_channels, conv.out_channels):
-                packed = ops.tc_pack_weight(w)
+                packed = ops.tc_pack_weight_split(w) if in_split else ops.tc_pack_weight(w)
             self.params.append((w, bias, scale, shift, packed))
             meta = self._meta.get(id(nbr)) if packed is not None else None
             rows = None
@@ -160,7 +173,7 @@ class BackbonePlan:
                     self._sorted[id(nbr)] = rows
                     self.steps.append(_Step("sort_rb", (nbr, out_lvl, rows[0], rows[1])))
             self.steps.append(_Step("conv", (cur_feat, nbr, w, bias, scale, shift, bn is not None, out_feat, out_lvl, K,
-                                             conv.in_channels, conv.out_channels, packed, rows, meta)))
+                                             conv.in_channels, conv.out_channels, packed, rows, meta, (in_split, out_split))))
             cur_feat, cur_lvl = out_feat, out_lvl
         self.out_feat, self.out_lvl = cur_feat, cur_lvl
         # sparse clear of every sorted level's bitmaps right after their last reader (the rulebook that built them or a
@@ -188,7 +201,8 @@ class BackbonePlan:
 
     def _new_meta(self, nbr):
         tiles = (nbr.shape[0] + 127) // 128
-        meta = (torch.zeros(tiles, dtype=torch.int64, device=self.device), torch.zeros(tiles, dtype=torch.int32, device=self.device))
+        meta = (torch.zeros(tiles, dtype=torch.int64, device=self.device),
+                torch.zeros(int(self.lib.btc_rulebook_tile_order_ints(nbr.shape[0])), dtype=torch.int32, device=self.device))
         self._meta[id(nbr)] = meta
         return meta
 
@@ -305,12 +319,13 @@ class BackbonePlan:
 
     def launch_conv(self, args, st):
         """One sparse-conv layer: tcgen05 tile when the weights were packed, fp32 FFMA tile otherwise."""
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = args
-        if packed is not None and meta is not None:
-            check(self.lib.btc_sparse_conv_fwd_tc_meta(_ptr(fin), _ptr(nbr), _ptr(packed), _ptr(bias), _ptr(scale),
-                                                       _ptr(shift), int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K,
-                                                       cin, cout, _ptr(meta[0]), _ptr(meta[1]), st),
-                  "btc_sparse_conv_fwd_tc_meta")
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta, fmt = args
+        if packed is not None and rows is None:
+            tm, to = (None, None) if meta is None else meta
+            check(self.lib.btc_sparse_conv_fwd_tc_split(_ptr(fin), _ptr(nbr), _ptr(packed), _ptr(bias), _ptr(scale),
+                                                        _ptr(shift), int(relu), _ptr(fout), lout.cap, _ptr(lout.n_dev), K,
+                                                        cin, cout, int(fmt[0]), int(fmt[1]), _ptr(tm), _ptr(to), st),
+                  "btc_sparse_conv_fwd_tc_split")
         elif packed is not None and rows is not None:
             check(self.lib.btc_sparse_conv_fwd_tc_rows(_ptr(fin), _ptr(rows[0]), _ptr(rows[1]), _ptr(packed), _ptr(bias),
                                                        _ptr(scale), _ptr(shift), int(relu), _ptr(fout), lout.cap,

@@ -268,19 +268,66 @@ def tc_supported(K, c_in, c_out):
 
 def tc_config(producer_warps=-1, concat_b=-1, dynamic_tiles=-1):
     """Process-wide variant knobs of the tcgen05 tile (A/B measurements, tests); -1 keeps a setting.
-    Defaults: 16 producer warps, three MMAs per k-step (no [B_hi|B_lo] concatenation), dynamic tile scheduling."""
+    Defaults: 16 producer warps, dynamic tile scheduling.  concat_b must stay 0 / -1 (variant removed, no gain measured)."""
     check(_lib.load().btc_sparse_conv_tc_config(int(producer_warps), int(concat_b), int(dynamic_tiles)),
           "btc_sparse_conv_tc_config")
 
 
-def tc_commit_group(stages=1):
-    """EXPERIMENTAL: one tcgen05.commit per group of `stages` ring stages (1 = verified default)."""
-    check(_lib.load().btc_sparse_conv_tc_commit_group(int(stages)), "btc_sparse_conv_tc_commit_group")
+def tc_split_supported(K, c_in, c_out, in_split, out_split):
+    return bool(_lib.load().btc_sparse_conv_tc_split_supported(int(K), int(c_in), int(c_out), int(bool(in_split)),
+                                                               int(bool(out_split))))
 
 
-def tc_pdl(on=False):
-    """EXPERIMENTAL: programmatic dependent launch of the tcgen05 tile (off = verified default)."""
-    check(_lib.load().btc_sparse_conv_tc_pdl(int(bool(on))), "btc_sparse_conv_tc_pdl")
+def tc_pack_weight_split(weight):
+    """Pack [K,Cin,Cout] fp32 weights for a SPLIT-input layer (bf16 hi / lo tiles of 64 reduction elements)."""
+    lib = _lib.load()
+    _require_cuda(weight)
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    K = weight.numel() // (c_in * c_out)
+    nbytes = int(lib.btc_sparse_conv_tc_split_packed_bytes(K, c_in, c_out))
+    if nbytes < 0:
+        raise _lib.BtcError("split-format tile does not support K=%d Cin=%d Cout=%d" % (K, c_in, c_out))
+    weight = weight.detach().to(torch.float32).contiguous()
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    check(lib.btc_sparse_conv_tc_pack_split(_ptr(weight), K, c_in, c_out, _ptr(packed), _stream()), "btc_sparse_conv_tc_pack_split")
+    return packed
+
+
+def features_to_split(features, n_dev=None):
+    """fp32 rows [N, C] (C % 32 == 0) -> split rows (same shape / bytes, float32-typed storage of packed bf16 hi / lo)."""
+    _require_cuda(features)
+    features = features.to(torch.float32).contiguous()
+    out = torch.empty_like(features)
+    check(_lib.load().btc_features_to_split(_ptr(features), features.shape[0], _ptr(n_dev), features.shape[1], _ptr(out),
+                                            _stream()), "btc_features_to_split")
+    return out
+
+
+def features_from_split(split, n_dev=None):
+    _require_cuda(split)
+    split = split.contiguous()
+    out = torch.empty_like(split)
+    check(_lib.load().btc_features_from_split(_ptr(split), split.shape[0], _ptr(n_dev), split.shape[1], _ptr(out), _stream()),
+          "btc_features_from_split")
+    return out
+
+
+def sparse_conv_fwd_tc_split(features, nbr_out, packed_weight, c_in, c_out, in_split, out_split, bias=None, scale=None,
+                             shift=None, relu=False, n_out_dev=None, out=None, tile_mask=None, tile_order=None):
+    """tcgen05 gather-GEMM with the split (bf16 hi / lo) feature format on the input and / or output side.
+    packed_weight: tc_pack_weight_split(w) when in_split else tc_pack_weight(w)."""
+    _require_cuda(features, nbr_out, packed_weight)
+    lib = _lib.load()
+    n_out, K = nbr_out.shape
+    features, nbr_out = features.contiguous(), nbr_out.contiguous()
+    assert features.dtype == torch.float32 and features.shape[1] == c_in
+    if out is None:
+        out = torch.empty((n_out, c_out), dtype=torch.float32, device=features.device)
+    check(lib.btc_sparse_conv_fwd_tc_split(_ptr(features), _ptr(nbr_out), _ptr(packed_weight), _ptr(bias), _ptr(scale),
+                                           _ptr(shift), int(bool(relu)), _ptr(out), n_out, _ptr(n_out_dev), K, int(c_in),
+                                           int(c_out), int(bool(in_split)), int(bool(out_split)), _ptr(tile_mask),
+                                           _ptr(tile_order), _stream()), "btc_sparse_conv_fwd_tc_split")
+    return out
 
 
 def tc_pack_weight(weight):
@@ -372,7 +419,9 @@ class SparseConvFunction(torch.autograd.Function):
     """indice_conv of spconv.ops with autograd (forward + dX + dW + db on the CUDA library).
 
     algo: 0 = auto (tcgen05 3xTF32 tile when the shape qualifies, fp32 FFMA tile otherwise), 1 = FFMA, 2 = tcgen05.
-    The backward kernels are fp32 FFMA / atomics in every mode."""
+    Backward: dX is the same gather-GEMM over the transposed relation — the sub-manifold table read with the mirrored
+    offsets W'[k] = W[K-1-k]^T, or nbr_in with W[k]^T for strided / transposed layers — and runs on the tcgen05 tile
+    whenever that shape qualifies (algo != 1); dW / db are fp32 outer products with atomics."""
 
     @staticmethod
     def forward(ctx, features, weight, bias, rulebook: Rulebook, algo):
@@ -391,6 +440,7 @@ class SparseConvFunction(torch.autograd.Function):
         ctx.save_for_backward(features, weight)
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
+        ctx.algo = algo
         return out
 
     @staticmethod
@@ -400,8 +450,19 @@ class SparseConvFunction(torch.autograd.Function):
         d_out = d_out.contiguous()
         d_feat = d_w = d_b = None
         if ctx.needs_input_grad[0]:
-            table, mirror = (rb.nbr_out, True) if rb.subm else (rb.nbr_in, False)
-            d_feat = sparse_conv_bwd_data(d_out, table, mirror, weight, features.shape[0])
+            c_in, c_out = weight.shape[-2], weight.shape[-1]
+            n_in = features.shape[0]
+            if ctx.algo != 1 and n_in > 0 and d_out.shape[0] > 0 and tc_supported(rb.K, c_out, c_in) \
+                    and d_out.data_ptr() % 16 == 0:
+                wk = weight.detach().reshape(rb.K, c_in, c_out)
+                if rb.subm:     # nbr_out[o][k] = i  <=>  nbr_out[i][K-1-k] = o
+                    table, wb = rb.nbr_out, wk.flip(0).transpose(1, 2).contiguous()
+                else:
+                    table, wb = rb.nbr_in, wk.transpose(1, 2).contiguous()
+                d_feat = sparse_conv_fwd_tc(d_out, table, tc_pack_weight(wb), c_out, c_in)
+            else:
+                table, mirror = (rb.nbr_out, True) if rb.subm else (rb.nbr_in, False)
+                d_feat = sparse_conv_bwd_data(d_out, table, mirror, weight, n_in)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             d_w, d_b = sparse_conv_bwd_weight(features, d_out, rb.nbr_out, tuple(weight.shape), ctx.has_bias)
         return d_feat, d_w, d_b, None, None

@@ -197,9 +197,6 @@ int btc_rulebook_conv(const int* coords_in, int n_in_cap, const int* n_in_dev,
                       int* nbr_out, int* nbr_in,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Heaviest-first order of the live tiles from their masks (see btc_rulebook_tile_meta): one small launch. */
-int btc_rulebook_tile_order(const uint64_t* tile_mask, int n_out_cap, const int* n_out_dev, int* tile_order, void* stream);
-
 /*
  * Sparse two-level build of a strided / transposed rulebook (same results as btc_rulebook_conv, bit for bit).
  * `summary` [btc_index_summary_words(out_entries)] u32 holds one bit per 32-cell word of `out_index`; BOTH bitmaps must
@@ -273,10 +270,9 @@ int btc_sparse_conv_fwd(const float* feat_in, const int* nbr_out,
  */
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out);
 /* Tile-variant knobs for A/B measurements and tests (process-wide; -1 keeps a setting): producer_warps 8 | 16
- * (16 needs c_out <= 64), concat_b 0 | 1 = issue A_hi x [B_hi|B_lo] as one MMA of width 2N (c_out <= 64),
- * dynamic_tiles 0 | 1 = persistent CTAs fetch 128-row tiles from a global counter instead of a fixed round-robin.
- * Results of the variants agree to fp32 rounding (the order of the three 3xTF32 partial sums differs with concat_b;
- * dynamic_tiles does not change any result bit). */
+ * (16 needs c_out <= 64), dynamic_tiles 0 | 1 = persistent CTAs fetch 128-row tiles from a global counter instead of a
+ * fixed round-robin (no result bit changes).  concat_b must be 0 or -1: the concatenated [B_hi|B_lo] variant of round 1
+ * was measured on hardware (no gain, profiles/r2_battery.json) and removed; 1 returns BTC_E_UNSUPPORTED. */
 int btc_sparse_conv_tc_config(int producer_warps, int concat_b, int dynamic_tiles);
 /* Timing diagnostics for the profile write-ups (tools/step_breakdown.py --diag): a non-zero mask makes the tile skip a
  * part of its work — bit 0 the gather, bit 1 the smem read-back / hi-lo split / TMEM stores, bit 2 two of the three
@@ -291,14 +287,6 @@ int btc_sparse_conv_tc_trace(void* trace_u64);
 /* Cap on the persistent grid of the tcgen05 tile (default 148 = one CTA per SM): a smaller grid leaves whole SMs to
  * kernels running concurrently on other streams (the rulebook chain of the engine).  Process-wide. */
 int btc_sparse_conv_tc_grid(int max_ctas);
-/* EXPERIMENTAL (not verified on hardware in round 1; default 1 = the verified path, whose machine code is unchanged):
- * release the operand-ring stages in groups of `stages` (1, 2 or 3; 3 falls back to 2 where the ring has four slots)
- * with one tcgen05.commit per group instead of one per stage.  Process-wide. */
-int btc_sparse_conv_tc_commit_group(int stages);
-/* EXPERIMENTAL (not verified on hardware in round 1; default 0): launch the tile with programmatic stream serialisation —
- * prologue, first index tile and weight prefetch of a layer run under the tail of the previous kernel in the stream; the
- * first gather waits for it (griddepcontrol.wait).  Applies to the default tile (3-MMA k-steps, commit group 1). */
-int btc_sparse_conv_tc_pdl(int on);
 int64_t btc_sparse_conv_tc_packed_bytes(int K, int c_in, int c_out);
 int btc_sparse_conv_tc_pack(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
 int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void* packed_weight,
@@ -318,14 +306,35 @@ int btc_sparse_conv_fwd_tc(const float* feat_in, const int* nbr_out, const void*
 int btc_rulebook_sort_rows(const int* nbr_out, int n_cap, const int* n_dev, int K, int* nbr_sorted, int* out_rows,
                            void* stream);
 /*
+ * Split feature format (round 2): the same 4*C bytes per row, every value stored as two bfloat16, x = hi + lo with
+ * hi = bf16_rn(x), lo = bf16_rn(x - hi) (|x - hi - lo| <= 2^-17 |x|); per 32 channels the row holds [32 x hi | 32 x lo].
+ * A layer whose INPUT is in split format (c_in % 32 == 0) gathers the packed operands as they are (no per-stage ALU work)
+ * and runs three bf16 MMAs of K = 16 per k-step instead of three tf32 MMAs of K = 8; a layer whose OUTPUT is split
+ * (c_out % 32 == 0) writes the format from its epilogue.  Weights for a split-input layer are packed by
+ * btc_sparse_conv_tc_pack_split (bf16 hi / lo tiles of 64 reduction elements).  btc_features_to_split / _from_split
+ * convert whole feature matrices (tests, or a consumer that needs fp32).  Accuracy: ~2^-16 per product, inside the 1e-4
+ * parity bar (tests/test_parity_gpu.py).  in_split / out_split = 0 reproduces btc_sparse_conv_fwd_tc_meta.
+ */
+int btc_sparse_conv_tc_split_supported(int K, int c_in, int c_out, int in_split, int out_split);
+int64_t btc_sparse_conv_tc_split_packed_bytes(int K, int c_in, int c_out);
+int btc_sparse_conv_tc_pack_split(const float* weight, int K, int c_in, int c_out, void* packed, void* stream);
+int btc_features_to_split(const float* feat, int n_cap, const int* n_dev, int c, void* out, void* stream);
+int btc_features_from_split(const void* feat_split, int n_cap, const int* n_dev, int c, float* out, void* stream);
+int btc_sparse_conv_fwd_tc_split(const void* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,
+                                 const float* scale, const float* shift, int relu, void* feat_out, int n_out_cap,
+                                 const int* n_out_dev, int K, int c_in, int c_out, int in_split, int out_split,
+                                 const uint64_t* tile_mask, const int* tile_order, void* stream);
+/*
  * Per-tile metadata of a neighbour table for the tcgen05 tile (tiles = 128 consecutive rows):
  *   tile_mask  [ceil(n_out_cap / 128)] u64: bit k set iff a live row of the tile has a neighbour through offset k
  *              (the block-skipping mask the tile otherwise derives from its staged index block, ~2.5 us per tile);
- *   tile_order [ceil(n_out_cap / 128)] i32 or NULL: the live tiles by descending number of active offsets — the dynamic
- *              tile scheduler hands tiles out in this order, so a launch ends on its cheapest tiles (no long tail).
- * Built once per rulebook (2 launches), shared by every layer that uses the table.  K <= 64.
+ *   tile_order [btc_rulebook_tile_order_ints(n_out_cap)] i32 or NULL: the live tiles bucketed by cost class (number of
+ *              active offsets): 65 class counts followed by 65 buckets of tile ids.  The dynamic tile scheduler hands
+ *              tiles out heaviest class first, so a launch ends on its cheapest tiles (no long tail).
+ * Built once per rulebook (one launch, no CTA waits for another), shared by every layer that uses the table.  K <= 64.
  * btc_sparse_conv_fwd_tc_meta = btc_sparse_conv_fwd_tc with the two arrays (either may be NULL); results are identical.
  */
+int64_t btc_rulebook_tile_order_ints(int n_out_cap);
 int btc_rulebook_tile_meta(const int* nbr_out, int n_out_cap, const int* n_out_dev, int K, uint64_t* tile_mask,
                            int* tile_order, void* stream);
 int btc_sparse_conv_fwd_tc_meta(const float* feat_in, const int* nbr_out, const void* packed_weight, const float* bias,

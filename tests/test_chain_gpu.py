@@ -37,9 +37,6 @@ def _model(seed=0):
         if hasattr(mod, "reset_parameters") and not isinstance(mod, torch.nn.BatchNorm1d):
             mod.reset_parameters()
     backbones.randomize_bn_(m, seed)
-    # an untrained head predicts ~0.5 everywhere: bias the occupied class down so that a realistic few thousand cells pass
-    with torch.no_grad():
-        m.occ_head.conv_cls[0].bias.copy_(torch.tensor([1.2, -1.2]))
     return m.cuda().eval()
 
 
@@ -50,6 +47,7 @@ def test_chain_stagewise_against_oracle(cuda, oracle):
     geo = occ_masks.OccGeometry()
     model = _model()
     bd = chain.synthetic_batch([11, 12], n_points=20000, with_rot=True, mode="test")
+    chain.calibrate_occ_head_bias(model, bd, 0.03)      # an untrained head would pass nothing (or everything)
     inp = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in bd.items()}
     with torch.no_grad():
         out = model(bd)
@@ -127,6 +125,7 @@ def test_chain_against_the_reference_modules_on_cuda(cuda, oracle):
     Cfg = ref_loader.Cfg
     model = _model(1)
     bd = chain.synthetic_batch([21, 22], n_points=20000, with_rot=True, mode="test")
+    chain.calibrate_occ_head_bias(model, bd, 0.03)
     inp = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in bd.items()}
     with torch.no_grad():
         out = model(bd)

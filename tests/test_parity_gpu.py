@@ -272,7 +272,7 @@ def test_tensor_core_multi_tile_persistent(cuda, n_out, K, cin, cout, density, r
     assert torch.equal(out2, out)
 
 
-@pytest.mark.parametrize("npw,cat,dyn", [(16, 1, 1), (16, 0, 1), (16, 1, 0), (8, 1, 1), (8, 0, 0), (16, 0, 0)])
+@pytest.mark.parametrize("npw,cat,dyn", [(16, 0, 1), (8, 0, 1), (8, 0, 0), (16, 0, 0)])
 @pytest.mark.parametrize("n_out,K,cin,cout,density,run", [
     (45000, 27, 32, 32, 0.27, 97), (33000, 27, 64, 64, 0.35, 300), (70000, 27, 16, 16, 0.03, 1024),
     (21000, 3, 64, 128, 0.45, 97), (130, 27, 32, 64, 0.2, 7)])
@@ -312,75 +312,6 @@ def test_tensor_core_tile_variants(cuda, npw, cat, dyn, n_out, K, cin, cout, den
         ops.sparse_conv_fwd_tc(feat, table, packed, cin, cout, bias, n_out_dev=n_dev, out=static)
         assert torch.equal(static, outs[0])
     finally:
-        ops.tc_config(16, 0, 1)
-
-
-@pytest.mark.skipif(os.environ.get("BTC_TEST_EXPERIMENTAL") != "1",
-                    reason="commit groups > 1 are not verified on hardware yet (DESIGN.md §8.1(0)); set BTC_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("cg,npw", [(2, 16), (3, 16), (2, 8)])
-@pytest.mark.parametrize("n_out,K,cin,cout,density,run", [
-    (45000, 27, 32, 32, 0.27, 97), (33000, 27, 64, 64, 0.35, 300), (70000, 27, 16, 16, 0.03, 1024),
-    (21000, 3, 64, 128, 0.45, 97), (130, 27, 32, 64, 0.2, 7)])
-def test_tensor_core_commit_groups_experimental(cuda, cg, npw, n_out, K, cin, cout, density, run):
-    """One tcgen05.commit per 2 / 3 stages: bit-identical to the per-stage-commit tile (same MMAs, same order)."""
-    from btcdet_b200 import ops
-    rng = np.random.default_rng(n_out + K + cin)
-    n_in = 40000
-    pat = rng.random((64, K)) < density
-    valid = pat[(np.arange(n_out) // run) % 64] ^ (rng.random((n_out, K)) < 0.01)
-    valid[:, K // 2] |= ~valid.any(1)
-    nbr = torch.from_numpy(np.where(valid, rng.integers(0, n_in, (n_out, K)), -1).astype(np.int32)).cuda()
-    n_dev = torch.tensor([n_out], dtype=torch.int32, device="cuda")
-    feat = torch.from_numpy(rng.standard_normal((n_in, cin)).astype(np.float32)).cuda()
-    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32)).cuda()
-    packed = ops.tc_pack_weight(w)
-    try:
-        ops.tc_config(npw, 0, 1)
-        ref = torch.zeros((n_out, cout), device="cuda")
-        ops.sparse_conv_fwd_tc(feat, nbr, packed, cin, cout, None, n_out_dev=n_dev, out=ref)
-        ops.tc_commit_group(cg)
-        for rep in range(2):
-            out = torch.zeros((n_out, cout), device="cuda")
-            ops.sparse_conv_fwd_tc(feat, nbr, packed, cin, cout, None, n_out_dev=n_dev, out=out)
-            torch.cuda.synchronize()
-            assert torch.equal(out, ref)
-    finally:
-        ops.tc_commit_group(1)
-        ops.tc_config(16, 0, 1)
-
-
-@pytest.mark.skipif(os.environ.get("BTC_TEST_EXPERIMENTAL") != "1",
-                    reason="programmatic dependent launch is not verified on hardware yet (DESIGN.md §8.1); set BTC_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("npw", [16, 8])
-def test_tensor_core_pdl_chain_experimental(cuda, npw):
-    """Four dependent layers launched back to back with programmatic stream serialisation: every layer's first gather
-    must wait for the previous layer (griddepcontrol.wait) — results identical to ordinary launches, repeatedly."""
-    from btcdet_b200 import ops
-    rng = np.random.default_rng(5)
-    n, K, c = 60000, 27, 64
-    valid = rng.random((n, K)) < 0.3
-    valid[:, K // 2] = True
-    nbr = torch.from_numpy(np.where(valid, rng.integers(0, n, (n, K)), -1).astype(np.int32)).cuda()
-    x0 = torch.from_numpy(rng.standard_normal((n, c)).astype(np.float32)).cuda()
-    ws = [ops.tc_pack_weight(torch.from_numpy((rng.standard_normal((K, c, c)) * 0.05).astype(np.float32)).cuda())
-          for _ in range(4)]
-
-    def chain():
-        x = x0
-        for pk in ws:
-            x = ops.sparse_conv_fwd_tc(x, nbr, pk, c, c, relu=True)
-        return x
-    try:
-        ops.tc_config(npw, 0, 1)
-        ref = chain()
-        torch.cuda.synchronize()
-        ops.tc_pdl(True)
-        for rep in range(3):
-            got = chain()
-            torch.cuda.synchronize()
-            assert torch.equal(got, ref)
-    finally:
-        ops.tc_pdl(False)
         ops.tc_config(16, 0, 1)
 
 
@@ -434,7 +365,9 @@ def test_sparse_conv_backward_matches_oracle_autograd(cuda, oracle):
     coords = _scene_coords(oracle, 40, n=3000)
     shape = [41, 1600, 1408]
     rng = np.random.default_rng(0)
-    for kind, cin, cout in [("subm", 16, 32), ("conv", 32, 16), ("conv", 6, 20)]:
+    for kind, cin, cout, algo in [("subm", 16, 32, 1), ("conv", 32, 16, 1), ("conv", 6, 20, 1),
+                                  ("subm", 32, 32, 0), ("subm", 64, 64, 0), ("conv", 32, 64, 0), ("conv", 64, 128, 0)]:
+        # algo 0: forward and dX on the tcgen05 tile (3xTF32), dW / db on the fp32 kernels
         if kind == "subm":
             outids, pairs, pair_num, _ = oracle.get_indice_pairs(coords, 1, shape, 3, subm=True)
             rb = ops.rulebook_subm(torch.from_numpy(coords).cuda(), 1, shape, 3)
@@ -454,7 +387,7 @@ def test_sparse_conv_backward_matches_oracle_autograd(cuda, oracle):
                 out = out.index_add(0, pr[1, k, :nh], f1[pr[0, k, :nh]] @ w1[k])
         (out + b1).backward(go)
         f2, w2, b2 = (t.clone().cuda().requires_grad_() for t in (feat, w, b))
-        y = ops.SparseConvFunction.apply(f2, w2, b2, rb, 1)
+        y = ops.SparseConvFunction.apply(f2, w2, b2, rb, algo)
         y.backward(go.cuda())
         assert rel_err(f2.grad.cpu().numpy(), f1.grad.numpy()) < REL_TOL
         assert rel_err(w2.grad.cpu().numpy(), w1.grad.numpy()) < REL_TOL
@@ -515,3 +448,54 @@ def test_revoxelize_sorted_matches_torch_unique(cuda):
         ref[v, s] = feat[i]
         seen[v] = s + 1
     assert torch.equal(vox.cpu(), ref)
+
+
+@pytest.mark.parametrize("n_out,K,cin,cout,density,run", [
+    (45000, 27, 32, 32, 0.27, 97), (33000, 27, 64, 64, 0.35, 300), (21000, 3, 64, 128, 0.45, 97), (130, 27, 32, 64, 0.2, 7),
+    (52000, 27, 128, 64, 0.2, 50), (9000, 27, 32, 128, 0.3, 11)])
+def test_tensor_core_split_format(cuda, n_out, K, cin, cout, density, run):
+    """Split (bf16 hi / lo) feature format on the input and / or output side of the tcgen05 tile against the fp32 FFMA tile:
+    every combination inside the 1e-4 bar; conversion round trip to 2^-16."""
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(n_out + K + cin + cout)
+    n_in = 40000
+    pat = rng.random((64, K)) < density
+    valid = pat[(np.arange(n_out) // run) % 64] ^ (rng.random((n_out, K)) < 0.01)
+    valid[:, K // 2] |= ~valid.any(1)
+    nbr = torch.from_numpy(np.where(valid, rng.integers(0, n_in, (n_out, K)), -1).astype(np.int32)).cuda()
+    n_dev = torch.tensor([n_out], dtype=torch.int32, device="cuda")
+    feat = torch.from_numpy((rng.standard_normal((n_in, cin)) * np.exp(rng.uniform(-3, 3, (n_in, 1)))).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((K, cin, cout)) * 0.1).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).cuda()
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)).cuda()
+    shift = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).cuda()
+    want = ops.sparse_conv_fwd(feat, nbr, w, bias, scale, shift, relu=True, algo=1).cpu().numpy()
+    fs = ops.features_to_split(feat)
+    back = ops.features_from_split(fs)
+    assert float(((back - feat).abs() / feat.abs().clamp_min(1e-30)).max()) <= 2.0 ** -16
+    pk32, pks = ops.tc_pack_weight(w), ops.tc_pack_weight_split(w)
+    from btcdet_b200 import _lib as _lib_mod
+    tmask = torch.zeros((n_out + 127) // 128, dtype=torch.int64, device="cuda")
+    tiles = (n_out + 127) // 128
+    torder = torch.zeros(int(_lib_mod.load().btc_rulebook_tile_order_ints(n_out)), dtype=torch.int32, device="cuda")
+    from btcdet_b200 import _lib
+    import ctypes
+    _lib.check(_lib.load().btc_rulebook_tile_meta(ctypes.c_void_p(nbr.data_ptr()), n_out, ctypes.c_void_p(n_dev.data_ptr()), K,
+                                                  ctypes.c_void_p(tmask.data_ptr()), ctypes.c_void_p(torder.data_ptr()),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "tile_meta")
+    to = torder.cpu().numpy()
+    counts, buckets = to[:65], to[65:].reshape(65, tiles)
+    assert int(counts.sum()) == tiles
+    listed = sorted(int(t) for c in range(65) for t in buckets[c, :counts[c]])
+    assert listed == list(range(tiles))                                   # every live tile in exactly one class bucket
+    pop = np.array([bin(int(v) & (2 ** 64 - 1)).count("1") for v in tmask.cpu().numpy()])
+    assert all(pop[t] == c for c in range(65) for t in buckets[c, :counts[c]])
+    for in_split, out_split in ((True, False), (True, True), (False, True), (False, False)):
+        if not ops.tc_split_supported(K, cin, cout, in_split, out_split):
+            continue
+        for meta in (False, True):
+            out = ops.sparse_conv_fwd_tc_split(fs if in_split else feat, nbr, pks if in_split else pk32, cin, cout, in_split,
+                                               out_split, bias, scale, shift, relu=True, n_out_dev=n_dev,
+                                               tile_mask=tmask if meta else None, tile_order=torder if meta else None)
+            got = (ops.features_from_split(out) if out_split else out).cpu().numpy()
+            assert rel_err(got, want) < 1e-4, (in_split, out_split, meta, rel_err(got, want))

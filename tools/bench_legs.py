@@ -160,11 +160,10 @@ def chain_leg(dev, steps=5, warmup=2, batch=2):
     torch.manual_seed(0)
     model = chain.BtcHotPath()
     backbones.randomize_bn_(model, 0)
-    with torch.no_grad():
-        model.occ_head.conv_cls[0].bias.copy_(torch.tensor([1.2, -1.2]))
     model = model.to(dev).eval()
     bds = [chain.synthetic_batch([900 + 10 * i + b for b in range(batch)], n_points=20000, device=dev, with_rot=True, mode="test")
            for i in range(2)]
+    chain.calibrate_occ_head_bias(model, bds[0], 0.03)   # random-init head: let ~3 % of the candidate cells pass the threshold
 
     def run(i):
         bd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in bds[i % len(bds)].items()}

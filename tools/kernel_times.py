@@ -14,6 +14,8 @@ import torch  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--no-split", action="store_true")
+    ap.add_argument("--plain", action="store_true", help="no profiler: just run eager steps (target for ncu)")
     ap.add_argument("--no-tile-meta", action="store_true")
     args = ap.parse_args()
     from btcdet_b200 import backbones, engine, synthetic as S
@@ -23,12 +25,17 @@ def main():
     B = args.batch
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=5, max_voxels=16000, device=dev, use_graph=False,
-                               tile_meta=not args.no_tile_meta).capture()
+                               tile_meta=not args.no_tile_meta, split_format=not args.no_split).capture()
     pts, offs = S.batch_points([S.lidar_like(20000, seed=1000 + i) for i in range(B)])
     p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
     for _ in range(3):
         plan.forward(p, o)
     torch.cuda.synchronize()
+    if args.plain:
+        plan.forward(p, o)
+        torch.cuda.synchronize()
+        print("plain run done")
+        return
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         plan.forward(p, o)

@@ -28,8 +28,7 @@ def main():
     ap.add_argument("--side-priority", type=int, default=0, help="priority of the rulebook stream (-1 high, 0 default)")
     ap.add_argument("--diag", action="store_true", help="also time the conv chain with parts of the tcgen05 tile skipped "
                     "(btc_sparse_conv_tc_diag masks; wrong results, timing only)")
-    ap.add_argument("--commit-group", type=int, default=1, help="EXPERIMENTAL: stages per tcgen05.commit (1, 2, 3)")
-    ap.add_argument("--pdl", action="store_true", help="EXPERIMENTAL: programmatic dependent launch of the conv tile")
+    ap.add_argument("--no-split", action="store_true")
     ap.add_argument("--no-tile-meta", action="store_true", help="A/B: without the per-rulebook tile masks / heaviest-first order")
     ap.add_argument("--grids", default="", help="comma-separated caps on the conv grid: only the captured graph is timed per cap")
     ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
@@ -60,7 +59,7 @@ def grid_sweep(args):
         plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                    max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
                                    device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority,
-                               tile_meta=not args.no_tile_meta).capture()
+                               tile_meta=not args.no_tile_meta, split_format=not args.no_split).capture()
         plan.load_points(pts_d, offs_d)
         ms = []
         for r in range(args.reps + 3):
@@ -81,8 +80,6 @@ def grid_sweep(args):
 def run(args, npw, cat, dyn):
     from btcdet_b200 import ops
     ops.tc_config(npw, cat, dyn)
-    ops.tc_commit_group(args.commit_group)
-    ops.tc_pdl(args.pdl)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, N = args.batch, 20000
@@ -91,7 +88,7 @@ def run(args, npw, cat, dyn):
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
                                device=dev, use_graph=True, sort_rows=args.sort, side_priority=args.side_priority,
-                               tile_meta=not args.no_tile_meta).capture()
+                               tile_meta=not args.no_tile_meta, split_format=not args.no_split).capture()
     pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
     plan.load_points(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     plan.step()

@@ -23,6 +23,7 @@ import torch  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--no-split", action="store_true")
     ap.add_argument("--no-tile-meta", action="store_true")
     args = ap.parse_args()
     from btcdet_b200 import _lib, backbones, engine, synthetic as S
@@ -32,7 +33,7 @@ def main():
     model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
     B = args.batch
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
-                               max_points=5, max_voxels=16000, device=dev, use_graph=False, tile_meta=not args.no_tile_meta).capture()
+                               max_points=5, max_voxels=16000, device=dev, use_graph=False, tile_meta=not args.no_tile_meta, split_format=not args.no_split).capture()
     pts, offs = S.batch_points([S.lidar_like(20000, seed=1000 + i) for i in range(B)])
     plan.forward(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     torch.cuda.synchronize()
@@ -44,7 +45,7 @@ def main():
     for s in plan.steps:
         if s.kind != "conv":
             continue
-        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta = s.args
+        fin, nbr, w, bias, scale, shift, relu, fout, lout, K, cin, cout, packed, rows, meta, fmt = s.args
         if packed is None:
             continue
         rec = {"layer": "%d->%d K=%d" % (cin, cout, K), "rows": int(lout.n_dev.item())}
