@@ -42,12 +42,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--sort", action="store_true", help="mask-sort the rulebook rows inside 2048-row windows (A/B; off by default)")
     ap.add_argument("--no-sort", action="store_true", help=argparse.SUPPRESS)   # former default-on switch, now a no-op
-    ap.add_argument("--overlap", action="store_true", help="EXPERIMENTAL: also measure e2e through engine.OverlappedBackbone "
-                    "(reported under the separate key e2e_overlapped; the e2e key stays the verified path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the gpu_native_baseline / train / chain / stress legs")
-    ap.add_argument("--conv-grid", type=int, default=0, help="cap on the persistent conv grid (0 = one CTA per SM); with "
-                    "--overlap a smaller grid leaves whole SMs to the rulebook chain of the next batch")
+    ap.add_argument("--conv-grid", type=int, default=0, help="A/B: cap on the persistent conv grid (0 = one CTA per SM)")
     ap.add_argument("--no-tile-meta", action="store_true", help="A/B: without per-rulebook tile masks / heaviest-first order")
     ap.add_argument("--no-split", action="store_true", help="A/B: fp32 features between all layers (3xTF32 MMAs everywhere)")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the bounded CPU sample (0 = auto)")
@@ -299,41 +296,6 @@ def run_ours(args, rank, world):
             last_ev[0].synchronize()
 
     ms_e2e = timed_pipelined(step_e2e, drain, args.steps, args.warmup)
-    e2e_ov = None
-    if args.overlap:
-        try:
-            def make_plan():
-                return engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE,
-                                           S.KITTI_RANGE, max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"],
-                                           algo=args.algo, device=dev, use_graph=False, sort_rows=args.sort,
-                                           tile_meta=not args.no_tile_meta, split_format=not args.no_split)
-            ov = engine.OverlappedBackbone(make_plan, slots=2).capture()
-            ov_out, ov_last = [0], [None]
-
-            def step_ov(i):
-                p, o = host_batches[i % len(host_batches)]
-                ov.submit(p, o)
-                ov_out[0] += 1
-                if ov_out[0] > 1:
-                    _, _, ev = ov.retrieve()
-                    ov_out[0] -= 1
-                    ov_last[0] = ev
-
-            def drain_ov():
-                while ov_out[0] > 0:
-                    _, _, ev = ov.retrieve()
-                    ov_out[0] -= 1
-                    ov_last[0] = ev
-                if ov_last[0] is not None:
-                    ov_last[0].synchronize()
-
-            ms_ov = timed_pipelined(step_ov, drain_ov, args.steps, args.warmup,
-                                    tail_streams=[ov.idx_stream, ov.conv_stream, ov.copy_stream])
-            e2e_ov = {"value": round(world * B * args.steps / (ms_ov * 1e-3), 2), "unit": "scenes/s",
-                      "ms_per_step": round(ms_ov / args.steps, 4),
-                      "what": "experimental: rulebook graph of batch i+1 overlapped with the conv graph of batch i"}
-        except Exception as exc:   # the experimental leg must never take the bench line down
-            e2e_ov = {"error": repr(exc)}
     clocks = sampler.stop() if rank == 0 else None
     h2d_bytes = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
 
@@ -387,8 +349,6 @@ def run_ours(args, rank, world):
         "gpu_launches": plan.launches_per_step * args.steps,
         "clocks": clocks,
     }
-    if e2e_ov is not None:
-        res["e2e_overlapped"] = e2e_ov
     if roof:
         res["roofline"] = roof
     # ---- further legs (north_star items the headline metric does not cover) ---------------------------

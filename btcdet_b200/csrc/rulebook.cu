@@ -260,6 +260,115 @@ __device__ __forceinline__ bool out_coord_fast(int in, int kk, int s, int p, int
     return o >= 0 && o < out_dim;
 }
 
+// ---- fast path for the geometries the backbones use: per axis (k = 3, s = 2, d = 1) or (k = 1, s = 1), not transposed ----
+// The generic kernels below walk k^3 taps through runtime-parameter tests; threads of a warp take different paths and
+// the integer work (not memory) bounds them (25-30 us per build at every level size, profiles/r2_index_kernels.md).
+// For a stride-2 3-tap axis the valid taps follow from a parity: t = in + p - kk must be even and >= 0, so
+// kk0 = (in + p) & 1 with o0 = (in + p - kk0) / 2, and, when kk0 = 0, also kk = 2 with o0 - 1: at most two candidates per
+// axis, eight per site, in straight-line code.
+struct AxisFast {
+    int k, s, p, out_dim;
+};
+__device__ __forceinline__ int axis_cand(int in, const AxisFast& a, int (&kk)[2], int (&o)[2]) {
+    if (a.k == 1) {                       // k = 1, s = 1
+        kk[0] = 0;
+        o[0] = in + a.p;
+        kk[1] = 0;
+        o[1] = -1;
+        return (o[0] >= 0 && o[0] < a.out_dim) ? 1 : 0;
+    }
+    const int t = in + a.p;               // k = 3, s = 2
+    const int k0 = t & 1, o0 = (t - k0) >> 1;
+    int cnt = 0;
+    if (o0 >= 0 && o0 < a.out_dim) { kk[cnt] = k0; o[cnt] = o0; ++cnt; }
+    if (k0 == 0 && o0 - 1 >= 0 && o0 - 1 < a.out_dim) { kk[cnt] = 2; o[cnt] = o0 - 1; ++cnt; }
+    if (cnt < 2) { kk[1] = 0; o[1] = -1; }
+    if (cnt < 1) { kk[0] = 0; o[0] = -1; }
+    return cnt;
+}
+static bool fast_geometry(const ConvGeom& g) {
+    if (g.transposed) return false;
+    for (int a = 0; a < 3; ++a) {
+        const bool k3s2 = g.k[a] == 3 && g.s[a] == 2 && g.dil[a] == 1;
+        const bool k1s1 = g.k[a] == 1 && g.s[a] == 1;
+        if (!k3s2 && !k1s1) return false;
+    }
+    return true;
+}
+
+__global__ void conv_mark2_fast_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, Shape3 out,
+                                       AxisFast az, AxisFast ay, AxisFast ax, unsigned* __restrict__ out_index_words,
+                                       unsigned* __restrict__ summary) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        int kz[2], oz[2], ky[2], oy[2], kx[2], ox[2];
+        const int nz = axis_cand(c.y, az, kz, oz), ny = axis_cand(c.z, ay, ky, oy), nx = axis_cand(c.w, ax, kx, ox);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                if (a < nz && b < ny && nx > 0) {
+                    // the (at most two) x candidates are neighbouring cells: one RED carries both bits unless they straddle a
+                    // word boundary.  The LSU / L2 atomic rate bounds this kernel (lg_throttle in ncu), so fewer, fatter
+                    // reductions are the lever.
+                    const int64_t key0 = flat_key(c.x, oz[a], oy[b], ox[0], out);
+                    const int64_t w0 = key0 >> 5;
+                    unsigned bits0 = 1u << (unsigned)(key0 & 31);
+                    if (nx > 1) {
+                        const int64_t key1 = key0 + (ox[1] - ox[0]);
+                        const int64_t w1 = key1 >> 5;
+                        if (w1 == w0) {
+                            bits0 |= 1u << (unsigned)(key1 & 31);
+                        } else {
+                            atomicOr(out_index_words + 2 * w1, 1u << (unsigned)(key1 & 31));
+                            atomicOr(summary + (w1 >> 5), 1u << (unsigned)(w1 & 31));
+                        }
+                    }
+                    atomicOr(out_index_words + 2 * w0, bits0);
+                    atomicOr(summary + (w0 >> 5), 1u << (unsigned)(w0 & 31));
+                }
+            }
+    }
+}
+
+__global__ void conv_tables2_fast_kernel(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, Shape3 out,
+                                         AxisFast az, AxisFast ay, AxisFast ax, int K, const uint2* __restrict__ out_index,
+                                         int out_cap, int* __restrict__ nbr_out, int* __restrict__ nbr_in,
+                                         int4* __restrict__ out_coords) {
+    const int n = live_count(n_cap, n_dev);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(coords + i);
+        if (nbr_in)
+            for (int k = 0; k < K; ++k) nbr_in[(int64_t)i * K + k] = -1;
+        int kz[2], oz[2], ky[2], oy[2], kx[2], ox[2];
+        const int nz = axis_cand(c.y, az, kz, oz), ny = axis_cand(c.z, ay, ky, oy), nx = axis_cand(c.w, ax, kx, ox);
+        uint2 e[8];
+        int64_t key[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {                  // the (at most) eight rank-bitmap loads, issued together
+            const int a = t >> 2, b = (t >> 1) & 1, d = t & 1;
+            const bool v = a < nz && b < ny && d < nx;
+            key[t] = v ? flat_key(c.x, oz[a], oy[b], ox[d], out) : -1;
+            e[t] = v ? __ldg(out_index + (key[t] >> 5)) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (key[t] < 0) continue;
+            const int a = t >> 2, b = (t >> 1) & 1, d = t & 1;
+            const int k = (kz[a] * ay.k + ky[b]) * ax.k + kx[d];
+            const unsigned bit = 1u << (unsigned)(key[t] & 31);
+            int o = (e[t].x & bit) ? (int)(e[t].y + __popc(e[t].x & (bit - 1u))) : -1;
+            if (o >= out_cap) o = -1;
+            if (nbr_in) nbr_in[(int64_t)i * K + k] = o;
+            if (o >= 0) {
+                if (nbr_out) nbr_out[(int64_t)o * K + k] = i;
+                if (out_coords) out_coords[o] = make_int4(c.x, oz[a], oy[b], ox[d]);
+            }
+        }
+    }
+}
+
 // One thread per input site; nested tap loops with the validity tests inline (no per-thread tap arrays: dynamically
 // indexed local arrays live in local memory).  Two fire-and-forget reductions per (site, tap) pair (RED.OR, results
 // unused: the thread never waits for the L2).  Measured alternatives (profiles/r2_index_kernels.md): a test-before-atomic
@@ -726,19 +835,31 @@ int btc_rulebook_conv_sparse(const int* coords_in, int n_in_cap, const int* n_in
     unsigned long long* status = (unsigned long long*)((char*)workspace + 16);
     BTC_CUDA(cudaMemsetAsync(workspace, 0, 16 + (size_t)tiles * 8, st), "conv_sparse memset");
     const int64_t work = (int64_t)(n_in_cap > 0 ? n_in_cap : 1);
+    const bool fast = fast_geometry(g);
+    const AxisFast az{g.k[0], g.s[0], g.p[0], g.out.d}, ay{g.k[1], g.s[1], g.p[1], g.out.h}, ax{g.k[2], g.s[2], g.p[2], g.out.w};
     if (n_in_cap > 0) {
-        conv_mark2_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
-                                                           (unsigned*)out_index, summary);
+        if (fast)
+            conv_mark2_fast_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g.out, az, ay,
+                                                                    ax, (unsigned*)out_index, summary);
+        else
+            conv_mark2_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+                                                               (unsigned*)out_index, summary);
         BTC_CHECK_LAUNCH("conv_mark2");
     }
     scan_rank_kernel<<<tiles, kSeThreads, 0, st>>>((uint2*)out_index, summary, (int)n_sum, status, tile_ctr, n_out);
     BTC_CHECK_LAUNCH("scan_rank");
     if (out_cap > 0 && nbr_out)
         fill_table_kernel<<<grid_for((int64_t)out_cap * g.K / 4 + 1, 256), 256, 0, st>>>(nbr_out, out_cap, n_out, g.K);
-    if (n_in_cap > 0)
-        conv_tables2_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
-                                                             (const uint2*)out_index, out_cap, nbr_out, nbr_in,
-                                                             (int4*)out_coords);
+    if (n_in_cap > 0) {
+        if (fast)
+            conv_tables2_fast_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g.out, az,
+                                                                      ay, ax, g.K, (const uint2*)out_index, out_cap, nbr_out,
+                                                                      nbr_in, (int4*)out_coords);
+        else
+            conv_tables2_kernel<<<grid_for(work, 128), 128, 0, st>>>((const int4*)coords_in, n_in_cap, n_in_dev, g,
+                                                                 (const uint2*)out_index, out_cap, nbr_out, nbr_in,
+                                                                 (int4*)out_coords);
+    }
     BTC_CHECK_LAUNCH("conv rulebook (sparse)");
     return BTC_OK;
 }

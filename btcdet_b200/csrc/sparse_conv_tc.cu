@@ -376,7 +376,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     int* nbr_s = (int*)(a_stage + TC_PRODUCER_WARPS * TC_DEPTH * 4096);     // [2][TC_BM * K]
 
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], nbr_full[2], nbr_empty[2],
-        list_full[2], b_full[8];
+        list_full[2];
     __shared__ uint32_t s_tmem;
     __shared__ int s_cnt[2];                        // active reduction chunks of the tile in each index buffer
     __shared__ int s_tile[2];                       // tile id in each index buffer (-1: no more tiles for this CTA)
@@ -405,11 +405,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 128);          // the 128 threads of one producer group
+            mbar_init(&full_bar[s], 128 + 1);      // the 128 threads of one producer group + the weight loader (+ its tx bytes)
             mbar_init(&empty_bar[s], 1);           // one tcgen05.commit
-        }
-        for (int s = 0; s < NB; ++s) {
-            mbar_init(&b_full[s], 1);              // the weight loader's arrive (+ bulk-copy tx bytes)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 2);           // the issuer's early arrive (publishes the tile id) + one tcgen05.commit
@@ -609,7 +606,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // and the descriptor words are hoisted, and a stage's descriptors differ from the base only by an add on the
         // 14-bit start-address field (no carry: shared addresses < 256 KB).
         const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-        const uint32_t bfull0 = smem_u32(&b_full[0]);
         const uint64_t desc0 = make_desc_sw128(smem_u32(stages));
         const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = (uint32_t)desc0;
@@ -679,9 +675,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 if (s1 == (uint32_t)STAGES) { s1 = 0; ph1 ^= 1u; }
                 long long tw1 = 0;
                 if (tr) tw1 = clock64();
-                mbar_wait_a(bfull0 + 8u * s, ph);
-                mbar_wait_a(full0 + 8u * s, ph);
-                mbar_wait_a(bfull0 + 8u * s1, ph1);
+                mbar_wait_a(full0 + 8u * s, ph);          // A operand in TMEM and weight tile in smem (one barrier)
                 mbar_wait_a(full0 + 8u * s1, ph1);
                 if (tr) {
                     const long long t = clock64();
@@ -703,8 +697,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             for (; j < cnt; ++j) {
                 long long tw1 = 0;
                 if (tr) tw1 = clock64();
-                mbar_wait_a(bfull0 + 8u * s, ph);        // weight tile landed (requested STAGES stages ago)
-                mbar_wait_a(full0 + 8u * s, ph);         // A operand in TMEM
+                mbar_wait_a(full0 + 8u * s, ph);         // A operand in TMEM + weight tile landed
                 if (tr) {
                     const long long t = clock64();
                     tr_wait_full += t - tw1;
@@ -743,13 +736,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     mbar_wait(&empty_bar[sb], pb ^ 1u);   // the MMAs that read this slot have retired
                     tc_fence_after();
                     if (!(diag & 8)) {                         // (timing diagnostics: bit 3 drops the weight-tile copy)
-                        mbar_expect_tx(&b_full[sb], 2 * B_BYTES);
+                        mbar_expect_tx(&full_bar[sb], 2 * B_BYTES);
                         // split format: the 64-element tile that holds this 32-element chunk (chunk >> 1)
                         bulk_copy_g2s(stages + sb * STAGE_BYTES,
                                       (const char*)packed_w + (int64_t)(SIN ? (chunk >> 1) : chunk) * (2 * B_BYTES), 2 * B_BYTES,
-                                      &b_full[sb]);
+                                      &full_bar[sb]);
                     }
-                    mbar_arrive(&b_full[sb]);
+                    mbar_arrive(&full_bar[sb]);
                     if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
                 }
                 mbar_arrive(&nbr_empty[buf]);                  // done with this tile's chunk list
@@ -964,29 +957,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
 }
 
 // ---- per-tile metadata of a neighbour table (btc_rulebook_tile_meta) ------------------------------------------------
-// tile_mask[t]: bit k set iff some live row of tile t (rows [128 t, 128 t + 128)) has a neighbour through offset k.
-// One CTA per tile, coalesced sweep over the tile's [128 x K] block of the table.
-__global__ void __launch_bounds__(128) tile_mask_kernel(const int* __restrict__ table, int n_cap, const int* __restrict__ n_dev,
-                                                        int K, unsigned long long* __restrict__ tile_mask) {
-    __shared__ unsigned long long s_m[4];
-    const int n = live_count(n_cap, n_dev);
-    const int row0 = blockIdx.x * TC_BM;
-    if (row0 >= n && blockIdx.x > 0) return;          // capacity-sized grid: dead tiles leave without taking a ticket
-    const int live_tiles = n > 0 ? (n + TC_BM - 1) / TC_BM : 1;
-    unsigned long long m = 0;
-    if (row0 < n) {
-        const int rows = n - row0 < TC_BM ? n - row0 : TC_BM;
-        const int total = rows * K;
-        const int* src = table + (int64_t)row0 * K;
-        for (int i = threadIdx.x; i < total; i += 128)
-            if (__ldg(src + i) >= 0) m |= 1ull << (i % K);
-    }
-    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)m), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
-    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_mask[blockIdx.x] = s_m[0] | s_m[1] | s_m[2] | s_m[3];
-}
-
 // Masks and cost classes in ONE launch, no CTA waiting for another: every live CTA computes the mask of its tile, takes a
 // slot in the bucket of its cost class (number of active offsets, 0..64) with one atomic and stores its tile id there.
 // `tile_order` = [0, 65): class counts (zeroed by the caller), [65, 65 + 65 * tiles_cap): the buckets.  The conv kernel's

@@ -102,6 +102,9 @@ class BackbonePlan:
                                                                              self.max_points)),
                                   dtype=torch.uint8, device=dev)
         self.counts = []          # device count tensors to read back (overflow check / output size)
+        # live counts of every level in ONE small tensor (slot 0 = the voxeliser's total, copied; slot i = level i, written
+        # in place by the rulebook build): a single D2H copy reads them all
+        self.dev_counts = torch.zeros(16, dtype=torch.int32, device=dev)
         # ---- levels, rulebooks, feature buffers ---------------------------------------------
         shape0 = [int(s) for s in sparse_shape]
         lvl = _Level(shape0, cap1, torch.empty((cap1, 4), dtype=torch.int32, device=dev), self.n_voxels[B:B + 1])
@@ -136,7 +139,8 @@ class BackbonePlan:
                                                       conv.dilation)
                     cells = B * out_shape[0] * out_shape[1] * out_shape[2]
                     cap = int(min(cells, max(1024, level_growth * cur_lvl.cap)))
-                    n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+                    assert len(self.levels) < 16
+                    n_dev = self.dev_counts[len(self.levels):len(self.levels) + 1]
                     out_lvl = _Level(out_shape, cap, torch.empty((cap, 4), dtype=torch.int32, device=dev), n_dev)
                     out_lvl.index = torch.zeros(ops.index_entries(B, out_shape), dtype=torch.int64, device=dev)
                     out_lvl.summary = torch.zeros(int(self.lib.btc_index_summary_words(out_lvl.index.numel())),
@@ -189,7 +193,6 @@ class BackbonePlan:
         self._side_stream = torch.cuda.Stream(device=dev, priority=side_priority)
         self.launches_per_step = 0
         self.host_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32).pin_memory()
-        self.dev_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------------------------
     def _add_index(self, lvl: _Level):
@@ -252,8 +255,7 @@ class BackbonePlan:
             launches += 1
         main.wait_stream(side)
         # gather the live counts of every level into one small tensor (read back lazily by the caller)
-        for i, l in enumerate(self.levels):
-            self.dev_counts[i:i + 1].copy_(l.n_dev)
+        self.dev_counts[0:1].copy_(self.levels[0].n_dev)       # levels 1.. write their slot themselves
         self.launches_per_step = launches
         return launches
 
@@ -351,36 +353,6 @@ class BackbonePlan:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._run()
-        return self
-
-    def capture_split(self):
-        """Warm up once, then capture the rulebook chain (voxelise, indexes, neighbour tables) and the convolution chain
-        as TWO graphs, `graph_index` and `graph_conv`, for OverlappedBackbone (which replays batch i+1's rulebook graph
-        while batch i's convolution graph runs).  EXPERIMENTAL: not run on hardware in round 1."""
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self._run()                      # eager: loads modules, sizes the lazily allocated workspaces
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph_index = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_index):
-            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            launches = self.launch_voxelize(st)
-            for s in self.steps:
-                if s.kind != "conv":
-                    launches += self.launch_index_step(s, st)
-        self.graph_conv = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_conv):
-            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            for s in self.steps:
-                if s.kind == "conv":
-                    self.launch_conv(s.args, st)
-                    launches += 1
-            for i, l in enumerate(self.levels):
-                self.dev_counts[i:i + 1].copy_(l.n_dev)
-        self.launches_per_step = launches
         return self
 
     def load_points(self, points: torch.Tensor, scene_offsets: torch.Tensor):
@@ -489,106 +461,3 @@ class BackbonePlan:
     def level_features(self):
         """(features, coords, n_dev) of the last layer output (capacity-sized buffers)."""
         return self.out_feat, self.out_lvl.coords, self.out_lvl.n_dev
-
-
-class OverlappedBackbone:
-    """EXPERIMENTAL (not run on hardware in round 1, not used by bench.py's default path).
-
-    Throughput mode for a stream of batches: `slots` independent BackbonePlans (double-buffered inputs, levels, rulebooks,
-    features), each captured as a rulebook graph and a convolution graph.  submit() replays batch i's rulebook graph on an
-    index stream and its convolution graph on a conv stream, so the rulebook chain of batch i+1 (0.58 ms at batch 16)
-    runs while the convolutions of batch i (1.1 ms) occupy the tensor cores — inside one captured step the persistent
-    conv CTAs leave the rulebook kernels only their tails.  Results leave through the same staging + copy-stream scheme
-    as BackbonePlan.submit / retrieve, in submission order.
-    """
-
-    def __init__(self, make_plan, slots=2):
-        self.plans = [make_plan() for _ in range(slots)]
-        self.slots = slots
-        p0 = self.plans[0]
-        self.device, self.lib = p0.device, p0.lib
-        self.idx_stream = torch.cuda.Stream(device=self.device)
-        self.conv_stream = torch.cuda.Stream(device=self.device)
-        self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.k = 0
-        self.pending = []
-        self._st = None
-
-    def capture(self, result_rows=None):
-        for p in self.plans:
-            p.capture_split()
-        p0 = self.plans[0]
-        dev, C = self.device, p0.out_feat.shape[1]
-        rows = int(result_rows or min(p0.out_lvl.cap, p0.batch * 16384))
-        n = self.slots
-        self._st = {
-            "rows": rows,
-            "stage_feat": [torch.empty((rows, C), dtype=torch.float32, device=dev) for _ in range(n)],
-            "stage_coords": [torch.empty((rows, 4), dtype=torch.int32, device=dev) for _ in range(n)],
-            "stage_n": [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(n)],
-            "host_feat": [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(n)],
-            "host_coords": [torch.empty((rows, 4), dtype=torch.int32).pin_memory() for _ in range(n)],
-            "host_n": [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(n)],
-            "idx_done": [torch.cuda.Event() for _ in range(n)],
-            "conv_done": [None] * n,        # conv chain + staging of the slot's previous batch
-            "count_ready": [torch.cuda.Event() for _ in range(n)],
-            "d2h_done": [None] * n,
-        }
-        return self
-
-    def submit(self, points, scene_offsets):
-        """Enqueue one batch (pinned host or device tensors); returns immediately."""
-        st, slot = self._st, self.k % self.slots
-        plan = self.plans[slot]
-        if len(self.pending) >= self.slots:
-            raise _lib.BtcError("retrieve() the oldest batch before submitting more than %d batches" % self.slots)
-        self.idx_stream.wait_stream(torch.cuda.current_stream())    # `points` may have been produced on the caller's stream
-        # the slot's tables / features are still read by the convolution chain of its previous batch
-        if st["conv_done"][slot] is not None:
-            self.idx_stream.wait_event(st["conv_done"][slot])
-        with torch.cuda.stream(self.idx_stream):
-            plan.load_points(points, scene_offsets)
-            plan.graph_index.replay()
-            st["idx_done"][slot].record(self.idx_stream)
-        self.conv_stream.wait_event(st["idx_done"][slot])
-        if st["d2h_done"][slot] is not None:
-            self.conv_stream.wait_event(st["d2h_done"][slot])     # the slot's staging buffers have left the device
-        with torch.cuda.stream(self.conv_stream):
-            plan.graph_conv.replay()
-            cs = ctypes.c_void_p(self.conv_stream.cuda_stream)
-            C = plan.out_feat.shape[1]
-            cap = min(plan.out_lvl.cap, st["rows"])
-            check(self.lib.btc_copy_rows(_ptr(plan.out_feat), _ptr(st["stage_feat"][slot]), cap, _ptr(plan.out_lvl.n_dev),
-                                         C * 4, cs), "btc_copy_rows")
-            check(self.lib.btc_copy_rows(_ptr(plan.out_lvl.coords), _ptr(st["stage_coords"][slot]), cap,
-                                         _ptr(plan.out_lvl.n_dev), 16, cs), "btc_copy_rows")
-            st["stage_n"][slot].copy_(plan.out_lvl.n_dev, non_blocking=True)
-            st["host_n"][slot].copy_(st["stage_n"][slot], non_blocking=True)
-            st["count_ready"][slot].record(self.conv_stream)
-            ev = torch.cuda.Event()
-            ev.record(self.conv_stream)
-            st["conv_done"][slot] = ev
-        self.pending.append(slot)
-        self.k += 1
-
-    def retrieve(self):
-        """(features [n,C], coords [n,4], d2h_event) of the oldest submitted batch, as views of pinned host buffers that
-        stay valid until `slots` further submits."""
-        st = self._st
-        slot = self.pending.pop(0)
-        st["count_ready"][slot].synchronize()
-        n = int(st["host_n"][slot][0])
-        if n > st["rows"]:
-            raise _lib.BtcError("result of %d rows exceeds the staging capacity %d" % (n, st["rows"]))
-        self.copy_stream.wait_event(st["count_ready"][slot])
-        with torch.cuda.stream(self.copy_stream):
-            st["host_feat"][slot][:n].copy_(st["stage_feat"][slot][:n], non_blocking=True)
-            st["host_coords"][slot][:n].copy_(st["stage_coords"][slot][:n], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-        st["d2h_done"][slot] = ev
-        return st["host_feat"][slot][:n], st["host_coords"][slot][:n], ev
-
-    def read_counts(self, slot=0):
-        torch.cuda.current_stream().wait_stream(self.conv_stream)
-        return self.plans[slot].read_counts()

@@ -203,41 +203,3 @@ def test_pipelined_submit_retrieve_matches_forward(cuda, oracle):
     assert len(got) == len(want)
     for (gf, gc), (wf, wc) in zip(got, want):
         assert torch.equal(gc, wc) and torch.equal(gf, wf)
-
-
-@pytest.mark.skipif(os.environ.get("BTC_TEST_EXPERIMENTAL") != "1",
-                    reason="OverlappedBackbone has not run on hardware yet (DESIGN.md §8.2); set BTC_TEST_EXPERIMENTAL=1")
-def test_overlapped_backbone_experimental(cuda, oracle):
-    """Two double-buffered plans, rulebook graph of batch i+1 overlapping the conv graph of batch i: same results as the
-    synchronous forward, in submission order, for more batches than slots (slot reuse) and ragged scene sizes."""
-    from btcdet_b200 import backbones, engine, synthetic as S
-    torch.manual_seed(0)
-    model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
-
-    def make():
-        return engine.BackbonePlan(model.layer_specs(), model.sparse_shape, 2, 2 * 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
-                                   max_points=5, max_voxels=16000, use_graph=False)
-    ref_plan = make().capture()
-    batches = []
-    for i in range(7):
-        pts, offs = S.batch_points([S.lidar_like(20000 - 900 * i, seed=700 + 2 * i), S.lidar_like(12000 + 500 * i, seed=701 + 2 * i)])
-        batches.append((torch.from_numpy(pts).pin_memory(), torch.from_numpy(offs).pin_memory()))
-    want = []
-    for p, o in batches:
-        feat, coords, n_dev = ref_plan.forward(p, o)
-        n = int(n_dev.item())
-        want.append((feat[:n].cpu().clone(), coords[:n].cpu().clone()))
-    ov = engine.OverlappedBackbone(make, slots=2).capture()
-    got = []
-    for i, (p, o) in enumerate(batches):
-        ov.submit(p, o)
-        if i >= 1:
-            f, c, ev = ov.retrieve()
-            ev.synchronize()
-            got.append((f.clone(), c.clone()))
-    f, c, ev = ov.retrieve()
-    ev.synchronize()
-    got.append((f.clone(), c.clone()))
-    assert len(got) == len(want)
-    for (gf, gc), (wf, wc) in zip(got, want):
-        assert torch.equal(gc, wc) and torch.equal(gf, wf)
