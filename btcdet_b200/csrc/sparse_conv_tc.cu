@@ -386,8 +386,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     const int n = live_count(n_cap, n_dev);
     if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // Timeline diagnostics (btc_sparse_conv_tc_trace): 16 u64 slots per CTA, see tools/tc_timeline.py for the legend.
-    unsigned long long* tr = trace ? trace + (size_t)blockIdx.x * 16 : nullptr;
+    // Timeline diagnostics (btc_sparse_conv_tc_trace): 32 u64 slots per CTA, see tools/tc_timeline.py for the legend.
+    unsigned long long* tr = trace ? trace + (size_t)blockIdx.x * 32 : nullptr;
     if (tr && tid == 0) {
         unsigned long long g;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
@@ -512,8 +512,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         bool located = false;
         const bool tr_me = tr && warp == 0 && lane == 0;
         bool tr_first_issue = true, tr_first_arrive = true;
-        long long tr_wait_empty = 0;
+        long long tr_wait_empty = 0, tr_p_issue = 0, tr_p_cpwait = 0, tr_p_store = 0, tr_tp = 0;
         while (true) {
+            if (tr_me) tr_tp = clock64();
             // issue ahead: up to TC_DEPTH gathers in flight, never blocking while some are
             while (!it_done && inflight < TC_DEPTH) {
                 if (!located) located = locate(inflight == 0);
@@ -524,6 +525,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 located = false;
             }
             if (inflight == 0) break;              // iterator exhausted and everything drained
+            if (tr_me) { const long long t = clock64(); tr_p_issue += t - tr_tp; tr_tp = t; }
             --inflight;                            // = committed groups allowed to stay pending
             if (inflight == 0) cp_async_wait<0>();
             else if (inflight == 1) cp_async_wait<1>();
@@ -543,7 +545,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             __syncwarp();                          // everyone has read the slot before it is refilled
             long long tw0 = 0;
-            if (tr_me) tw0 = clock64();
+            if (tr_me) { tw0 = clock64(); tr_p_cpwait += tw0 - tr_tp; }
             mbar_wait_a(empty0 + 8u * (uint32_t)s, (uint32_t)(ph ^ 1));
             if (tr_me) tr_wait_empty += clock64() - tw0;
             tc_fence_after();
@@ -591,12 +593,18 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             tc_fence_before();
             mbar_arrive_a(full0 + 8u * (uint32_t)s);
             if (tr_me && tr_first_arrive) { tr[5] = (unsigned long long)clock64(); tr_first_arrive = false; }
+            if (tr_me) tr_p_store += clock64() - tw0;
             // advance the consume-side counters by two global stages
             s += G; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
             if (++slot == TC_DEPTH) slot = 0;
         }
         if (cur_tile >= 0) mbar_arrive(&nbr_empty[cur_tile & 1]);   // (not reached: the iterator releases as it leaves)
-        if (tr_me) tr[14] = (unsigned long long)tr_wait_empty;
+        if (tr_me) {
+            tr[14] = (unsigned long long)tr_wait_empty;
+            tr[22] = (unsigned long long)tr_p_issue;      // locate (incl. blocking on chunk lists) + gather issue
+            tr[23] = (unsigned long long)tr_p_cpwait;     // cp.async wait + shared read-back
+            tr[24] = (unsigned long long)tr_p_store;      // wait for the free A slot + TMEM store + arrive
+        }
     } else if (warp == TC_MMA_WARP) {
         // ================= MMA issuer =================
         // The whole warp runs the loop in warp-uniform control flow and one ELECTed lane issues: a divergent
@@ -775,11 +783,14 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             __syncwarp();
         }
+        long long tr_idx_wait = 0, tr_idx_fetch = 0, tr_idx_copy = 0, tr_idx_list = 0, tr_t = 0;
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
             int tile = -1;
+            if (tr) tr_t = clock64();
             if (lane == 0) {
                 mbar_wait(&nbr_empty[buf], ((tl >> 1) & 1) ^ 1);
+                if (tr) { const long long t = clock64(); tr_idx_wait += t - tr_t; tr_t = t; }
                 if (!tile_ctr) {
                     tile = tl < my_tiles ? (int)blockIdx.x + tl * (int)gridDim.x : -1;
                 } else if (tl == 0) {
@@ -804,12 +815,19 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 }
             }
             tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_fetch += t - tr_t; tr_t = t; }
             if (tile < 0) {                            // publish the end marker and leave
                 if (lane == 0) {
                     s_tile[buf] = -1;
                     s_cnt[buf] = 0;
                     mbar_arrive(&list_full[buf]);
-                    if (tr) tr[11] = (unsigned long long)tl;
+                    if (tr) {
+                        tr[11] = (unsigned long long)tl;
+                        tr[16] = (unsigned long long)tr_idx_wait;
+                        tr[17] = (unsigned long long)tr_idx_fetch;
+                        tr[18] = (unsigned long long)tr_idx_copy;
+                        tr[19] = (unsigned long long)tr_idx_list;
+                    }
                 }
                 break;
             }
@@ -844,6 +862,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
                 m = (unsigned long long)m_lo | ((unsigned long long)m_hi << 32);
             }
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_copy += t - tr_t; tr_t = t; }
             int cnt = 0;
             for (int c0 = 0; c0 < T; c0 += 32) {
                 const int c = c0 + lane;
@@ -867,13 +886,18 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             if (lane == 0) { s_cnt[buf] = cnt; s_tile[buf] = tile; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&list_full[buf]);
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_list += t - tr_t; tr_t = t; }
         }
     } else if (warp >= Roles::kEpi0 && warp < Roles::kEpi0 + 4) {
         // ================= epilogue =================
         const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
+        const bool tr_epi = tr && warp == Roles::kEpi0 && lane == 0;
+        long long tr_epi_wait = 0, tr_epi_busy = 0, tr_te = 0;
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
+            if (tr_epi) tr_te = clock64();
             mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+            if (tr_epi) { const long long t = clock64(); tr_epi_wait += t - tr_te; tr_te = t; }
             tc_fence_after();
             const int tile = s_epi_tile[buf];
             if (tile < 0) break;
@@ -942,7 +966,13 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);           // this accumulator buffer may be overwritten
-            if (tr && warp == Roles::kEpi0 && lane == 0) tr[8] = (unsigned long long)clock64();
+            if (tr_epi) {
+                const long long t = clock64();
+                tr_epi_busy += t - tr_te;
+                tr[8] = (unsigned long long)t;
+                tr[20] = (unsigned long long)tr_epi_wait;
+                tr[21] = (unsigned long long)tr_epi_busy;
+            }
         }
     }
     tc_fence_before();
@@ -1004,7 +1034,7 @@ __global__ void __launch_bounds__(128) tile_meta_kernel(const int* __restrict__ 
 constexpr int kTcCtrSlots = 1024;
 __device__ int g_tc_tile_ctr[kTcCtrSlots];
 static int g_tc_npw = 0, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM;
-static unsigned long long* g_tc_trace = nullptr;   // timeline diagnostics buffer (device, 16 u64 per CTA) or null
+static unsigned long long* g_tc_trace = nullptr;   // timeline diagnostics buffer (device, 32 u64 per CTA) or null
 
 static int* next_tile_counter() {
     static int* base[64] = {nullptr};            // (benign race: every thread computes the same address)
@@ -1125,7 +1155,7 @@ int btc_sparse_conv_tc_diag(int mask) {
 }
 
 int btc_sparse_conv_tc_trace(void* trace_u64) {
-    g_tc_trace = (unsigned long long*)trace_u64;   // device buffer of 148 * 16 u64, or null to switch the timeline off
+    g_tc_trace = (unsigned long long*)trace_u64;   // device buffer of 148 * 32 u64, or null to switch the timeline off
     return BTC_OK;
 }
 

@@ -38,7 +38,7 @@ def main():
     plan.forward(torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev))
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    trace = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     clk_ghz = None
     out = []
@@ -59,7 +59,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             _lib.check(lib.btc_sparse_conv_tc_trace(None), "trace off")
-        t = trace.cpu().numpy().reshape(148, 16).astype(np.float64)
+        t = trace.cpu().numpy().reshape(148, 32).astype(np.float64)
         live = t[:, 1] > 0
         t = t[live]
         wall_ns = t[:, 10].max() - t[:, 0].min()
@@ -85,6 +85,15 @@ def main():
             "issuer_wait_list_us_med": round(float(np.median(us(t[:, 3]))), 1),
             "issuer_wait_accumulator_us_med": round(float(np.median(us(t[:, 15]))), 1),
             "producer0_wait_empty_us_med": round(float(np.median(us(t[:, 14]))), 1),
+            "index_loader_us_med": {"wait_free_buffer": round(float(np.median(us(t[:, 16]))), 1),
+                                    "tile_fetch": round(float(np.median(us(t[:, 17]))), 1),
+                                    "index_copy_and_mask": round(float(np.median(us(t[:, 18]))), 1),
+                                    "chunk_list": round(float(np.median(us(t[:, 19]))), 1)},
+            "producer0_us_med": {"locate_and_issue": round(float(np.median(us(t[:, 22]))), 1),
+                                 "cp_async_wait_readback": round(float(np.median(us(t[:, 23]))), 1),
+                                 "slot_wait_tmem_store": round(float(np.median(us(t[:, 24]))), 1)},
+            "epilogue_us_med": {"wait_accumulator": round(float(np.median(us(t[:, 20]))), 1),
+                                "busy": round(float(np.median(us(t[:, 21]))), 1)},
             "cycles_per_stage_med": round(float(np.median((t[:, 7] - t[:, 6]) / np.maximum(t[:, 13], 1))), 1),
         })
         out.append(rec)
