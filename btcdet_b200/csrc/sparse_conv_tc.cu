@@ -149,6 +149,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// K-major, SWIZZLE_64B descriptor (bf16 tiles of 32 reduction elements: rows of 64 B, 8-row atoms 512 B apart, layout = 4)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
 // byte offset of element (row r, float j) inside a K-major SW128 tile
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) {
     return (r >> 3) * 1024 + (r & 7) * 128 + ((((j >> 2) ^ (r & 7)) & 7) << 4) + (j & 3) * 4;
@@ -178,30 +189,32 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, int K, int c_
     }
 }
 
-// byte offset of bf16 element (row r, element j of 64) inside a K-major SW128 tile
-__host__ __device__ __forceinline__ int sw128_offset_bf16(int r, int j) {
-    return (r >> 3) * 1024 + (r & 7) * 128 + ((((j >> 3) ^ (r & 7)) & 7) << 4) + (j & 7) * 2;
+// byte offset of bf16 element (row r, element j of 32) inside a K-major SWIZZLE_64B tile: rows of 64 B, 8-row atoms of
+// 512 B, the 16-byte chunk index XORed with bits [7,9) of the byte address (cute Swizzle<2,4,3>) = (r >> 1) & 3
+__host__ __device__ __forceinline__ int sw64_offset_bf16(int r, int j) {
+    return (r >> 3) * 512 + (r & 7) * 64 + ((((j >> 3) ^ (r >> 1)) & 3) << 4) + (j & 7) * 2;
 }
 
-// Split-format weights: the reduction axis e = k*c_in + ci in tiles of 64; packed[tile] = { B_hi image [N x 128 B] of
-// bf16, B_lo image }, hi = bf16_rn(w), lo = bf16_rn(w - hi).  A 32-element stage (chunk c) uses half c & 1 of tile c >> 1.
+// Split-format weights: the reduction axis e = k*c_in + ci in chunks of 32 (one MMA stage); packed[chunk] = { B_hi image
+// [N x 64 B] of bf16, B_lo image }, hi = bf16_rn(w), lo = bf16_rn(w - hi) — 64-byte rows, so a stage fetches exactly the
+// 2 * N * 64 bytes it multiplies (a 128-byte-row tile of 64 elements was fetched whole by both of its stages).
 __global__ void tc_pack_weight_split_kernel(const float* __restrict__ w, int K, int c_in, int c_out, int N,
                                             unsigned short* __restrict__ packed) {
     const int E = K * c_in;
-    const int ntile = (E + 63) / 64;
-    const int64_t total = (int64_t)ntile * N * 64;
+    const int nchunk = (E + TC_KC - 1) / TC_KC;
+    const int64_t total = (int64_t)nchunk * N * TC_KC;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(t % 64);
-        const int64_t r = t / 64;
+        const int j = (int)(t % TC_KC);
+        const int64_t r = t / TC_KC;
         const int n = (int)(r % N);
-        const int tt = (int)(r / N);
-        const int e = tt * 64 + j;
+        const int cc = (int)(r / N);
+        const int e = cc * TC_KC + j;
         const float v = (e < E && n < c_out) ? w[(int64_t)e * c_out + n] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        char* base = (char*)packed + (int64_t)tt * (2 * N * 128);
-        *(unsigned short*)(base + sw128_offset_bf16(n, j)) = __bfloat16_as_ushort(hi);
-        *(unsigned short*)(base + N * 128 + sw128_offset_bf16(n, j)) = __bfloat16_as_ushort(lo);
+        char* base = (char*)packed + (int64_t)cc * (2 * N * 64);
+        *(unsigned short*)(base + sw64_offset_bf16(n, j)) = __bfloat16_as_ushort(hi);
+        *(unsigned short*)(base + N * 64 + sw64_offset_bf16(n, j)) = __bfloat16_as_ushort(lo);
     }
 }
 
@@ -269,8 +282,10 @@ template <int NPW> struct TcRoles {
 // six stages at N = 32 (448 TMEM columns, 48 KB of weight tiles), four at N = 64 / 128 (64 / 128 KB of weight tiles).
 // Round-1 timing diagnostics (tools/step_breakdown.py --diag) on the way here: separate, deeper rings (6 x A, 8 x B) and
 // a second commit per stage were within 1 % of this; dropping the weight copies altogether changes < 1 %.
-template <int N, bool CAT> struct TcAStages { static constexpr int value = N <= 32 ? 6 : 4; };
-template <int N> struct TcBStages { static constexpr int value = N <= 32 ? 6 : 4; };   // == TcAStages
+// Split format: a stage's weight tile is half the bytes (64-byte rows) and its A operand half the TMEM columns (16 hi +
+// 16 lo), so the same shared memory / tensor memory holds rings twice as deep: 12 stages at N = 32, 8 at N = 64 / 128.
+template <int N, bool SPLIT> struct TcAStages { static constexpr int value = (N <= 32 ? 6 : 4) * (SPLIT ? 2 : 1); };
+template <int N, bool SPLIT> struct TcBStages { static constexpr int value = TcAStages<N, SPLIT>::value; };
 template <int N, int NPW> struct TcDepth { static constexpr int value = (N > 64 || NPW > 8) ? 2 : 4; };   // cp.async gather stages in flight per producer warp (smem budget)
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
@@ -337,8 +352,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 //                  32 channels the row holds [32 x hi | 32 x lo] (64 B + 64 B), so a stage's gather is byte-for-byte
 //                  the copy it was, the read-back registers ARE the packed A operands (no ALU work in the producers,
 //                  half the tcgen05.st) and the k-step is three kind::f16 (bf16) MMAs of K = 16: A_lo B_hi + A_hi B_lo
-//                  + A_hi B_hi — 6 MMAs per stage.  Weights are packed as bf16 hi / lo tiles of 64 reduction elements
-//                  (one 128-byte swizzle row); a stage uses the half its chunk parity names.
+//                  + A_hi B_hi — 6 MMAs per stage.  Weights are packed per 32-element chunk as bf16 hi / lo tiles with
+//                  64-byte rows (SWIZZLE_64B), so a stage fetches exactly the bytes it multiplies.
 // Both meet the 1e-4 parity bar (split: ~2^-16 per product, measured in tests/test_parity_gpu.py).  The experimental
 // variants of round 1 (concatenated [B_hi|B_lo] MMAs, commit groups, programmatic dependent launch) were measured on
 // hardware at the start of round 2 (profiles/r2_battery.json: no gain / slower) and removed.
@@ -351,16 +366,17 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                    const int* __restrict__ n_dev, int K, int c_in, int c_out, int* __restrict__ tile_ctr, int diag,
                    unsigned long long* __restrict__ trace, const unsigned long long* __restrict__ tile_mask,
                    const int* __restrict__ tile_order, int tiles_cap) {
-    constexpr int STAGES = TcAStages<N, false>::value;
+    constexpr int STAGES = TcAStages<N, SIN>::value;
     constexpr int TC_DEPTH = TcDepth<N, NPW>::value;
     using Roles = TcRoles<NPW>;
     constexpr int G = Roles::kGroups;               // producer groups; group g feeds the stages with gi % G == g
     constexpr int TC_PRODUCER_WARPS = NPW, TC_MMA_WARP = Roles::kMma, TC_IDX_WARP = Roles::kIdx, TC_BLD_WARP = Roles::kBld;
-    constexpr int NB = TcBStages<N>::value;         // weight-tile ring depth
-    static_assert(NB == TcAStages<N, false>::value, "the A ring and the weight ring share slot index, phase and the commit");
+    constexpr int NB = TcBStages<N, SIN>::value;    // weight-tile ring depth
+    static_assert(NB == STAGES, "the A ring and the weight ring share slot index, phase and the commit");
     static_assert(G <= STAGES, "a group advances by G stages and may wrap the ring at most once per step");
-    constexpr int B_BYTES = N * 128;              // one B tile (hi or lo), K-major SW128
+    constexpr int B_BYTES = N * (SIN ? 64 : 128); // one B tile (hi or lo): K-major SW128 (tf32) / SW64 (bf16), 32 elements per row
     constexpr int STAGE_BYTES = 2 * B_BYTES;
+    constexpr uint32_t A_STRIDE = SIN ? 32u : 64u; // TMEM columns of one A stage (hi + lo)
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t ACC_COLS = N;              // TMEM columns of one accumulator buffer
     constexpr uint32_t A_COL0 = 2 * ACC_COLS;     // first A-operand column
@@ -368,7 +384,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     // M>>4 at bit 24
     constexpr uint32_t FMT = SIN ? 1u : 2u;
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    static_assert(2 * ACC_COLS + 64 * STAGES <= 512, "TMEM budget");
+    static_assert(2 * ACC_COLS + A_STRIDE * STAGES <= 512, "TMEM budget");
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* stages = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
@@ -382,9 +398,18 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
     __shared__ int s_tile[2];                       // tile id in each index buffer (-1: no more tiles for this CTA)
     __shared__ int s_epi_tile[2];                   // tile id behind each accumulator buffer (MMA issuer -> epilogue)
     __shared__ int s_cls_start[66];                 // heaviest-first prefix of the cost-class counts (tile_order lookup)
+    // epilogue constants per output column, staged once per CTA: y = (acc + bias) * scale + shift (absent -> 0 / 1 / 0);
+    // a __ldg per column and row in the epilogue loop cost ~140 cycles per column (exposed L1 latency, round-2 timeline)
+    __shared__ __align__(16) float s_ep_bias[N], s_ep_scale[N], s_ep_shift[N];
 
     const int n = live_count(n_cap, n_dev);
-    if ((int)blockIdx.x * TC_BM >= n) return;     // no tile for this CTA (whole CTA leaves before any barrier)
+    if ((int)blockIdx.x * TC_BM >= n) {           // no tile for this CTA (whole CTA leaves before any barrier)
+        if (tile_ctr && threadIdx.x == 0 && atomicAdd(tile_ctr + 1, 1) == (int)gridDim.x - 1) {   // see the scheduler warp
+            atomicExch(tile_ctr, 0);
+            atomicExch(tile_ctr + 1, 0);
+        }
+        return;
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // Timeline diagnostics (btc_sparse_conv_tc_trace): 32 u64 slots per CTA, see tools/tc_timeline.py for the legend.
     unsigned long long* tr = trace ? trace + (size_t)blockIdx.x * 32 : nullptr;
@@ -418,6 +443,12 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         fence_mbar_init();
     }
     if (warp == TC_MMA_WARP) tmem_alloc(&s_tmem, TMEM_COLS);
+    for (int c = tid; c < N; c += Roles::kThreads) {
+        const bool in = c < c_out;
+        s_ep_bias[c] = (bias && in) ? __ldg(bias + c) : 0.f;
+        s_ep_scale[c] = (scale && in) ? __ldg(scale + c) : 1.f;
+        s_ep_shift[c] = (scale && in) ? __ldg(shift + c) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -564,7 +595,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                             w[4 * i + 2] = __float_as_uint(v[4 * h + i].z);
                             w[4 * i + 3] = __float_as_uint(v[4 * h + i].w);
                         }
-                        tmem_st16(lane_base + A_COL0 + (uint32_t)(s * 64 + 32 * h), w);
+                        tmem_st16(lane_base + A_COL0 + (uint32_t)s * A_STRIDE + 16u * (uint32_t)h, w);
                     }
                 }
             } else
@@ -614,7 +645,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // and the descriptor words are hoisted, and a stage's descriptors differ from the base only by an add on the
         // 14-bit start-address field (no carry: shared addresses < 256 KB).
         const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-        const uint64_t desc0 = make_desc_sw128(smem_u32(stages));
+        const uint64_t desc0 = SIN ? make_desc_sw64(smem_u32(stages)) : make_desc_sw128(smem_u32(stages));
         const uint64_t desc_hi64 = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = (uint32_t)desc0;
         uint32_t s = 0, ph = 0;   // ring slot / phase (A operand in TMEM and weight tile in smem share both)
@@ -642,13 +673,11 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             __syncwarp();
             if (tile < 0) break;
-            // one stage = 12 tf32 (6 bf16) MMAs + the commit that frees its A and weight slots.  `half`: split format only —
-            // which 32-element half of the 64-element weight tile the stage's chunk is (chunk parity).
-            const uint32_t list_s32 = smem_u32(s_list);
-            auto issue_stage = [&](uint32_t sa, bool first, uint32_t half) {
-                const uint32_t a_hi = tmem_base + A_COL0 + sa * 64u;
-                const uint32_t a_lo = a_hi + 32u;
-                const uint32_t dl = desc_lo0 + sa * (uint32_t)(STAGE_BYTES >> 4) + (SIN ? half * 4u : 0u);
+            // one stage = 12 tf32 (6 bf16) MMAs + the commit that frees its A and weight slots
+            auto issue_stage = [&](uint32_t sa, bool first) {
+                const uint32_t a_hi = tmem_base + A_COL0 + sa * A_STRIDE;
+                const uint32_t a_lo = a_hi + (SIN ? 16u : 32u);
+                const uint32_t dl = desc_lo0 + sa * (uint32_t)(STAGE_BYTES >> 4);
                 constexpr int KSTEPS = SIN ? TC_KC / 16 : TC_KC / 8;   // UMMA_K = 16 bf16 / 8 tf32 = 8 TMEM columns, 32 B of B
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk) {
@@ -671,9 +700,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 }
                 umma_commit_a(empty0 + 8u * sa);   // frees the A and weight stages once the MMAs retire
             };
-            auto chunk_half = [&](int jj) -> uint32_t {
-                return SIN ? (lds_u16(list_s32 + 2u * (uint32_t)(buf * T + jj)) & 1u) : 0u;
-            };
             // Two stages per trip where the list allows (diag bit 4 forces one): the wait -> fence -> elect -> issue ->
             // reconverge sequence has a fixed latency that a 12-MMA stage does not cover.
             int j = 0;
@@ -693,10 +719,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     tr_first = false;
                 }
                 tc_fence_after();
-                const uint32_t h0 = chunk_half(j), h1 = chunk_half(j + 1);
                 if (elect_one()) {
-                    issue_stage(s, j == 0, h0);
-                    issue_stage(s1, false, h1);
+                    issue_stage(s, j == 0);
+                    issue_stage(s1, false);
                 }
                 __syncwarp();
                 s = s1 + 1; ph = ph1;
@@ -714,8 +739,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     tr_first = false;
                 }
                 tc_fence_after();
-                const uint32_t h0 = chunk_half(j);
-                if (elect_one()) issue_stage(s, j == 0, h0);
+                if (elect_one()) issue_stage(s, j == 0);
                 __syncwarp();
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
             }
@@ -745,10 +769,8 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     tc_fence_after();
                     if (!(diag & 8)) {                         // (timing diagnostics: bit 3 drops the weight-tile copy)
                         mbar_expect_tx(&full_bar[sb], 2 * B_BYTES);
-                        // split format: the 64-element tile that holds this 32-element chunk (chunk >> 1)
-                        bulk_copy_g2s(stages + sb * STAGE_BYTES,
-                                      (const char*)packed_w + (int64_t)(SIN ? (chunk >> 1) : chunk) * (2 * B_BYTES), 2 * B_BYTES,
-                                      &full_bar[sb]);
+                        bulk_copy_g2s(stages + sb * STAGE_BYTES, (const char*)packed_w + (int64_t)chunk * (2 * B_BYTES),
+                                      2 * B_BYTES, &full_bar[sb]);
                     }
                     mbar_arrive(&full_bar[sb]);
                     if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
@@ -760,11 +782,40 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
         // ================= index loader: TMA-stage each tile's neighbour block, publish its active chunks ==========
         // Tile scheduler.  Static: tile = blockIdx.x + tl * gridDim.x.  Dynamic (tile_ctr != null): the first tile is
         // blockIdx.x, the following ones come from a global counter — tiles cost between a few and all T chunks, so a
-        // fixed round-robin leaves SMs idle ~20 % of a layer.  Exactly num_tiles fetches happen per
-        // launch (num_tiles - P that return a tile + one failing fetch per participating CTA, P = min(grid, tiles));
-        // the fetch that returns num_tiles - 1 is the last one and resets the counter for the next launch.
+        // fixed round-robin leaves SMs idle ~20 % of a layer.  tile_ctr[0] = positions handed out beyond
+        // the first P = min(grid, tiles), tile_ctr[1] = CTAs that are done claiming; the last CTA to report zeroes both.
         const int P = num_tiles < (int)gridDim.x ? num_tiles : (int)gridDim.x;
         const uint32_t nbr_s32 = smem_u32(nbr_s);
+        // Dynamic hand-out in guided batches (lane 0).  One global counter served a tile per atomicAdd: on the thin layers
+        // (~1700 tiles in ~40 us) 148 CTAs on one address run into the L2 atomic unit's per-address rate (B300_MICROARCH
+        // "L2-atom multi-CTA": ~27 cycles per op, microseconds of latency under contention), so a claim takes
+        // clamp(remaining / (4 P), 1, 4) consecutive positions of the heaviest-first sequence — the batches shrink to one
+        // tile towards the end, where balance matters.  While plenty of tiles remain (> 4 per CTA) the next claim is issued
+        // as soon as the local queue runs dry (two tiles ahead of the one being staged); in the last rounds only when the
+        // next tile is actually needed, so that no CTA sits on a claimed tile while others idle.  A reply is only looked
+        // at after the current tile's list has been published.
+        bool exhausted = false;       // the counter ran past the last position: no more claims
+        bool claim_inflight = false;
+        int claim_raw = 0, claim_n = 0, q_pos = 0, q_end = 0, rem_est = num_tiles - P;   // local queue [q_pos, q_end)
+        auto claim = [&]() {
+            if (!tile_ctr || exhausted || claim_inflight) return;
+            int b = rem_est / (4 * P);
+            b = b < 1 ? 1 : (b > 4 ? 4 : b);
+            claim_n = b;
+            claim_raw = atomicAdd(tile_ctr, b);
+            claim_inflight = true;
+        };
+        auto settle = [&]() {          // look at the reply of the claim in flight (stalls until it is back)
+            if (!claim_inflight) return;
+            claim_inflight = false;
+            const int first = P + claim_raw;
+            rem_est = num_tiles - first - claim_n;
+            if (first >= num_tiles) { exhausted = true; return; }
+            q_pos = first;
+            q_end = first + claim_n < num_tiles ? first + claim_n : num_tiles;
+            if (q_end == num_tiles) exhausted = true;
+        };
+        if (lane == 0) claim();                          // lands while the prefix below is built
         if (tile_order) {
             // s_cls_start[r] = number of tiles in classes heavier than class (64 - r); s_cls_start[65] = all tiles
             int c0 = __ldg(tile_order + (64 - lane)), c1 = __ldg(tile_order + (32 - lane >= 0 ? 32 - lane : 0));
@@ -784,38 +835,26 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             __syncwarp();
         }
         long long tr_idx_wait = 0, tr_idx_fetch = 0, tr_idx_copy = 0, tr_idx_list = 0, tr_t = 0;
+        auto static_pos = [&](int j) -> int { return j < my_tiles ? (int)blockIdx.x + j * (int)gridDim.x : -1; };
+        // heaviest-first hand-out (btc_rulebook_tile_meta): position in the sequence -> (cost class, slot) -> tile id, so
+        // that the last tiles of a launch are its cheapest and the CTAs finish together
+        auto order_lookup = [&](int pos) -> int {
+            if (pos < 0 || !tile_order) return pos;
+            int lo_r = 0, hi_r = 65;                    // largest r with s_cls_start[r] <= pos
+            while (hi_r - lo_r > 1) {
+                const int mid = (lo_r + hi_r) >> 1;
+                if (s_cls_start[mid] <= pos) lo_r = mid; else hi_r = mid;
+            }
+            return __ldg(tile_order + 65 + (int64_t)(64 - lo_r) * tiles_cap + (pos - s_cls_start[lo_r]));
+        };
+        int tile_cur = -1;
+        if (lane == 0) tile_cur = order_lookup((int)blockIdx.x);    // iteration 0 (static and dynamic alike)
         for (int tl = 0;; ++tl) {
             const int buf = tl & 1;
-            int tile = -1;
             if (tr) tr_t = clock64();
-            if (lane == 0) {
-                mbar_wait(&nbr_empty[buf], ((tl >> 1) & 1) ^ 1);
-                if (tr) { const long long t = clock64(); tr_idx_wait += t - tr_t; tr_t = t; }
-                if (!tile_ctr) {
-                    tile = tl < my_tiles ? (int)blockIdx.x + tl * (int)gridDim.x : -1;
-                } else if (tl == 0) {
-                    tile = (int)blockIdx.x;
-                } else {
-                    const int t = atomicAdd(tile_ctr, 1);
-                    tile = P + t;
-                    if (tile >= num_tiles) {
-                        tile = -1;
-                        if (t == num_tiles - 1) atomicExch(tile_ctr, 0);
-                    }
-                }
-                // heaviest-first hand-out (btc_rulebook_tile_meta): position in the sequence -> (cost class, slot) -> tile
-                // id, so that the last tiles of a launch are its cheapest and the CTAs finish together
-                if (tile >= 0 && tile_order) {
-                    int lo_r = 0, hi_r = 65;                    // largest r with s_cls_start[r] <= tile
-                    while (hi_r - lo_r > 1) {
-                        const int mid = (lo_r + hi_r) >> 1;
-                        if (s_cls_start[mid] <= tile) lo_r = mid; else hi_r = mid;
-                    }
-                    tile = __ldg(tile_order + 65 + (int64_t)(64 - lo_r) * tiles_cap + (tile - s_cls_start[lo_r]));
-                }
-            }
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            if (tr && lane == 0) { const long long t = clock64(); tr_idx_fetch += t - tr_t; tr_t = t; }
+            if (lane == 0) mbar_wait(&nbr_empty[buf], ((tl >> 1) & 1) ^ 1);
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_wait += t - tr_t; tr_t = t; }
+            const int tile = __shfl_sync(0xffffffffu, tile_cur, 0);
             if (tile < 0) {                            // publish the end marker and leave
                 if (lane == 0) {
                     s_tile[buf] = -1;
@@ -833,6 +872,9 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             }
             const int row0 = tile * TC_BM;
             int* dst = nbr_s + buf * TC_BM * K;
+            unsigned long long m = 0;
+            int tile_nxt = -1;
+            bool have_nxt = false;
             if (lane == 0) {
                 const int rows = n_cap - row0 < TC_BM ? n_cap - row0 : TC_BM;
                 const uint32_t bytes = (uint32_t)rows * K * 4, bulk = bytes & ~15u;
@@ -841,16 +883,29 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                     mbar_expect_tx(&nbr_full[buf], bulk);
                     bulk_copy_g2s(dst, src, bulk, &nbr_full[buf]);
                 }
+                if (tile_mask) m = __ldg(tile_mask + tile);
+                // next iteration's tile id: from the local queue when it holds one (its order entry then has this whole
+                // iteration to arrive), else from the claim in flight — looked at below, after this tile's list is out
+                if (!tile_ctr) {
+                    tile_nxt = order_lookup(static_pos(tl + 1));
+                    have_nxt = true;
+                } else if (q_pos < q_end) {
+                    tile_nxt = order_lookup(q_pos++);
+                    have_nxt = true;
+                    if (q_pos == q_end && rem_est > 4 * P) claim();   // the queue just ran dry: claim the next batch now
+                } else {
+                    claim();
+                }
                 for (uint32_t e = bulk / 4; e < bytes / 4; ++e) dst[e] = __ldg(src + e);   // < 16-byte tail
                 mbar_arrive(&nbr_full[buf]);
             }
             __syncwarp();
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_fetch += t - tr_t; tr_t = t; }
             // offsets with at least one valid neighbour among the tile's live rows: precomputed with the rulebook
-            // (btc_rulebook_tile_meta), else scanned here from the staged index tile (~2.5 us per tile on one warp)
-            unsigned long long m = 0;
+            // (btc_rulebook_tile_meta; the chunk list is then built while the index block is still in flight), else scanned
+            // here from the staged index tile (~2.5 us per tile on one warp)
             if (tile_mask) {
-                m = __ldg(tile_mask + tile);
-                mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
+                m = __shfl_sync(0xffffffffu, m, 0);
             } else {
                 mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
                 const int rows_live = n - row0 < TC_BM ? n - row0 : TC_BM;
@@ -862,7 +917,6 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(m >> 32));
                 m = (unsigned long long)m_lo | ((unsigned long long)m_hi << 32);
             }
-            if (tr && lane == 0) { const long long t = clock64(); tr_idx_copy += t - tr_t; tr_t = t; }
             int cnt = 0;
             for (int c0 = 0; c0 < T; c0 += 32) {
                 const int c = c0 + lane;
@@ -883,10 +937,30 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 if (lane == 0) s_list[buf * T] = 0;
                 cnt = 1;
             }
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_list += t - tr_t; tr_t = t; }
+            if (tile_mask) mbar_wait(&nbr_full[buf], (tl >> 1) & 1);     // the index block has landed
             if (lane == 0) { s_cnt[buf] = cnt; s_tile[buf] = tile; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&list_full[buf]);
-            if (tr && lane == 0) { const long long t = clock64(); tr_idx_list += t - tr_t; tr_t = t; }
+            if (tr && lane == 0) { const long long t = clock64(); tr_idx_copy += t - tr_t; tr_t = t; }
+            if (lane == 0 && !have_nxt) {              // the queue was dry: take the first tile of the claim in flight
+                settle();
+                if (q_pos < q_end) {
+                    tile_nxt = order_lookup(q_pos++);
+                    if (q_pos == q_end && rem_est > 4 * P) claim();
+                }
+            }
+            tile_cur = tile_nxt;
+        }
+        // every CTA of the launch reports here after its last claim; the last one re-arms the counter pair for the next
+        // launch that is handed this slot
+        if (lane == 0 && tile_ctr) {
+            settle();
+            __threadfence();
+            if (atomicAdd(tile_ctr + 1, 1) == (int)gridDim.x - 1) {
+                atomicExch(tile_ctr, 0);
+                atomicExch(tile_ctr + 1, 0);
+            }
         }
     } else if (warp >= Roles::kEpi0 && warp < Roles::kEpi0 + 4) {
         // ================= epilogue =================
@@ -907,61 +981,55 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             float* dst = feat_out + (int64_t)row * c_out;
 #pragma unroll 1
             for (int c0 = 0; c0 < N; c0 += 16) {
+                if (c0 >= c_out) break;                       // padded accumulator columns (c_out < N): nothing to write
                 uint32_t acc[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * ACC_COLS + (uint32_t)c0, acc);
+                if (row < n) {
+                float x[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {              // broadcast vector loads of the column constants
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_ep_bias + c0 + 4 * j4);
+                    const float4 s4 = *reinterpret_cast<const float4*>(s_ep_scale + c0 + 4 * j4);
+                    const float4 h4 = *reinterpret_cast<const float4*>(s_ep_shift + c0 + 4 * j4);
+                    x[4 * j4 + 0] = (__uint_as_float(acc[4 * j4 + 0]) + b4.x) * s4.x + h4.x;
+                    x[4 * j4 + 1] = (__uint_as_float(acc[4 * j4 + 1]) + b4.y) * s4.y + h4.y;
+                    x[4 * j4 + 2] = (__uint_as_float(acc[4 * j4 + 2]) + b4.z) * s4.z + h4.z;
+                    x[4 * j4 + 3] = (__uint_as_float(acc[4 * j4 + 3]) + b4.w) * s4.w + h4.w;
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
                 if (SOUT) {
                     // split format out: 16 channels -> 8 packed bf16 hi words + 8 lo words of the row's 128-byte block
-                    if (row < n && c0 < c_out) {
-                        uint32_t hi[8], lo[8];
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int pp = 0; pp < 8; ++pp) {
-                            float x[2];
-#pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const int col = c0 + 2 * pp + jj;
-                                float t = __uint_as_float(acc[2 * pp + jj]);
-                                if (bias) t += __ldg(bias + col);
-                                if (scale) t = t * __ldg(scale + col) + __ldg(shift + col);
-                                if (relu) t = fmaxf(t, 0.f);
-                                x[jj] = t;
-                            }
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[0]), h1 = __float2bfloat16_rn(x[1]);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[0] - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(x[1] - __bfloat162float(h1));
-                            hi[pp] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[pp] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
-                        char* blk = reinterpret_cast<char*>(dst) + (c0 >> 5) * 128 + ((c0 >> 4) & 1) * 32;
-                        *reinterpret_cast<uint4*>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(blk + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                        *reinterpret_cast<uint4*>(blk + 64) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(blk + 80) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    for (int pp = 0; pp < 8; ++pp) {
+                        const float x0 = x[2 * pp], x1 = x[2 * pp + 1];
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                        const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                        const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                        hi[pp] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lo[pp] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                     }
-                } else
-                if (row < n && c0 < c_out) {
+                    char* blk = reinterpret_cast<char*>(dst) + (c0 >> 5) * 128 + ((c0 >> 4) & 1) * 32;
+                    *reinterpret_cast<uint4*>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(blk + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(blk + 64) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(blk + 80) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                } else {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        float o[4];
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int col = c0 + j4 * 4 + jj;
-                            float x = __uint_as_float(acc[j4 * 4 + jj]);
-                            if (col < c_out) {
-                                if (bias) x += __ldg(bias + col);
-                                if (scale) x = x * __ldg(scale + col) + __ldg(shift + col);
-                                if (relu) x = fmaxf(x, 0.f);
-                            }
-                            o[jj] = x;
-                        }
                         const int col = c0 + j4 * 4;
                         if (col + 3 < c_out) {
-                            *reinterpret_cast<float4*>(dst + col) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(dst + col) = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
                         } else {
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj)
-                                if (col + jj < c_out) dst[col + jj] = o[jj];
+                                if (col + jj < c_out) dst[col + jj] = x[4 * j4 + jj];
                         }
                     }
+                }
                 }
             }
             tc_fence_before();
@@ -1028,11 +1096,11 @@ __global__ void __launch_bounds__(128) tile_meta_kernel(const int* __restrict__ 
     }
 }
 
-// Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter at zero again (see
+// Tile counters of the dynamic scheduler: zero at module load, every launch leaves its counter pair at zero again (see
 // the scheduler warp).  Launches rotate through the slots, so kernels that overlap on different streams (or a captured
 // graph and eager launches) do not share one unless kTcCtrSlots launches are in flight at once.
 constexpr int kTcCtrSlots = 1024;
-__device__ int g_tc_tile_ctr[kTcCtrSlots];
+__device__ int g_tc_tile_ctr[2 * kTcCtrSlots];   // per slot: {next position, CTAs finished}
 static int g_tc_npw = 0, g_tc_dyn = -1, g_tc_diag = 0, g_tc_grid = kNumSM;
 static unsigned long long* g_tc_trace = nullptr;   // timeline diagnostics buffer (device, 32 u64 per CTA) or null
 
@@ -1046,7 +1114,7 @@ static int* next_tile_counter() {
         if (cudaGetSymbolAddress(&p, g_tc_tile_ctr) != cudaSuccess) return nullptr;
         base[dev] = (int*)p;
     }
-    return base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
+    return base[dev] + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kTcCtrSlots);
 }
 
 // dynamic shared memory of one CTA: weight ring + cp.async staging + two index tiles + two chunk lists + alignment slack
@@ -1064,8 +1132,9 @@ static int launch_tc_npw(const float* feat_in, const int* table, const float* pa
                          const float* scale, const float* shift, int relu, float* feat_out, const int* out_rows, int n_cap,
                          const int* n_dev, int K, int c_in, int c_out, cudaStream_t st,
                          const unsigned long long* tile_mask, const int* tile_order) {
-    static_assert(TcBStages<N>::value == (N <= 32 ? 6 : 4) && TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
-                  "tc_smem_bytes mirrors these");
+    static_assert(TcBStages<N, false>::value == (N <= 32 ? 6 : 4) && TcBStages<N, true>::value == 2 * TcBStages<N, false>::value &&
+                      TcDepth<N, NPW>::value == ((N > 64 || NPW > 8) ? 2 : 4),
+                  "tc_smem_bytes mirrors these (split format: twice the stages of half the bytes)");
     const size_t smem = tc_smem_bytes(N, NPW, K, c_in);
     auto kern = conv_fwd_tc_kernel<N, NPW, SIN, SOUT>;
     // opt in to > 48 KB dynamic smem: the attribute is per device / context, so it is tracked per device (not a stream op)
@@ -1196,8 +1265,8 @@ int btc_sparse_conv_tc_split_supported(int K, int c_in, int c_out, int in_split,
 int64_t btc_sparse_conv_tc_split_packed_bytes(int K, int c_in, int c_out) {
     if (!btc_sparse_conv_tc_split_supported(K, c_in, c_out, 1, 0)) return BTC_E_UNSUPPORTED;
     const int N = tc_padded_n(c_out);
-    const int ntile = (K * c_in + 63) / 64;
-    return (int64_t)ntile * 2 * N * 128;
+    const int nchunk = (K * c_in + TC_KC - 1) / TC_KC;
+    return (int64_t)nchunk * 2 * N * 64;
 }
 
 int btc_sparse_conv_tc_pack_split(const float* weight, int K, int c_in, int c_out, void* packed, void* stream) {
@@ -1205,8 +1274,8 @@ int btc_sparse_conv_tc_pack_split(const float* weight, int K, int c_in, int c_ou
     if (!btc_sparse_conv_tc_split_supported(K, c_in, c_out, 1, 0))
         return set_error(BTC_E_UNSUPPORTED, "btc_sparse_conv_tc_pack_split: shape not supported", cudaSuccess);
     const int N = tc_padded_n(c_out);
-    const int ntile = (K * c_in + 63) / 64;
-    const int64_t total = (int64_t)ntile * N * 64;
+    const int nchunk = (K * c_in + TC_KC - 1) / TC_KC;
+    const int64_t total = (int64_t)nchunk * N * TC_KC;
     tc_pack_weight_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, c_in, c_out, N,
                                                                                        (unsigned short*)packed);
     BTC_CHECK_LAUNCH("tc_pack_weight_split");

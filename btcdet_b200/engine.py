@@ -393,6 +393,13 @@ class BackbonePlan:
             "count_ready": [torch.cuda.Event() for _ in range(slots)],
             "d2h_done": [None] * slots,
             "copy_stream": torch.cuda.Stream(device=dev),
+            # host -> device on its own stream: the points of batch i + 1 cross PCIe while batch i computes, the main stream
+            # only pays a device-to-device copy into the graph's static input buffer
+            "h2d_stream": torch.cuda.Stream(device=dev),
+            "in_points": [torch.empty_like(self.points) for _ in range(slots)],
+            "in_offsets": [torch.empty_like(self.scene_offsets) for _ in range(slots)],
+            "in_ready": [torch.cuda.Event() for _ in range(slots)],
+            "in_free": [None] * slots,
         }
         return self
 
@@ -404,7 +411,25 @@ class BackbonePlan:
         main = torch.cuda.current_stream()
         if pl["d2h_done"][slot] is not None:
             main.wait_event(pl["d2h_done"][slot])      # the previous occupant of this slot has left the device
-        self.load_points(points, scene_offsets)
+        if points.is_cuda:
+            self.load_points(points, scene_offsets)
+        else:
+            n = points.shape[0]
+            if n > self.n_cap:
+                raise _lib.BtcError("batch of %d points exceeds the planned capacity %d" % (n, self.n_cap))
+            hs = pl["h2d_stream"]
+            if pl["in_free"][slot] is not None:
+                hs.wait_event(pl["in_free"][slot])     # the staging buffers' previous batch has been consumed
+            with torch.cuda.stream(hs):
+                pl["in_points"][slot][:n].copy_(points, non_blocking=True)
+                pl["in_offsets"][slot].copy_(scene_offsets, non_blocking=True)
+                pl["in_ready"][slot].record(hs)
+            main.wait_event(pl["in_ready"][slot])
+            self.points[:n].copy_(pl["in_points"][slot][:n], non_blocking=True)
+            self.scene_offsets.copy_(pl["in_offsets"][slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            pl["in_free"][slot] = ev
         self.step()
         st = ctypes.c_void_p(main.cuda_stream)
         C = self.out_feat.shape[1]

@@ -279,7 +279,7 @@ def tc_split_supported(K, c_in, c_out, in_split, out_split):
 
 
 def tc_pack_weight_split(weight):
-    """Pack [K,Cin,Cout] fp32 weights for a SPLIT-input layer (bf16 hi / lo tiles of 64 reduction elements)."""
+    """Pack [K,Cin,Cout] fp32 weights for a SPLIT-input layer (bf16 hi / lo tiles per 32-element reduction chunk, 64-byte swizzled rows)."""
     lib = _lib.load()
     _require_cuda(weight)
     c_in, c_out = weight.shape[-2], weight.shape[-1]

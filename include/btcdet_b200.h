@@ -311,7 +311,7 @@ int btc_rulebook_sort_rows(const int* nbr_out, int n_cap, const int* n_dev, int 
  * A layer whose INPUT is in split format (c_in % 32 == 0) gathers the packed operands as they are (no per-stage ALU work)
  * and runs three bf16 MMAs of K = 16 per k-step instead of three tf32 MMAs of K = 8; a layer whose OUTPUT is split
  * (c_out % 32 == 0) writes the format from its epilogue.  Weights for a split-input layer are packed by
- * btc_sparse_conv_tc_pack_split (bf16 hi / lo tiles of 64 reduction elements).  btc_features_to_split / _from_split
+ * btc_sparse_conv_tc_pack_split (bf16 hi / lo tiles per 32-element reduction chunk, SWIZZLE_64B rows).  btc_features_to_split / _from_split
  * convert whole feature matrices (tests, or a consumer that needs fp32).  Accuracy: ~2^-16 per product, inside the 1e-4
  * parity bar (tests/test_parity_gpu.py).  in_split / out_split = 0 reproduces btc_sparse_conv_fwd_tc_meta.
  */

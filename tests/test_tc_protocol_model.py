@@ -406,8 +406,11 @@ def _tiles(rng, n, T, style):
 
 
 CONFIGS = [
-    dict(STAGES=4, G=4, CG=1, DEPTH=2, DYN=1),     # shipped: N = 64, 16 producer warps
-    dict(STAGES=6, G=4, CG=1, DEPTH=2, DYN=1),     # shipped: N = 32
+    dict(STAGES=4, G=4, CG=1, DEPTH=2, DYN=1),     # shipped: N = 64, 16 producer warps, fp32 rows
+    dict(STAGES=6, G=4, CG=1, DEPTH=2, DYN=1),     # shipped: N = 32, fp32 rows
+    dict(STAGES=8, G=4, CG=1, DEPTH=2, DYN=1),     # shipped: N = 64, split rows (rings twice as deep)
+    dict(STAGES=12, G=4, CG=1, DEPTH=2, DYN=1),    # shipped: N = 32, split rows
+    dict(STAGES=8, G=2, CG=1, DEPTH=2, DYN=1),     # shipped: N = 128, split rows (8 producer warps)
     dict(STAGES=4, G=2, CG=1, DEPTH=4, DYN=1),     # 8 producer warps (N = 128 uses DEPTH 2)
     dict(STAGES=4, G=4, CG=1, DEPTH=2, DYN=0),     # static tiles
     dict(STAGES=4, G=4, CG=2, DEPTH=2, DYN=1),     # experimental commit groups
