@@ -116,7 +116,8 @@ class OccBackbone(nn.Module):
 
     def forward(self, batch_dict):
         x = spconv.SparseConvTensor(features=batch_dict["voxel_features"], indices=batch_dict["voxel_coords"].int(),
-                                    spatial_shape=self.sparse_shape, batch_size=batch_dict["batch_size"])
+                                    spatial_shape=self.sparse_shape, batch_size=batch_dict["batch_size"],
+                                    n_dev=batch_dict.get("voxel_n_dev"))      # static mode when the count is on the device
         x = self.deconv5(self.deconv4(self.conv3(self.conv2(self.conv1(x)))))
         batch_dict.update({"encoded_spconv_tensor": x, "encoded_spconv_tensor_stride": 1})
         return batch_dict
@@ -188,11 +189,12 @@ class DetBackboneOcc(nn.Module):
     def forward(self, batch_dict):
         coords = batch_dict["voxel_coords"].int()
         B = batch_dict["batch_size"]
+        n_dev = batch_dict.get("voxel_n_dev")             # static mode when the count is on the device
         x = spconv.SparseConvTensor(features=batch_dict["voxel_features"], indices=coords, spatial_shape=self.sparse_shape,
-                                    batch_size=B)
+                                    batch_size=B, n_dev=n_dev)
         x_conv1 = self.conv1(x)
         occ_in = spconv.SparseConvTensor(features=batch_dict["occ_voxel_features"], indices=coords,
-                                         spatial_shape=self.sparse_shape, batch_size=B)     # fresh rulebook cache (:959-964)
+                                         spatial_shape=self.sparse_shape, batch_size=B, n_dev=n_dev)   # fresh rulebook cache (:959-964)
         x_conv1 = self.conv1_combine(x_conv1)
         x_conv2 = self.conv2(x_conv1)
         x_occ2 = self.occ_conv2(occ_in)

@@ -1229,8 +1229,10 @@ int btc_sparse_conv_tc_trace(void* trace_u64) {
 }
 
 int btc_sparse_conv_tc_supported(int K, int c_in, int c_out) {
-    if (!(K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 4 && c_out % 4 == 0 && tc_padded_n(c_out) != 0 &&
-          (int64_t)K * c_in >= 32))
+    // c_out: a multiple of 4 (vector stores of 16-byte aligned row pieces) or below 4 (scalar stores: the occupancy head's
+    // 32 -> 2 and 32 -> 3 sub-manifold convolutions, occ_head_3D.py:25-31)
+    if (!(K >= 1 && K <= 64 && c_in >= 4 && c_in % 4 == 0 && c_out >= 1 && (c_out % 4 == 0 || c_out < 4) &&
+          tc_padded_n(c_out) != 0 && (int64_t)K * c_in >= 32))
         return 0;
     const int N = tc_padded_n(c_out);   // the index tiles of large kernels (K > 33) do not fit next to the rings
     return tc_smem_bytes(N, N <= 64 ? 16 : 8, K, c_in) <= kTcMaxSmem && tc_smem_bytes(N, 8, K, c_in) <= kTcMaxSmem ? 1 : 0;

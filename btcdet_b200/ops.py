@@ -99,6 +99,64 @@ def build_hash(coords: torch.Tensor, batch: int, shape, n_dev=None) -> CoordInde
 
 
 # ------------------------------------------------------------------------------------------
+# static (capacity) mode: device-side counts instead of exact shapes
+# ------------------------------------------------------------------------------------------
+class StaticChecks:
+    """(device count, capacity, what) triples registered by the capacity-sized allocations of a static-mode forward;
+    `verify()` reads them all with ONE device->host copy (after the forward / graph replay) and raises if a capacity
+    was exceeded — the kernels clamp silently at their capacities."""
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, n_dev, cap, what):
+        self.items.append((n_dev, int(cap), what))
+
+    def verify(self):
+        if not self.items:
+            return []
+        counts = torch.cat([n.reshape(1).to(torch.int32) for n, _, _ in self.items]).tolist()
+        for c, (_, cap, what) in zip(counts, self.items):
+            if c > cap:
+                raise _lib.BtcError("static-mode capacity exceeded: %s has %d rows > capacity %d" % (what, c, cap))
+        return counts
+
+
+_static_checks: Optional[StaticChecks] = None
+
+
+class static_checks:
+    """`with ops.static_checks() as chk:` collects the capacity checks of the static-mode calls made inside."""
+
+    def __enter__(self):
+        global _static_checks
+        self.prev, _static_checks = _static_checks, StaticChecks()
+        return _static_checks
+
+    def __exit__(self, *exc):
+        global _static_checks
+        _static_checks = self.prev
+        return False
+
+
+def _register_cap(n_dev, cap, what):
+    if _static_checks is not None:
+        _static_checks.add(n_dev, cap, what)
+
+
+STATIC_GROWTH = 1.0   # capacity of a strided level relative to its input level (static mode; overflow is checked)
+
+
+def _static_cap(n_in_cap, ksize, stride, transposed, cells):
+    """Output capacity of a static-mode rulebook: the true bound (every input touches prod(ceil(k/s)) outputs, k^3 for
+    stride-1 / transposed layers) where the grid is small, else STATIC_GROWTH x the input capacity (checked afterwards)."""
+    true_bound = _out_bound(n_in_cap, ksize, stride, transposed, cells)
+    if transposed or all(int(st) == 1 for st in stride):
+        return true_bound
+    return max(1, min(true_bound, max(1024, int(STATIC_GROWTH * n_in_cap))))
+
+
+# ------------------------------------------------------------------------------------------
 # rulebooks
 # ------------------------------------------------------------------------------------------
 @dataclass
@@ -124,8 +182,13 @@ class Rulebook:
     dilation: list
     transposed: bool = False
     out_index: Optional[CoordIndex] = None
+    # static (capacity) mode: the tables are capacity-sized and the live row counts stay on the device — no host read,
+    # the whole forward is CUDA-graph capturable (SparseConvTensor.n_dev); None = exact shapes
+    n_in_dev: Optional[torch.Tensor] = None
+    n_out_dev: Optional[torch.Tensor] = None
     _pairs: Optional[tuple] = field(default=None, repr=False)
     _sorted: Optional[tuple] = field(default=None, repr=False)
+    _meta: Optional[tuple] = field(default=None, repr=False)
 
     def sorted_rows(self):
         """(nbr_sorted, out_rows): the output-stationary table with rows reordered by valid-offset mask inside
@@ -133,6 +196,14 @@ class Rulebook:
         if self._sorted is None:
             self._sorted = rulebook_sort_rows(self.nbr_out)
         return self._sorted
+
+    def tile_meta(self):
+        """(tile_mask [tiles] i64, tile_order) of nbr_out for the tcgen05 tile (btc_rulebook_tile_meta), computed once per
+        rulebook; (None, None) for kernels with more than 64 offsets."""
+        if self._meta is None:
+            self._meta = rulebook_tile_meta(self.nbr_out, self.n_out_dev) if self.K <= 64 and self.nbr_out.shape[0] > 0 \
+                else (None, None)
+        return self._meta
 
     def inverse(self) -> "Rulebook":
         """Rulebook of SparseInverseConv3d: swap the pair directions."""
@@ -142,7 +213,8 @@ class Rulebook:
         else:
             nbr_out_inv, nbr_in_inv = self.nbr_in, self.nbr_out
         return Rulebook(nbr_out_inv, nbr_in_inv, None, self.n_out, self.n_in, self.K, self.subm, self.out_shape,
-                        self.in_shape, self.ksize, self.stride, self.padding, self.dilation, not self.transposed)
+                        self.in_shape, self.ksize, self.stride, self.padding, self.dilation, not self.transposed,
+                        n_in_dev=self.n_out_dev, n_out_dev=self.n_in_dev)
 
     def pairs(self):
         """spconv-1.2.1-format (indice_pairs [2,K,N_in], indice_pair_num [K]) in canonical order."""
@@ -153,7 +225,7 @@ class Rulebook:
 
 
 def rulebook_subm(coords: torch.Tensor, batch: int, shape, ksize, dilation=1,
-                  index: Optional[CoordIndex] = None) -> Rulebook:
+                  index: Optional[CoordIndex] = None, n_dev: Optional[torch.Tensor] = None) -> Rulebook:
     _require_cuda(coords)
     lib = _lib.load()
     ksize, dilation = _triple(ksize), _triple(dilation)
@@ -163,18 +235,18 @@ def rulebook_subm(coords: torch.Tensor, batch: int, shape, ksize, dilation=1,
     n = coords.shape[0]
     K = ksize[0] * ksize[1] * ksize[2]
     if index is None:
-        index = build_hash(coords, batch, shape)
+        index = build_hash(coords, batch, shape, n_dev=n_dev)
     nbr = torch.empty((n, K), dtype=torch.int32, device=coords.device)
     if index.hash_keys is not None:
-        check(lib.btc_rulebook_subm_hash(_ptr(coords), n, None, int(batch), int3(shape), int3(ksize), int3(dilation),
+        check(lib.btc_rulebook_subm_hash(_ptr(coords), n, _ptr(n_dev), int(batch), int3(shape), int3(ksize), int3(dilation),
                                          _ptr(index.hash_keys), _ptr(index.hash_vals), index.hash_keys.numel(),
                                          _ptr(nbr), _stream()), "btc_rulebook_subm_hash")
     else:
-        check(lib.btc_rulebook_subm(_ptr(coords), n, None, int(batch), int3(shape), int3(ksize), int3(dilation),
+        check(lib.btc_rulebook_subm(_ptr(coords), n, _ptr(n_dev), int(batch), int3(shape), int3(ksize), int3(dilation),
                                     _ptr(index.entries), index.entries.numel(), _ptr(index.perm), _ptr(nbr), _stream()),
               "btc_rulebook_subm")
     return Rulebook(nbr, None, coords, n, n, K, True, list(shape), list(shape), ksize, [1, 1, 1],
-                    [k // 2 for k in ksize], dilation, False, index)
+                    [k // 2 for k in ksize], dilation, False, index, n_in_dev=n_dev, n_out_dev=n_dev)
 
 
 def _out_bound(n_in, ksize, stride, transposed, cells):
@@ -188,8 +260,10 @@ def _out_bound(n_in, ksize, stride, transposed, cells):
 
 
 def rulebook_conv(coords: torch.Tensor, batch: int, in_shape, ksize, stride=1, padding=0, dilation=1,
-                  transposed=False, output_padding=0, out_cap: Optional[int] = None) -> Rulebook:
-    """Regular / transposed sparse conv (and pooling) rulebook.  One host read of n_out."""
+                  transposed=False, output_padding=0, out_cap: Optional[int] = None,
+                  n_dev: Optional[torch.Tensor] = None) -> Rulebook:
+    """Regular / transposed sparse conv (and pooling) rulebook.  One host read of n_out — none in static mode (`n_dev`
+    given: `coords` is capacity-sized with n_dev live rows, the result is capacity-sized with its count on the device)."""
     _require_cuda(coords)
     lib = _lib.load()
     ksize, stride, padding, dilation = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
@@ -206,24 +280,33 @@ def rulebook_conv(coords: torch.Tensor, batch: int, in_shape, ksize, stride=1, p
     dev = coords.device
     out_entries = index_entries(batch, out_shape)
     cells = batch * out_shape[0] * out_shape[1] * out_shape[2]
-    cap = out_cap if out_cap is not None else _out_bound(n_in, ksize, stride, transposed, cells)
+    static = n_dev is not None
+    if out_cap is not None:
+        cap = out_cap
+    else:
+        cap = _static_cap(n_in, ksize, stride, transposed, cells) if static else _out_bound(n_in, ksize, stride, transposed, cells)
     out_index = torch.zeros(out_entries, dtype=torch.int64, device=dev)
     summary = torch.zeros(int(lib.btc_index_summary_words(out_entries)), dtype=torch.int32, device=dev)
-    out_coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    # static mode: dead coordinate rows stay zero so that torch gathers through them remain in bounds
+    out_coords = (torch.zeros if static else torch.empty)((cap, 4), dtype=torch.int32, device=dev)
     nbr_out = torch.empty((cap, K), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((max(n_in, 1), K), dtype=torch.int32, device=dev)
     n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_bytes = int(lib.btc_rulebook_conv_sparse_workspace_bytes(out_entries))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     # sparse two-level build (freshly zeroed bitmaps; the rank bitmap stays populated for sub-manifold layers on this level)
-    check(lib.btc_rulebook_conv_sparse(_ptr(coords), n_in, None, int(batch), int3(in_shape), int3(out_shape), int3(ksize),
+    check(lib.btc_rulebook_conv_sparse(_ptr(coords), n_in, _ptr(n_dev), int(batch), int3(in_shape), int3(out_shape), int3(ksize),
                                        int3(stride), int3(padding), int3(dilation), int(bool(transposed)), _ptr(out_index),
                                        out_entries, _ptr(summary), _ptr(out_coords), cap, _ptr(n_out_dev), _ptr(nbr_out),
                                        _ptr(nbr_in), _ptr(ws), ws_bytes, _stream()), "btc_rulebook_conv_sparse")
+    idx = CoordIndex(out_index, None, int(batch), out_shape)
+    if static:
+        _register_cap(n_out_dev, cap, "rulebook %s -> %s" % (in_shape, out_shape))
+        return Rulebook(nbr_out, nbr_in, out_coords, n_in, cap, K, False, in_shape, out_shape, ksize, stride, padding,
+                        dilation, bool(transposed), idx, n_in_dev=n_dev, n_out_dev=n_out_dev)
     n_out = int(n_out_dev.item())  # the one host sync of a new rulebook (exact tensor shapes for torch)
     if n_out > cap:
         raise _lib.BtcError("rulebook capacity exceeded: %d output sites > capacity %d" % (n_out, cap))
-    idx = CoordIndex(out_index, None, int(batch), out_shape)
     return Rulebook(nbr_out[:n_out], nbr_in[:n_in], out_coords[:n_out], n_in, n_out, K, False, in_shape, out_shape,
                     ksize, stride, padding, dilation, bool(transposed), idx)
 
@@ -346,6 +429,21 @@ def tc_pack_weight(weight):
     return packed
 
 
+def rulebook_tile_meta(nbr_out, n_out_dev=None):
+    """btc_rulebook_tile_meta: per 128-row tile the mask of offsets with at least one valid neighbour, and the tiles
+    bucketed by cost class (heaviest-first hand-out order of the tcgen05 tile)."""
+    _require_cuda(nbr_out)
+    lib = _lib.load()
+    nbr_out = nbr_out.contiguous()
+    n_out, K = nbr_out.shape
+    tiles = (n_out + 127) // 128
+    tile_mask = torch.empty(max(tiles, 1), dtype=torch.int64, device=nbr_out.device)
+    tile_order = torch.empty(int(lib.btc_rulebook_tile_order_ints(n_out)), dtype=torch.int32, device=nbr_out.device)
+    check(lib.btc_rulebook_tile_meta(_ptr(nbr_out), n_out, _ptr(n_out_dev), K, _ptr(tile_mask), _ptr(tile_order), _stream()),
+          "btc_rulebook_tile_meta")
+    return tile_mask, tile_order
+
+
 def rulebook_sort_rows(nbr_out, n_out_dev=None, out=None):
     """btc_rulebook_sort_rows: rows of nbr_out reordered by valid-offset mask within 2048-row windows.
     Returns (nbr_sorted [N_out, K], out_rows [N_out]); row i of nbr_sorted is row out_rows[i] of nbr_out."""
@@ -424,19 +522,33 @@ class SparseConvFunction(torch.autograd.Function):
     whenever that shape qualifies (algo != 1); dW / db are fp32 outer products with atomics."""
 
     @staticmethod
-    def forward(ctx, features, weight, bias, rulebook: Rulebook, algo):
+    def forward(ctx, features, weight, bias, rulebook: Rulebook, algo, epilogue=None):
         c_in, c_out = weight.shape[-2], weight.shape[-1]
+        scale, shift, relu = epilogue if epilogue is not None else (None, None, False)
+        if epilogue is not None and c_in % 4 != 0 and algo != 1:
+            # inference fast path: zero-pad the input channels to a multiple of 4 (16-byte gather pieces) so that thin odd
+            # layers (the detection backbone's 6 -> 16 input convolution) run on the tcgen05 tile as well
+            pad = 4 - c_in % 4
+            features = torch.nn.functional.pad(features, (0, pad))
+            weight = torch.nn.functional.pad(weight, (0, 0, 0, pad))
+            c_in += pad
+        if epilogue is not None and (features.requires_grad or weight.requires_grad) and torch.is_grad_enabled():
+            raise _lib.BtcError("the fused conv epilogue is inference-only (no backward through the folded BatchNorm)")
         use_tc = algo != 1 and tc_supported(rulebook.K, c_in, c_out) and features.shape[0] > 0 \
             and features.data_ptr() % 16 == 0
         if algo == 2 and not use_tc:
             raise _lib.BtcError("tensor-core tile requested for an unsupported shape (K=%d Cin=%d Cout=%d)" %
                                 (rulebook.K, c_in, c_out))
         if use_tc:
-            nbr_sorted, out_rows = rulebook.sorted_rows()
-            out = sparse_conv_fwd_tc(features.contiguous(), nbr_sorted, _packed_weight(weight), c_in, c_out, bias,
-                                     out_rows=out_rows)
+            # per-tile offset masks + heaviest-first tile order, computed once per rulebook (one launch; the mask sort this
+            # replaced cost 18 launches / 1.26 ms of a 5.5 ms config-3 step and saved less than it cost)
+            tile_mask, tile_order = rulebook.tile_meta()
+            out = sparse_conv_fwd_tc_split(features.contiguous(), rulebook.nbr_out, _packed_weight(weight), c_in, c_out,
+                                           False, False, bias=bias, scale=scale, shift=shift, relu=relu,
+                                           n_out_dev=rulebook.n_out_dev, tile_mask=tile_mask, tile_order=tile_order)
         else:
-            out = sparse_conv_fwd(features, rulebook.nbr_out, weight, bias, algo=1)
+            out = sparse_conv_fwd(features, rulebook.nbr_out, weight, bias, scale, shift, relu, algo=1,
+                                  n_out_dev=rulebook.n_out_dev)
         ctx.save_for_backward(features, weight)
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
@@ -465,17 +577,17 @@ class SparseConvFunction(torch.autograd.Function):
                 d_feat = sparse_conv_bwd_data(d_out, table, mirror, weight, n_in)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             d_w, d_b = sparse_conv_bwd_weight(features, d_out, rb.nbr_out, tuple(weight.shape), ctx.has_bias)
-        return d_feat, d_w, d_b, None, None
+        return d_feat, d_w, d_b, None, None, None
 
 
-def maxpool_fwd(features, nbr_out):
+def maxpool_fwd(features, nbr_out, n_out_dev=None):
     lib = _lib.load()
     _require_cuda(features, nbr_out)
     n_out, K = nbr_out.shape
     c = features.shape[1]
     features, nbr_out = features.contiguous(), nbr_out.contiguous()
     out = torch.empty((n_out, c), dtype=torch.float32, device=features.device)
-    check(lib.btc_maxpool_fwd(_ptr(features), _ptr(nbr_out), _ptr(out), n_out, None, K, c, _stream()),
+    check(lib.btc_maxpool_fwd(_ptr(features), _ptr(nbr_out), _ptr(out), n_out, _ptr(n_out_dev), K, c, _stream()),
           "btc_maxpool_fwd")
     return out
 
@@ -483,7 +595,7 @@ def maxpool_fwd(features, nbr_out):
 class SparseMaxPoolFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, rulebook: Rulebook):
-        out = maxpool_fwd(features, rulebook.nbr_out)
+        out = maxpool_fwd(features, rulebook.nbr_out, rulebook.n_out_dev)
         ctx.save_for_backward(features, out)
         ctx.rulebook = rulebook
         return out
@@ -505,13 +617,13 @@ class ToDenseFunction(torch.autograd.Function):
     """SparseConvTensor.dense(): [N,C] rows -> [B,C,D,H,W] (channels first)."""
 
     @staticmethod
-    def forward(ctx, features, coords, batch, shape):
+    def forward(ctx, features, coords, batch, shape, n_dev=None):
         lib = _lib.load()
         _require_cuda(features, coords)
         features, coords = features.contiguous(), coords.contiguous()
         n, c = features.shape
         out = torch.empty((batch, c, shape[0], shape[1], shape[2]), dtype=torch.float32, device=features.device)
-        check(lib.btc_to_dense(_ptr(features), _ptr(coords), n, None, c, int(batch), int3(shape), _ptr(out), _stream()),
+        check(lib.btc_to_dense(_ptr(features), _ptr(coords), n, _ptr(n_dev), c, int(batch), int3(shape), _ptr(out), _stream()),
               "btc_to_dense")
         ctx.save_for_backward(coords)
         ctx.geom = (n, c, int(batch), list(shape))
@@ -526,7 +638,7 @@ class ToDenseFunction(torch.autograd.Function):
         d_feat = torch.empty((n, c), dtype=torch.float32, device=d_out.device)
         check(lib.btc_from_dense(_ptr(d_out), _ptr(coords), n, None, c, batch, int3(shape), _ptr(d_feat), _stream()),
               "btc_from_dense")
-        return d_feat, None, None, None
+        return d_feat, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -645,7 +757,8 @@ def occ_geometry_arrays(voxel_size, point_cloud_range, support_sphere_range, dis
     return gf, gi
 
 
-def occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom_i, rot_z=None, want_sphere=False):
+def occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom_i, rot_z=None, want_sphere=False,
+                n_dev=None):
     """Fused GPU occupancy / occlusion masks.  Returns a dict of uint8 [B,nz,ny,nx] tensors."""
     _require_cuda(voxels, voxel_coords, voxel_num_points)
     lib = _lib.load()
@@ -664,7 +777,7 @@ def occ_targets(voxels, voxel_coords, voxel_num_points, batch_size, geom_f, geom
     ws_bytes = int(lib.btc_occ_targets_workspace_bytes(B, gf, gi))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rz = None if rot_z is None else rot_z.to(torch.float32).contiguous()
-    check(lib.btc_occ_targets(_ptr(voxels), P, C, _ptr(coords), _ptr(nump), m, None, B, _ptr(rz), gf, gi,
+    check(lib.btc_occ_targets(_ptr(voxels), P, C, _ptr(coords), _ptr(nump), m, _ptr(n_dev), B, _ptr(rz), gf, gi,
                               _ptr(out["voxelwise_mask"]), _ptr(out["vcc_mask"]), _ptr(out["occ_voxelwise_mask"]),
                               _ptr(out["general_cls_loss_mask"]), _ptr(sphere), _ptr(ws), ws_bytes, _stream()),
           "btc_occ_targets")
@@ -859,7 +972,7 @@ def occ_select(probs, residuals, thresh, max_points, occ_voxel_size, occ_origin,
     return out
 
 
-def occ_vfe(voxels, voxel_num_points, num_raw_features=4):
+def occ_vfe(voxels, voxel_num_points, num_raw_features=4, n_dev=None):
     """OccVFE.forward (btcdet/models/backbones_3d/vfe/occ_vfe.py:24-55): returns (voxel_features [M,C], occ_voxel_features)."""
     _require_cuda(voxels, voxel_num_points)
     lib = _lib.load()
@@ -868,8 +981,8 @@ def occ_vfe(voxels, voxel_num_points, num_raw_features=4):
     m, P, C = voxels.shape
     feats = torch.empty((m, C), dtype=torch.float32, device=voxels.device)
     occ = torch.empty((m, C - num_raw_features), dtype=torch.float32, device=voxels.device)
-    check(lib.btc_occ_vfe(_ptr(voxels), _ptr(nump), m, None, P, C, int(num_raw_features), _ptr(feats), _ptr(occ), _stream()),
-          "btc_occ_vfe")
+    check(lib.btc_occ_vfe(_ptr(voxels), _ptr(nump), m, _ptr(n_dev), P, C, int(num_raw_features), _ptr(feats), _ptr(occ),
+                          _stream()), "btc_occ_vfe")
     return feats, occ
 
 
@@ -892,3 +1005,93 @@ def pass_occ_vox(probs, residuals, det_voxels, det_voxel_num_points, det_voxel_c
     shape = [int(det_grid[2]), int(det_grid[1]), int(det_grid[0])]
     voxels, counts, vox_coords = revoxelize_sorted(coords, points, batch_size, shape)
     return voxels, counts, vox_coords, sel
+
+
+# ------------------------------------------------------------------------------------------
+# static (capacity) mode of the injection stage: no host read anywhere, CUDA-graph capturable
+# ------------------------------------------------------------------------------------------
+def occ_select_static(probs, residuals, thresh, max_points, cap, occ_voxel_size, occ_origin, det_voxel_size, det_range,
+                      det_grid, rot_z=None, inten=0.0):
+    """occ_select with a fixed capacity `cap` and the counts left on the device: returns (dict of capacity-sized tensors,
+    counts [B+1] i32 with counts[B] = total).  The reference's top-k branch (more than `max_points` cells above threshold
+    in one scene, add_occ_template.py:117-121) is not taken here: the per-scene counts are registered as capacity checks
+    (ops.static_checks) and the caller falls back to the exact path when one fails."""
+    _require_cuda(probs)
+    lib = _lib.load()
+    dev = probs.device
+    probs = probs.to(torch.float32).contiguous()
+    res = None if residuals is None else residuals.to(torch.float32).contiguous()
+    B, nz, ny, nx = probs.shape
+    grid = int3([nx, ny, nz])
+    ws_bytes = int(lib.btc_occ_select_workspace_bytes(B, grid))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    gf = float_array(list(occ_voxel_size) + list(occ_origin) + list(det_voxel_size) + list(det_range[:3]))
+    rz = None if rot_z is None else rot_z.to(torch.float32).contiguous()
+    out = {"occ_coords": torch.zeros((cap, 4), dtype=torch.int32, device=dev),
+           "occ_probs": torch.zeros(cap, dtype=torch.float32, device=dev),
+           "occ_xyz": torch.zeros((cap, 3), dtype=torch.float32, device=dev),
+           "det_coords": torch.zeros((cap, 4), dtype=torch.int32, device=dev),
+           "occ_points": torch.zeros((cap, 6), dtype=torch.float32, device=dev)}
+    counts = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    check(lib.btc_occ_select(_ptr(probs), _ptr(res), B, grid, ctypes.c_float(thresh), _ptr(rz), gf, int3(det_grid),
+                             ctypes.c_float(inten), cap, _ptr(out["occ_coords"]), _ptr(out["occ_probs"]),
+                             _ptr(out["occ_xyz"]), _ptr(out["det_coords"]), _ptr(out["occ_points"]), _ptr(counts),
+                             _ptr(ws), ws_bytes, _stream()), "btc_occ_select")
+    _register_cap(counts[B:B + 1], cap, "occupancy cells above threshold")
+    for b in range(B):
+        _register_cap(counts[b:b + 1], int(max_points), "occupancy cells above threshold in scene %d (top-k branch)" % b)
+    return out, counts
+
+
+def pass_occ_vox_static(probs, residuals, det_voxels, det_voxel_num_points, det_voxel_coords, det_n_dev, batch_size, thresh,
+                        max_points, occ_cap, vox_cap, p_max, occ_voxel_size, occ_origin, det_voxel_size, det_range, det_grid,
+                        rot_z=None, inten=0.0):
+    """pass_occ_vox without a host read.  det_voxels [Mcap, P, C] / det_voxel_num_points [Mcap] / det_voxel_coords
+    [Mcap, 4] are capacity-sized with det_n_dev live rows.  Returns (voxels [vox_cap, p_max, C+2], num_points [vox_cap]
+    i32, coords [vox_cap, 4] i32 (dead rows zero), m_dev [1] i32, selection dict, selection counts)."""
+    lib = _lib.load()
+    dev = det_voxels.device
+    sel, sel_counts = occ_select_static(probs, residuals, thresh, max_points, occ_cap, occ_voxel_size, occ_origin, det_voxel_size,
+                                        det_range, det_grid, rot_z=rot_z, inten=inten)
+    Mcap, P, C = det_voxels.shape
+    # raw points of the live det voxels in (voxel, slot) order == det_voxels[mask] of the reference (pass_occ_vox.py:33-41),
+    # as static-shape index arithmetic: point j lives in the voxel whose inclusive count prefix first exceeds j
+    nump = det_voxel_num_points.to(torch.int64)
+    live = torch.arange(Mcap, device=dev) < det_n_dev.to(torch.int64)
+    nump = torch.where(live, nump, torch.zeros_like(nump))
+    ends = torch.cumsum(nump, 0)
+    total_gt = ends[-1]
+    j = torch.arange(Mcap * P, device=dev)
+    vox = torch.searchsorted(ends, j, right=True).clamp_(max=Mcap - 1)
+    slot = (j - (ends[vox] - nump[vox])).clamp_(0, P - 1)
+    cap_pts = Mcap * P + occ_cap + 1                    # last row: dump for the dead occupancy rows
+    points = torch.zeros((cap_pts, C + 2), dtype=torch.float32, device=dev)
+    coords = torch.zeros((cap_pts, 4), dtype=torch.int32, device=dev)
+    points[:Mcap * P, :C] = det_voxels.to(torch.float32)[vox, slot]
+    coords[:Mcap * P] = det_voxel_coords.to(torch.int32)[vox]
+    # occupancy pseudo points go right behind the live raw points
+    n_occ = sel_counts[batch_size].to(torch.int64)
+    i = torch.arange(occ_cap, device=dev)
+    dst = torch.where(i < n_occ, total_gt + i, torch.full_like(i, cap_pts - 1))
+    points.index_copy_(0, dst, sel["occ_points"])
+    coords.index_copy_(0, dst, sel["det_coords"])
+    n_pts = (total_gt + n_occ).to(torch.int32).reshape(1)
+    shape = [int(det_grid[2]), int(det_grid[1]), int(det_grid[0])]
+    n_entries = index_entries(batch_size, shape)
+    index = torch.zeros(n_entries, dtype=torch.int64, device=dev)
+    vox_coords = torch.zeros((vox_cap, 4), dtype=torch.int32, device=dev)
+    vox_count = torch.zeros(vox_cap, dtype=torch.int32, device=dev)
+    slots = torch.empty(cap_pts, dtype=torch.int32, device=dev)
+    pt_voxel = torch.empty(cap_pts, dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.btc_revoxelize_workspace_bytes(max(cap_pts, vox_cap), n_entries))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.btc_revoxelize(_ptr(coords), cap_pts, _ptr(n_pts), int(batch_size), int3(shape), _ptr(index), n_entries,
+                             _ptr(vox_coords), vox_cap, _ptr(vox_count), _ptr(slots), _ptr(pt_voxel), _ptr(counts[0:1]),
+                             _ptr(counts[1:2]), _ptr(ws), ws_bytes, _stream()), "btc_revoxelize")
+    _register_cap(counts[0:1], vox_cap, "re-voxelised det voxels")
+    _register_cap(counts[1:2], p_max, "points per re-voxelised voxel")
+    voxels = torch.empty((vox_cap, p_max, C + 2), dtype=torch.float32, device=dev)
+    check(lib.btc_revoxelize_fill(_ptr(points), _ptr(pt_voxel), _ptr(slots), cap_pts, _ptr(n_pts), C + 2, p_max, _ptr(voxels),
+                                  vox_cap, _stream()), "btc_revoxelize_fill")
+    return voxels, vox_count, vox_coords, counts[0:1], sel, sel_counts

@@ -84,7 +84,9 @@ class SparseConvolution(SparseModule):
                 "subm={subm}, transposed={transposed}, inverse={inverse}, indice_key={indice_key}").format(
                     **self.__dict__)
 
-    def forward(self, input):
+    def forward(self, input, epilogue=None):
+        """epilogue (extension): (scale [Cout], shift [Cout], relu) applied inside the kernel after the bias — what
+        SparseSequential folds an eval-mode BatchNorm1d + ReLU into in static mode."""
         assert isinstance(input, SparseConvTensor)
         features = input.features
         indices = input.indices
@@ -99,7 +101,11 @@ class SparseConvolution(SparseModule):
             out_features = torch.mm(features, self.weight.view(self.in_channels, self.out_channels))
             if self.bias is not None:
                 out_features = out_features + self.bias
-            out_tensor = SparseConvTensor(out_features, indices, spatial_shape, batch_size)
+            if epilogue is not None:
+                out_features = out_features * epilogue[0] + epilogue[1]
+                if epilogue[2]:
+                    out_features = torch.relu(out_features)
+            out_tensor = SparseConvTensor(out_features, indices, spatial_shape, batch_size, n_dev=input.n_dev)
             out_tensor.indice_dict = input.indice_dict
             out_tensor.grid = input.grid
             out_tensor._index = input._index
@@ -128,14 +134,14 @@ class SparseConvolution(SparseModule):
                 d3 = _pad3(self.dilation, nd, 1)
                 if self.subm:
                     if input._index is None:
-                        input._index = _ops.build_hash(coords4, batch_size, shape3)
-                    rulebook = _ops.rulebook_subm(coords4, batch_size, shape3, k3, d3, index=input._index)
+                        input._index = _ops.build_hash(coords4, batch_size, shape3, n_dev=input.n_dev)
+                    rulebook = _ops.rulebook_subm(coords4, batch_size, shape3, k3, d3, index=input._index, n_dev=input.n_dev)
                     out_indices, out_spatial_shape = indices, spatial_shape
                     out_index = input._index
                 else:
                     rulebook = _ops.rulebook_conv(coords4, batch_size, shape3, k3, _pad3(self.stride, nd, 1),
                                                   _pad3(self.padding, nd, 0), d3, transposed=self.transposed,
-                                                  output_padding=_pad3(self.output_padding, nd, 0))
+                                                  output_padding=_pad3(self.output_padding, nd, 0), n_dev=input.n_dev)
                     out_indices = rulebook.out_coords if nd == 3 else rulebook.out_coords[:, [0, 2, 3]].contiguous()
                     out_spatial_shape = rulebook.out_shape if nd == 3 else rulebook.out_shape[1:]
                     out_index = rulebook.out_index
@@ -148,8 +154,8 @@ class SparseConvolution(SparseModule):
                     "in_index": input._index,
                 }
 
-        out_features = _ops.SparseConvFunction.apply(features, self.weight, self.bias, rulebook, self.algo)
-        out_tensor = SparseConvTensor(out_features, out_indices, out_spatial_shape, batch_size)
+        out_features = _ops.SparseConvFunction.apply(features, self.weight, self.bias, rulebook, self.algo, epilogue)
+        out_tensor = SparseConvTensor(out_features, out_indices, out_spatial_shape, batch_size, n_dev=rulebook.n_out_dev)
         out_tensor.indice_dict = input.indice_dict
         out_tensor.grid = input.grid
         out_tensor._index = out_index

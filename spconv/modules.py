@@ -69,11 +69,23 @@ class SparseSequential(SparseModule):
         self.add_module(name, module)
 
     def forward(self, input):
-        for k, module in self._modules.items():
+        mods = list(self._modules.items())
+        skip = 0
+        for i, (k, module) in enumerate(mods):
+            if skip:
+                skip -= 1
+                continue
             if is_spconv_module(module):
                 assert isinstance(input, SparseConvTensor)
                 self._sparity_dict[k] = input.sparity
-                input = module(input)
+                # static mode (SparseConvTensor.n_dev): an eval-mode BatchNorm1d (+ ReLU) behind a convolution is folded into
+                # the convolution's epilogue (per-channel affine + max) — no elementwise passes over capacity-sized rows
+                fuse = _fusable_epilogue(module, mods, i) if getattr(input, "n_dev", None) is not None else None
+                if fuse is not None:
+                    scale, shift, relu, skip = fuse
+                    input = module(input, epilogue=(scale, shift, relu))
+                else:
+                    input = module(input)
             else:
                 if isinstance(input, SparseConvTensor):
                     if input.indices.shape[0] != 0:
@@ -85,6 +97,29 @@ class SparseSequential(SparseModule):
     def fused(self):
         """spconv's conv+BN fusion helper; not used by the reference."""
         raise NotImplementedError("SparseSequential.fused() is not part of the BtcDet hot path")
+
+
+def _fusable_epilogue(conv, mods, i):
+    """(scale, shift, relu, modules consumed) when mods[i + 1] is an eval-mode BatchNorm1d (optionally followed by ReLU)."""
+    from .conv import SparseConvolution
+    if not isinstance(conv, SparseConvolution) or i + 1 >= len(mods):
+        return None
+    bn = mods[i + 1][1]
+    if not isinstance(bn, nn.BatchNorm1d) or bn.training or not bn.track_running_stats or bn.running_var is None:
+        return None
+    key = (bn.running_var._version, bn.running_mean._version,
+           None if bn.weight is None else bn.weight._version, None if bn.bias is None else bn.bias._version)
+    cached = getattr(bn, "_btc_fold", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            w = bn.weight if bn.weight is not None else torch.ones_like(bn.running_var)
+            b = bn.bias if bn.bias is not None else torch.zeros_like(bn.running_var)
+            scale = (w / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+            shift = (b - bn.running_mean * scale).float().contiguous()
+        cached = (key, scale, shift)
+        bn._btc_fold = cached
+    relu = i + 2 < len(mods) and isinstance(mods[i + 2][1], nn.ReLU)
+    return cached[1], cached[2], relu, (2 if relu else 1)
 
 
 class ToDense(SparseModule):

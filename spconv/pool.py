@@ -31,17 +31,17 @@ class SparseMaxPool(SparseModule):
         k3, d3 = _pad3(self.kernel_size, nd, 1), _pad3(self.dilation, nd, 1)
         if self.subm:
             if input._index is None:
-                input._index = _ops.build_hash(coords4, batch_size, shape3)
-            rulebook = _ops.rulebook_subm(coords4, batch_size, shape3, k3, d3, index=input._index)
+                input._index = _ops.build_hash(coords4, batch_size, shape3, n_dev=input.n_dev)
+            rulebook = _ops.rulebook_subm(coords4, batch_size, shape3, k3, d3, index=input._index, n_dev=input.n_dev)
             out_indices, out_spatial_shape, out_index = input.indices, input.spatial_shape, input._index
         else:
             rulebook = _ops.rulebook_conv(coords4, batch_size, shape3, k3, _pad3(self.stride, nd, 1),
-                                          _pad3(self.padding, nd, 0), d3, transposed=False)
+                                          _pad3(self.padding, nd, 0), d3, transposed=False, n_dev=input.n_dev)
             out_indices = rulebook.out_coords if nd == 3 else rulebook.out_coords[:, [0, 2, 3]].contiguous()
             out_spatial_shape = rulebook.out_shape if nd == 3 else rulebook.out_shape[1:]
             out_index = rulebook.out_index
         out_features = _ops.SparseMaxPoolFunction.apply(features, rulebook)
-        out_tensor = SparseConvTensor(out_features, out_indices, out_spatial_shape, batch_size)
+        out_tensor = SparseConvTensor(out_features, out_indices, out_spatial_shape, batch_size, n_dev=rulebook.n_out_dev)
         out_tensor.indice_dict = input.indice_dict
         out_tensor.grid = input.grid
         out_tensor._index = out_index

@@ -7,11 +7,15 @@ from btcdet_b200 import ops as _ops
 
 
 class SparseConvTensor(object):
-    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, n_dev=None):
         """
         features: [N, C] float32; indices: [N, ndim+1] int32 rows (batch, *spatial) — 3-D (b,z,y,x)
         or 2-D (b,y,x); spatial_shape: list/array of ndim ints; grid: kept for API compatibility
         (spconv's dense lookup grid; the B200 path uses a rank bitmap kept in `_index`).
+        n_dev (extension, not in spconv): int32 [1] CUDA tensor = number of live rows; features / indices are then
+        capacity-sized ("static mode"): every layer keeps its counts on the device, allocates capacity-sized outputs
+        and never reads the host, so a whole forward can be captured in one CUDA graph (inference; train-mode
+        BatchNorm would average over the dead rows).
         """
         self.features = features
         self.indices = indices
@@ -20,6 +24,7 @@ class SparseConvTensor(object):
         self.indice_dict = {}
         self.grid = grid
         self._index = None  # btcdet_b200.ops.CoordIndex of `indices`, filled lazily
+        self.n_dev = n_dev
 
     @property
     def spatial_size(self):
@@ -49,7 +54,7 @@ class SparseConvTensor(object):
     def dense(self, channels_first=True):
         """zeros [B, *spatial, C], index-assign rows, permute to channels first."""
         shape3 = self._shape3()
-        out = _ops.ToDenseFunction.apply(self.features, self._coords4(), int(self.batch_size), shape3)
+        out = _ops.ToDenseFunction.apply(self.features, self._coords4(), int(self.batch_size), shape3, self.n_dev)
         if len(self.spatial_shape) == 2:
             out = out.squeeze(2)
         if not channels_first:
