@@ -156,22 +156,26 @@ def dominant_roofline(per_layer, specs, tot_ms, B):
     achieved = dom["bytes"] / (dom_us * 1e-6) / 1e9
     # DRAM / L2 bytes of exactly this launch from the committed ncu capture (null when the workload differs)
     traffic = l2_bytes = None
-    tr_path = os.path.join(ROOT, "profiles", "r1_final_conv_tc_traffic.json")
+    tr_path = os.path.join(ROOT, "profiles", "r2_conv_tc_traffic.json")
+    tensor_pct = None
     if os.path.exists(tr_path):
         tr = json.load(open(tr_path))
         if tr["config"]["scenes_per_step_per_gpu"] == B and tr["config"]["n_out"] == key[3] and (key[1], key[2]) == (64, 64):
-            traffic, l2_bytes = tr["dram_bytes_per_launch"], tr["l2_bytes_per_launch"]
+            traffic, l2_bytes = tr["dram_bytes_per_launch"], tr.get("l2_to_sm_read_bytes_per_launch", tr["l2_bytes_per_launch"])
+            tensor_pct = tr.get("tensor_pipe_pct_active")
     roof = {"bound": "hbm",
             "kernel": "conv_fwd_tc gather-GEMM, %s %d->%d K=%d on %d rows (%d identical launches per step, %.0f%% of the conv time)"
                       % (key[0], key[1], key[2], key[4], key[3], dom["n"], 100.0 * dom["us"] / (tot_ms * 1e3)),
             "achieved": round(achieved, 2), "peak": peak_gbs, "unit": "GB/s", "frac": round(achieved / peak_gbs, 5),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback",
-            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1_final_conv_tc_ncu_full.md" if traffic else None,
+            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r2_conv_tc_ncu.json" if traffic else None,
+            "tensor_pipe_pct_active_ncu": tensor_pct,
             "alg_bytes_per_launch": dom["bytes"], "alg_flops_per_launch": dom["flops"], "us_per_launch": round(dom_us, 2),
             "achieved_tflops": round(dom["flops"] / (dom_us * 1e-6) / 1e12, 3),
             "l2_to_sm_bytes_per_launch": l2_bytes,
-            "note": "working set is L2-resident (DRAM < 5% of peak in ncu); the binding resource is L2->SM traffic "
-                    "(13x the algorithmic bytes: re-streamed weight tiles + gathers), see profiles/",
+            "note": "working set is L2-resident (DRAM ~8% of peak in ncu, 0.7x the algorithmic bytes); L2->SM traffic is 8.6x the "
+                    "algorithmic bytes (weight tiles re-streamed per 128-row tile + gathers); the binding resources are the "
+                    "per-stage hand-off of the issuing warp and the producers' LSU issue (DESIGN.md section 4)",
             "all_conv_layers": {"launches": len(specs), "alg_bytes_per_step": alg_bytes, "alg_flops_per_step": alg_flops,
                                 "conv_ms_per_step": round(tot_ms, 4),
                                 "achieved_gbs": round(alg_bytes / (tot_ms * 1e-3) / 1e9, 2),
@@ -185,6 +189,10 @@ def run_ours(args, rank, world):
     _lib.load()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
+    # one process per GPU: cores / first-touch pinned memory on the GPU's own NUMA node (before anything is pinned)
+    from btcdet_b200 import dist as btc_dist
+    host_binding = btc_dist.bind_host_to_gpu(dev.index or 0, int(os.environ.get("LOCAL_RANK", 0)),
+                                             int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     B = args.batch
     model = build_model()
     if args.conv_grid:
@@ -344,6 +352,7 @@ def run_ours(args, rank, world):
                          "result rows to pinned host memory" % (len(dev_batches), B),
                    "cuda_graph": not args.no_graph, "conv_algo": args.algo, "mask_sorted_rows": args.sort,
                    "level_sites": counts},
+        "host_binding": host_binding,
         "e2e": {"value": round(scenes_total / (ms_e2e * 1e-3), 2), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": plan.launches_per_step * args.steps,
@@ -476,7 +485,12 @@ def main():
 
     if world > 1:
         torch.distributed.init_process_group("nccl")
+    all_cores = os.sched_getaffinity(0)
     res, scenes = run_ours(args, rank, world)
+    try:
+        os.sched_setaffinity(0, all_cores)      # the CPU baseline below may use every core again (run_ours bound this rank)
+    except OSError:
+        pass
     if rank == 0:
         if not args.no_cpu_baseline:
             n_cpu = args.cpu_scenes or 6

@@ -70,6 +70,7 @@ SIGNATURES = {
     "btc_occ_select": (_i, [_p, _p, _i, _p, ctypes.c_float, _p, _p, _p, ctypes.c_float, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_occ_abs_mean_vfe": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p]),
     "btc_occ_vfe": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
+    "btc_occ_head_prob": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _p]),
     "btc_occ_box_targets_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "btc_occ_box_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i,
                                  _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

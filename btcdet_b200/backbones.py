@@ -136,10 +136,19 @@ class OccHead(nn.Module):
 
     def forward(self, batch_dict):
         enc = batch_dict["encoded_spconv_tensor"]
-        logits = self.conv_cls(enc).dense()
-        prob = torch.softmax(logits, dim=1)[:, -1:, ...]
-        batch_dict["pred_occ_logit"] = logits
-        batch_dict["batch_pred_occ_prob"] = prob[:, -1, ...] * batch_dict["general_cls_loss_mask"]
+        cls = self.conv_cls(enc)
+        if batch_dict.get("fused_occ_head", False) and not torch.is_grad_enabled():
+            # inference: probability volume straight from the sparse rows (btc_occ_head_prob) — no dense
+            # logits, no softmax / product passes over [B, 2, 9, 157, 209]
+            from . import ops
+            nz, ny, nx = [int(v) for v in cls.spatial_shape]
+            batch_dict["batch_pred_occ_prob"] = ops.occ_head_prob(cls.features, cls.indices, batch_dict["batch_size"], (nx, ny, nz),
+                                                                  batch_dict["general_cls_loss_mask"], n_dev=cls.n_dev)
+        else:
+            logits = cls.dense()
+            prob = torch.softmax(logits, dim=1)[:, -1:, ...]
+            batch_dict["pred_occ_logit"] = logits
+            batch_dict["batch_pred_occ_prob"] = prob[:, -1, ...] * batch_dict["general_cls_loss_mask"]
         batch_dict["pred_sem_residuals"] = self.conv_res(enc).dense()
         return batch_dict
 

@@ -165,7 +165,7 @@ class PlannedHotPath:
         m, inp, B = self.model, self.inp, self.B
         gf, gi = m.geom
         rot = inp["rot_z"]
-        bd = {"batch_size": B, "is_train": False}
+        bd = {"batch_size": B, "is_train": False, "fused_occ_head": True}
         with torch.no_grad():
             tg = ops.occ_targets(inp["voxels"], inp["voxel_coords"], inp["voxel_num_points"], B, gf, gi, rot_z=rot,
                                  n_dev=inp["n_occ"])

@@ -305,6 +305,34 @@ __global__ void occ_emit_kernel(const float* __restrict__ probs, const float* __
     }
 }
 
+// OccHead3D.forward tail (occ_head_3D.py:46-49) without the dense logits volume: prob = softmax(dense(logits), dim=1)[:, -1]
+// * mask.  A cell without an active site has logits (0, .., 0) -> softmax 1 / n_cls (0.5 for the two-class head), so the
+// volume is `mask / n_cls` everywhere and the active rows overwrite their cells with their own softmax (max-subtracted,
+// expf, sum in class order, one division — the op order of torch's softmax kernel).
+__global__ void occ_head_fill_kernel(const unsigned char* __restrict__ mask, int64_t cells, float base, float* __restrict__ prob) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < cells; t += (int64_t)gridDim.x * blockDim.x)
+        prob[t] = mask ? __fmul_rn(base, (float)mask[t]) : base;
+}
+__global__ void occ_head_rows_kernel(const float* __restrict__ logits, const int4* __restrict__ coords, int n_cap,
+                                     const int* __restrict__ n_dev, int n_cls, int nx, int ny, int nz,
+                                     const unsigned char* __restrict__ mask, float* __restrict__ prob) {
+    const int n = live_count(n_cap, n_dev);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const float* l = logits + (int64_t)r * n_cls;
+        float m = l[0];
+        for (int c = 1; c < n_cls; ++c) m = fmaxf(m, l[c]);
+        float sum = 0.f, last = 0.f;
+        for (int c = 0; c < n_cls; ++c) {
+            last = expf(__fsub_rn(l[c], m));
+            sum = __fadd_rn(sum, last);
+        }
+        const int4 q = coords[r];          // (b, z, y, x)
+        const int64_t cell = (((int64_t)q.x * nz + q.y) * ny + q.z) * nx + q.w;
+        const float p = __fdiv_rn(last, sum);
+        prob[cell] = mask ? __fmul_rn(p, (float)mask[cell]) : p;
+    }
+}
+
 // OccVFE (occ_vfe.py:24-55): slots with code < 0.05 are raw points, the others injected occupancy points.
 __global__ void occ_vfe_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points, int m_cap,
                                const int* __restrict__ m_dev, int P, int C, int n_raw, float* __restrict__ feats,
@@ -451,6 +479,22 @@ int btc_occ_abs_mean_vfe(const float* voxels, int max_points, int n_feat, const 
     occ_abs_vfe_kernel<<<grid_for(m_cap, 128), 128, 0, (cudaStream_t)stream>>>(voxels, max_points, n_feat, num_points, m_cap, m_dev,
                                                                               voxels_abs, voxel_mean);
     BTC_CHECK_LAUNCH("occ_abs_vfe");
+    return BTC_OK;
+}
+
+int btc_occ_head_prob(const float* logits, const int* coords, int n_cap, const int* n_dev, int n_cls, int batch, const int* grid,
+                      const unsigned char* mask, float* prob, void* stream) {
+    if (!grid || batch < 1 || n_cls < 1 || n_cap < 0) return badarg("btc_occ_head_prob: bad sizes");
+    if (!prob) return badarg("btc_occ_head_prob: null output");
+    const int64_t cells = (int64_t)batch * grid[0] * grid[1] * grid[2];
+    cudaStream_t st = (cudaStream_t)stream;
+    occ_head_fill_kernel<<<grid_for(cells, 256), 256, 0, st>>>(mask, cells, 1.0f / (float)n_cls, prob);
+    if (n_cap > 0) {
+        if (!logits || !coords) return badarg("btc_occ_head_prob: null inputs");
+        occ_head_rows_kernel<<<grid_for(n_cap, 256), 256, 0, st>>>(logits, (const int4*)coords, n_cap, n_dev, n_cls, grid[0], grid[1],
+                                                                   grid[2], mask, prob);
+    }
+    BTC_CHECK_LAUNCH("occ_head_prob");
     return BTC_OK;
 }
 

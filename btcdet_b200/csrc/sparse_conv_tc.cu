@@ -904,8 +904,14 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
             // offsets with at least one valid neighbour among the tile's live rows: precomputed with the rulebook
             // (btc_rulebook_tile_meta; the chunk list is then built while the index block is still in flight), else scanned
             // here from the staged index tile (~2.5 us per tile on one warp)
+            // Thin layers (c_in <= 16: a 32-element chunk spans two or more offsets, and a 128-row tile of a LiDAR scene
+            // touches practically all of them) take every chunk as active when no mask is given: skipping is only an
+            // optimisation, and neither the mask launch (22 us on the serial front of the step) nor the scan pays there.
+            const bool dense = !tile_mask && c_in <= 16;
             if (tile_mask) {
                 m = __shfl_sync(0xffffffffu, m, 0);
+            } else if (dense) {
+                m = ~0ull;
             } else {
                 mbar_wait(&nbr_full[buf], (tl >> 1) & 1);
                 const int rows_live = n - row0 < TC_BM ? n - row0 : TC_BM;
@@ -938,7 +944,7 @@ conv_fwd_tc_kernel(const float* __restrict__ feat_in, const int* __restrict__ ta
                 cnt = 1;
             }
             if (tr && lane == 0) { const long long t = clock64(); tr_idx_list += t - tr_t; tr_t = t; }
-            if (tile_mask) mbar_wait(&nbr_full[buf], (tl >> 1) & 1);     // the index block has landed
+            if (tile_mask || dense) mbar_wait(&nbr_full[buf], (tl >> 1) & 1);     // the index block has landed
             if (lane == 0) { s_cnt[buf] = cnt; s_tile[buf] = tile; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&list_full[buf]);

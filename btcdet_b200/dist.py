@@ -48,3 +48,46 @@ def sum_over_ranks(value, device="cpu"):
 def aggregate_throughput(units_this_rank, seconds_this_rank, device="cpu"):
     """Whole-job units/s = all ranks' units / slowest rank's time."""
     return sum_over_ranks(units_this_rank, device) / max_over_ranks(seconds_this_rank, device)
+
+
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index, local_rank=0, local_world=1):
+    """Pin this process to cores of the NUMA node its GPU hangs off (a disjoint slice per local rank), BEFORE pinned host
+    buffers are allocated, so that first-touch places them on that node: with one process per GPU the host side of the
+    end-to-end path (37 MB of pinned H2D + D2H per step and GPU) otherwise crosses the socket interconnect for half of
+    the GPUs (round-1 SCALE: e2e efficiency 0.59 at 8 GPUs with every rank on cores 0-31 / node 0).
+    Returns a small dict for the bench line; never raises (containers may forbid any of this)."""
+    import os
+    info = {"numa_node": None, "cores": None, "bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = _cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = os.sched_getaffinity(0)
+        mine = sorted(cpus & allowed)
+        if not mine:
+            info["note"] = "the GPU's node has no core in this process' allowed set (%d allowed cores)" % len(allowed)
+            return info
+        # ranks that share the node share its cores evenly (at least two cores each: main thread + copy / NCCL threads)
+        per = max(2, len(mine) // max(1, local_world))
+        lo = (local_rank * per) % len(mine)
+        sl = (mine + mine)[lo:lo + per]
+        os.sched_setaffinity(0, set(sl))
+        info.update({"cores": len(sl), "bound": True})
+    except Exception as e:      # noqa: BLE001
+        info["note"] = repr(e)[:120]
+    return info

@@ -122,8 +122,13 @@ class BackbonePlan:
             key = conv.indice_key
             rb = self.rulebooks.get(key) if key is not None else None
             if rb is None:
+                # (thin sub-manifold layers, c_in <= 16, run all chunks: no mask launch — see the index loader of conv_fwd_tc;
+                # measured: 131 -> 124 us for the two level-1 layers plus 22 us of mask launch off the serial front of the
+                # step, while the strided 16 -> 32 layer loses 15 us without its masks and keeps them)
+                users = [c for c, _ in specs[li:] if c is conv or (key is not None and c.indice_key == key)]
                 want_meta = self.tile_meta and not self.sort_rows and K <= 64 and self.algo != 1 and \
-                    ops.tc_supported(K, conv.in_channels, conv.out_channels)
+                    ops.tc_supported(K, conv.in_channels, conv.out_channels) and \
+                    (not conv.subm or any(c.in_channels > 16 for c in users))
                 if conv.subm:
                     if cur_lvl.index is None and cur_lvl.hash_keys is None:
                         self._add_index(cur_lvl)

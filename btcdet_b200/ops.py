@@ -542,7 +542,8 @@ class SparseConvFunction(torch.autograd.Function):
         if use_tc:
             # per-tile offset masks + heaviest-first tile order, computed once per rulebook (one launch; the mask sort this
             # replaced cost 18 launches / 1.26 ms of a 5.5 ms config-3 step and saved less than it cost)
-            tile_mask, tile_order = rulebook.tile_meta()
+            # (thin sub-manifold layers run every chunk: the mask launch does not pay there)
+            tile_mask, tile_order = rulebook.tile_meta() if (c_in > 16 or not rulebook.subm) else (None, None)
             out = sparse_conv_fwd_tc_split(features.contiguous(), rulebook.nbr_out, _packed_weight(weight), c_in, c_out,
                                            False, False, bias=bias, scale=scale, shift=shift, relu=relu,
                                            n_out_dev=rulebook.n_out_dev, tile_mask=tile_mask, tile_order=tile_order)
@@ -970,6 +971,21 @@ def occ_select(probs, residuals, thresh, max_points, occ_voxel_size, occ_origin,
         out = {k: v[keep] for k, v in out.items()}
     out["counts"] = c
     return out
+
+
+def occ_head_prob(logits, coords, batch_size, grid_xyz, mask=None, n_dev=None):
+    """softmax(dense(logits), dim=1)[:, -1] * mask of OccHead3D.forward (occ_head_3D.py:46-49) from the head's sparse rows:
+    logits [N, n_cls], coords [N, 4] (b,z,y,x), grid_xyz = (nx, ny, nz), mask u8 [B,nz,ny,nx] or None -> prob f32 [B,nz,ny,nx]."""
+    _require_cuda(logits, coords)
+    lib = _lib.load()
+    logits = logits.to(torch.float32).contiguous()
+    coords = coords.to(torch.int32).contiguous()
+    nx, ny, nz = [int(v) for v in grid_xyz]
+    prob = torch.empty((int(batch_size), nz, ny, nx), dtype=torch.float32, device=logits.device)
+    m = None if mask is None else mask.to(torch.uint8).contiguous()
+    check(lib.btc_occ_head_prob(_ptr(logits), _ptr(coords), logits.shape[0], _ptr(n_dev), logits.shape[1], int(batch_size),
+                                int3([nx, ny, nz]), _ptr(m), _ptr(prob), _stream()), "btc_occ_head_prob")
+    return prob
 
 
 def occ_vfe(voxels, voxel_num_points, num_raw_features=4, n_dev=None):

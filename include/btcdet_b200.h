@@ -471,6 +471,13 @@ int btc_occ_select(const float* probs, const float* residuals, int batch, const 
                    int* counts, void* workspace, int64_t workspace_bytes, void* stream);
 int btc_occ_vfe(const float* voxels, const int* num_points, int m_cap, const int* m_dev, int P, int C,
                 int num_raw, float* feats, float* occ_feats, void* stream);
+/* SURVEY §8(f) N4, occupancy-head half: the tail of OccHead3D.forward (occ_pnt/occ_dense_heads/occ_head_3D.py:46-49),
+ * `softmax(conv_cls(x).dense(), dim=1)[:, -1] * general_cls_loss_mask`, straight from the head's sparse rows — the
+ * [B, n_cls, nz, ny, nx] logits volume, the softmax pass over it and the mask product are never materialised.
+ * logits [n_cap, n_cls], coords [n_cap, 4] (b,z,y,x), grid = (nx, ny, nz), mask u8 [B,nz,ny,nx] or NULL -> prob f32 [B,nz,ny,nx]
+ * (cells without an active site: softmax of all-zero logits = 1/n_cls, times the mask, as dense() + softmax gives). */
+int btc_occ_head_prob(const float* logits, const int* coords, int n_cap, const int* n_dev, int n_cls, int batch,
+                      const int* grid, const unsigned char* mask, float* prob, void* stream);
 /* MeanVFE of the occupancy branch (occ side): occ_targets_3d.py:45-47 (USE_ABSXYZ) rewrites every slot of
  * the cylindrical occ voxels to cylinder_uvd2absxyz(rho, phi, z) + extra columns, mean_vfe.py:27-44 then averages all
  * slots / clamp_min(count, 1).  voxels [m_cap, max_points, n_feat] (rho, phi_deg, z, ...) -> voxels_abs (same shape, may

@@ -80,7 +80,8 @@ def test_tensor_core_tile_host_queries(lib_path):
                          (2, 128, 64), (27, 256, 128), (27, 128, 128), (27, 32, 2 * 2)]:
         assert sup(K, cin, cout) == 1, (K, cin, cout)
     assert sup(27, 6, 16) == 0 and sup(27, 34, 32) == 0          # c_in % 4 != 0 -> FFMA tile
-    assert sup(27, 32, 3) == 0 and sup(27, 32, 256) == 0         # c_out % 4 != 0 / > 128
+    assert sup(27, 32, 6) == 0 and sup(27, 32, 256) == 0         # c_out % 4 != 0 (>= 4: misaligned vector stores) / > 128
+    assert sup(27, 32, 2) == 1 and sup(27, 32, 3) == 1           # the occupancy head's 32 -> 2 / 32 -> 3 (scalar stores)
     assert sup(1, 4, 16) == 0                                    # reduction shorter than one 32-element stage
     assert sup(33, 32, 64) == 1 and sup(34, 32, 64) == 0         # two [128 x K] index tiles must fit next to the rings
     assert sup(49, 32, 32) == 1 and sup(50, 32, 32) == 0         # (the N = 32 weight ring is 16 KB smaller)

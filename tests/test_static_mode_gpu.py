@@ -125,3 +125,25 @@ def test_planned_chain_one_graph_matches_eager_chain(cuda):
         assert np.array_equal(_live(enc.indices, n), enc_r.indices.cpu().numpy())
         assert _rel(_live(enc.features, n), enc_r.features.cpu().numpy()) < 1e-4
         assert _rel(out["spatial_features"].cpu().numpy(), ref["spatial_features"].cpu().numpy()) < 1e-4
+
+
+def test_fused_occ_head_probability_equals_dense_softmax(cuda):
+    """btc_occ_head_prob against the reference's op sequence dense() -> softmax(dim=1)[:, -1] * mask
+    (occ_head_3D.py:46-49) on random sparse logits, including cells without an active site (softmax of zeros = 0.5)."""
+    import spconv
+    from btcdet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, nz, ny, nx = 2, 9, 157, 209
+    cells = B * nz * ny * nx
+    pick = torch.randperm(cells, device="cuda", generator=g)[:40000].sort().values
+    b, rem = pick // (nz * ny * nx), pick % (nz * ny * nx)
+    coords = torch.stack([b, rem // (ny * nx), (rem // nx) % ny, rem % nx], dim=1).int()
+    logits = torch.randn((coords.shape[0], 2), device="cuda", generator=g) * 3
+    mask = (torch.rand((B, nz, ny, nx), device="cuda", generator=g) > 0.4).to(torch.uint8)
+    dense = spconv.SparseConvTensor(logits, coords, [nz, ny, nx], B).dense()
+    want = torch.softmax(dense, dim=1)[:, -1] * mask
+    got = ops.occ_head_prob(logits, coords, B, (nx, ny, nz), mask)
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-7)
+    assert float((got - want).abs().max()) <= 6e-8          # one ulp of 0.5: same op order as torch's softmax
+    torch.testing.assert_close(ops.occ_head_prob(logits, coords, B, (nx, ny, nz), None), torch.softmax(dense, dim=1)[:, -1],
+                               rtol=1e-6, atol=1e-7)
