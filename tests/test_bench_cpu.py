@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _layers():
-    rec = json.load(open(os.path.join(ROOT, "profiles", "r1_final_bench_b16.json")))
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_b16.json")))
     per_layer = rec["roofline"]["per_layer"]
     specs = []
     n_in = rec["config"]["level_sites"][0]
@@ -28,11 +28,14 @@ def test_dominant_roofline_object():
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in roof
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s"
-    assert "64->64" in roof["kernel"] and "163309" in roof["kernel"]      # the level-3 SubM pair dominates
+    tr = json.load(open(os.path.join(ROOT, "profiles", "r2_conv_tc_traffic.json")))
+    n_out, pairs = tr["config"]["n_out"], tr["config"]["pairs"]
+    assert "64->64" in roof["kernel"] and str(n_out) in roof["kernel"]      # the level-3 SubM pair dominates
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-4
-    # algorithmic bytes per launch of that layer and the matching ncu capture
-    assert roof["alg_bytes_per_launch"] == 4 * 163309 * 64 * 2 + 8 * 1535511 + 4 * 27 * 64 * 64
-    assert roof["traffic"] == json.load(open(os.path.join(ROOT, "profiles", "r1_final_conv_tc_traffic.json")))["dram_bytes_per_launch"]
+    # algorithmic bytes per launch of that layer and the matching ncu capture (same batch, same row count)
+    assert roof["alg_bytes_per_launch"] == 4 * n_out * 64 * 2 + 8 * pairs + 4 * 27 * 64 * 64
+    assert roof["traffic"] == tr["dram_bytes_per_launch"]
+    assert roof["tensor_pipe_pct_active_ncu"] == tr["tensor_pipe_pct_active"]
     assert roof["all_conv_layers"]["launches"] == 12
     # a different workload must not inherit the captured traffic
     roof2 = bench.dominant_roofline(per_layer, specs, tot_ms, 8)
