@@ -196,6 +196,7 @@ class BackbonePlan:
         self.graph = None
         # (a high-priority rulebook stream, side_priority=-1, was measured: no effect on the captured step, 1515 us both ways)
         self._side_stream = torch.cuda.Stream(device=dev, priority=side_priority)
+        self._side_stream2 = torch.cuda.Stream(device=dev, priority=side_priority)
         self.launches_per_step = 0
         self.host_counts = torch.zeros(len(self.levels) + 1, dtype=torch.int32).pin_memory()
 
@@ -224,45 +225,89 @@ class BackbonePlan:
     def _run(self):
         """Enqueue the whole step (no host synchronisation anywhere).
 
-        Two streams: the rulebook chain (voxelise -> hash -> neighbour tables of every level) depends only on
-        coordinates, the convolution chain only needs rulebook l before layer l.  Running them on separate
-        streams (parallel branches of the captured graph) hides the ~50 small latency-bound indexing kernels
-        behind the tensor-core layers, whose persistent CTAs (448 threads, one per SM) leave room on every SM.
+        Three streams (parallel branches of the captured graph).  The rulebook work depends only on coordinates and is a
+        DAG, not a chain: the strided rulebooks form the critical path (voxelise -> level 2 -> level 3 -> ...), while
+        each level's hash / sub-manifold table / tile metadata / bitmap clear hang off it.  `side` carries the critical
+        path, `side2` everything else, `main` the convolutions, each behind the events of exactly what it reads.  The
+        small latency-bound indexing kernels then overlap each other (they only get SM time in the gaps between the
+        persistent convolution launches, which hold every SM's registers and shared memory).
         """
-        lib, B = self.lib, self.batch
         main = torch.cuda.current_stream()
-        side = self._side_stream
+        side, side2 = self._side_stream, self._side_stream2
         launches = 0
-        lvl0 = self.levels[0]
         side.wait_stream(main)
-        last_rb_event = None
-        with torch.cuda.stream(side):
-            launches += self.launch_voxelize(ctypes.c_void_p(side.cuda_stream))
-            last_rb_event = torch.cuda.Event()
-            last_rb_event.record(side)
-        # pass 1: the whole rulebook chain on the side stream, one event per step
-        conv_deps = []
+        side2.wait_stream(main)
+        written, readers = {}, {}     # resource -> event of its last writer / events of the reads since then
+
+        def enqueue(stream, reads, writes, fn):
+            for r in reads:
+                ev = written.get(r)
+                if ev is not None and ev[1] is not stream:
+                    stream.wait_event(ev[0])
+            for w in writes:                     # write-after-read / write-after-write across streams
+                for ev in readers.get(w, []) + ([written[w]] if w in written else []):
+                    if ev[1] is not stream:
+                        stream.wait_event(ev[0])
+            with torch.cuda.stream(stream):
+                n = fn(ctypes.c_void_p(stream.cuda_stream))
+                e = torch.cuda.Event()
+                e.record(stream)
+            for r in reads:
+                readers.setdefault(r, []).append((e, stream))
+            for w in writes:
+                written[w] = (e, stream)
+                readers[w] = []
+            return n
+
+        lvl0 = self.levels[0]
+        launches += enqueue(side, [], [("coords", id(lvl0))], self.launch_voxelize)
         for s in self.steps:
             if s.kind == "conv":
-                conv_deps.append((s, last_rb_event))   # needs every rulebook step enqueued before it
+                nbr, rows, meta = s.args[1], s.args[13], s.args[14]
+                reads = [("nbr", id(nbr))] + ([("meta", id(nbr))] if (meta is not None or rows is not None) else [])
+                for r in reads:
+                    ev = written.get(r)
+                    if ev is not None:
+                        main.wait_event(ev[0])
+                with torch.cuda.stream(main):
+                    self.launch_conv(s.args, ctypes.c_void_p(main.cuda_stream))
+                    e = torch.cuda.Event()
+                    e.record(main)
+                for r in reads:
+                    readers.setdefault(r, []).append((e, main))
+                launches += 1
                 continue
-            with torch.cuda.stream(side):
-                launches += self.launch_index_step(s, ctypes.c_void_p(side.cuda_stream))
-                last_rb_event = torch.cuda.Event()
-                last_rb_event.record(side)
-        # pass 2: the convolution chain on the main stream, each layer behind its rulebook's event
-        waited = None
-        for s, ev in conv_deps:
-            if ev is not waited:
-                main.wait_event(ev)
-                waited = ev
-            self.launch_conv(s.args, ctypes.c_void_p(main.cuda_stream))
-            launches += 1
+            if s.kind == "hash_build":
+                (lvl,) = s.args
+                reads, writes, stream = [("coords", id(lvl))], [("index", id(lvl))], side2
+            elif s.kind == "subm_rb":
+                lvl, nbr = s.args[0], s.args[3]
+                reads, writes, stream = [("coords", id(lvl)), ("index", id(lvl))], [("nbr", id(nbr))], side2
+            elif s.kind == "conv_rb":
+                lin, lout, nbr = s.args[0], s.args[1], s.args[6]
+                reads, writes, stream = [("coords", id(lin))], [("coords", id(lout)), ("index", id(lout)), ("nbr", id(nbr))], side
+            elif s.kind == "tile_meta":
+                nbr, lvl = s.args[0], s.args[1]
+                reads, writes, stream = [("nbr", id(nbr)), ("coords", id(lvl))], [("meta", id(nbr))], side2
+            elif s.kind == "index_clear":
+                (lvl,) = s.args
+                reads, writes, stream = [("coords", id(lvl))], [("index", id(lvl))], side2
+            elif s.kind == "sort_rb":
+                nbr, lvl = s.args[0], s.args[1]
+                reads, writes, stream = [("nbr", id(nbr)), ("coords", id(lvl))], [("meta", id(nbr))], side2
+            else:
+                raise ValueError(s.kind)
+            launches += enqueue(stream, reads, writes, lambda st, s=s, stream=stream: self._launch_index_on(s, st, stream))
         main.wait_stream(side)
+        main.wait_stream(side2)
         # gather the live counts of every level into one small tensor (read back lazily by the caller)
         self.dev_counts[0:1].copy_(self.levels[0].n_dev)       # levels 1.. write their slot themselves
         self.launches_per_step = launches
         return launches
+
+    def _launch_index_on(self, s, st, stream):
+        with torch.cuda.stream(stream):
+            return self.launch_index_step(s, st)
 
     def launch_voxelize(self, st):
         """points -> voxels / coords / counts / MeanVFE features of level 0 (9 launches)."""
