@@ -71,6 +71,9 @@ SIGNATURES = {
     "btc_occ_abs_mean_vfe": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p]),
     "btc_occ_vfe": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
     "btc_occ_head_prob": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _p]),
+    "btc_boxes_bev": (_i, [_p, _i, _p, _i, _i, _p, _p]),
+    "btc_nms_workspace_bytes": (_i64, [_i]),
+    "btc_nms": (_i, [_p, _i, ctypes.c_float, _i, _p, _p, _p, _i64, _p]),
     "btc_occ_box_targets_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "btc_occ_box_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i,
                                  _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

@@ -571,6 +571,26 @@ int btc_occ_inject_revoxelize(const int* pt_coords, int n_cap, const int* n_dev,
                               int* slots, int* pt_voxel, int* n_voxels, int* max_count,
                               void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Rotated BEV overlap / IoU and rotated NMS.                */
+/* Replace the reference's btcdet/ops/iou3d_nms extension:                      */
+/*   boxes_overlap_bev_gpu / boxes_iou_bev_gpu  (iou3d_nms.cpp:58-100,           */
+/*     iou3d_nms_kernel.cu:236-266)            -> btc_boxes_bev (mode 1 / 0)     */
+/*   nms_gpu / nms_normal_gpu (iou3d_nms.cpp:103-188: N x N/64 mask on the       */
+/*     device, copied to the host and scanned there, iou3d_nms_kernel.cu:269-413) */
+/*                                              -> btc_nms (mask + greedy scan    */
+/*     on the device, keep list and count stay on the device, no sync).           */
+/* boxes: rows of 7 floats (x, y, z, dx, dy, dz, heading).  btc_nms expects the   */
+/* boxes sorted by descending score (the reference's Python wrapper sorts) and    */
+/* writes the kept row indices, ascending, to keep[0 .. *num_out).                */
+/* ------------------------------------------------------------------------- */
+int btc_boxes_bev(const float* boxes_a, int n, const float* boxes_b, int m, int mode /* 0 IoU, 1 overlap area */,
+                  float* out /* [n, m] */, void* stream);
+int64_t btc_nms_workspace_bytes(int n);
+int btc_nms(const float* boxes, int n, float thresh, int normal /* 1: axis-aligned IoU (nms_normal_gpu) */,
+            long long* keep /* device [n] */, int* num_out /* device */, void* workspace, int64_t workspace_bytes,
+            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
