@@ -44,3 +44,12 @@ def test_shard_covers_everything_for_any_world():
             parts = [list(bd.shard(n, r, world)) for r in range(world)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_cpulist_and_host_binding_never_raise():
+    """dist.bind_host_to_gpu must degrade to a no-op (returning its reason) wherever it cannot bind — here: no GPU."""
+    from btcdet_b200 import dist
+    assert dist._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._cpulist("") == set()
+    info = dist.bind_host_to_gpu(0, local_rank=1, local_world=4)
+    assert set(info) >= {"numa_node", "cores", "bound"} and info["bound"] in (True, False)
