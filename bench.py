@@ -200,7 +200,8 @@ def run_ours(args, rank, world):
     plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N_POINTS, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
                                max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], algo=args.algo,
                                device=dev, use_graph=not args.no_graph, sort_rows=args.sort,
-                               tile_meta=not args.no_tile_meta, split_format=not args.no_split).capture()
+                               tile_meta=not args.no_tile_meta, split_format=not args.no_split,
+                               **({"early_conv_grid": None} if args.conv_grid else {})).capture()
     scenes = make_scenes(rank, N_SCENE_POOL)
     # batches: host pinned (for e2e) and device resident (for value)
     n_batches = N_SCENE_POOL // B if N_SCENE_POOL >= B else 1
@@ -376,7 +377,8 @@ def run_ours(args, rank, world):
                 res["gpu_native_baseline"] = nat
             except Exception as exc:
                 res["gpu_native_baseline"] = {"error": repr(exc)}
-            for key, fn in (("chain", lambda: bench_legs.chain_leg(dev)),
+            for key, fn in (("batch32", lambda: bench_legs.batch_leg(model, scenes, dev, 32)),
+                            ("chain", lambda: bench_legs.chain_leg(dev)),
                             ("stress", lambda: bench_legs.stress_leg(dev, float(roof["peak"]) if roof else 6552.0))):
                 try:
                     res[key] = fn()

@@ -60,10 +60,16 @@ class BackbonePlan:
 
     def __init__(self, layer_specs, sparse_shape, batch, max_points_total, voxel_size, point_range, max_points=5,
                  max_voxels=16000, level_growth=2.0, algo=0, device="cuda", use_graph=True, sort_rows=False, side_priority=0,
-                 tile_meta=True, split_format=True):
+                 tile_meta=True, split_format=True, early_conv_grid=(4, 116)):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.batch = int(batch)
+        # (layers, ctas): the first `layers` convolutions run on at most `ctas` SMs, leaving the others to the rulebook
+        # streams while most of the rulebook chain is still ahead.  The thin first layers are bound by their index-tile
+        # pipeline, not by the SM count, and the rulebook kernels cannot share an SM with a persistent convolution CTA:
+        # measured at batch 16 (tools/step_breakdown.py --early, profiles/r2_early_grid_sweep.json) the captured step drops
+        # from 1 154 to 1 116 us with (4, 116); None = every layer on all SMs
+        self.early_conv_grid = early_conv_grid
         self.voxel_size, self.point_range = list(voxel_size), list(point_range)
         self.grid = ops.voxel_grid_size(voxel_size, point_range)
         self.max_points, self.max_voxels = int(max_points), int(max_voxels)
@@ -260,6 +266,7 @@ class BackbonePlan:
             return n
 
         lvl0 = self.levels[0]
+        n_conv = 0
         launches += enqueue(side, [], [("coords", id(lvl0))], self.launch_voxelize)
         for s in self.steps:
             if s.kind == "conv":
@@ -270,6 +277,10 @@ class BackbonePlan:
                     if ev is not None:
                         main.wait_event(ev[0])
                 with torch.cuda.stream(main):
+                    if self.early_conv_grid is not None:
+                        capped = n_conv < self.early_conv_grid[0]
+                        check(self.lib.btc_sparse_conv_tc_grid(int(self.early_conv_grid[1]) if capped else 148), "tc grid")
+                    n_conv += 1
                     self.launch_conv(s.args, ctypes.c_void_p(main.cuda_stream))
                     e = torch.cuda.Event()
                     e.record(main)
@@ -298,6 +309,8 @@ class BackbonePlan:
             else:
                 raise ValueError(s.kind)
             launches += enqueue(stream, reads, writes, lambda st, s=s, stream=stream: self._launch_index_on(s, st, stream))
+        if self.early_conv_grid is not None:
+            check(self.lib.btc_sparse_conv_tc_grid(148), "tc grid")      # process-wide knob: back to one CTA per SM
         main.wait_stream(side)
         main.wait_stream(side2)
         # gather the live counts of every level into one small tensor (read back lazily by the caller)

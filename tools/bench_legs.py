@@ -155,6 +155,35 @@ def train_leg(rank, world, dev, steps=10, warmup=4, batch=2):
                     "backward + grad clip + Adam, VoxelBackBone8x + BEV 1x1 head, train-mode BatchNorm, eager spconv shim"}
 
 
+def batch_leg(model, scenes, dev, batch=32, steps=20, warmup=3):
+    """The headline workload at another batch size (same plan, same timing rules: HBM-resident input, L2 flushed between
+    timed steps, CUDA events per step): how far the latency-bound parts of the step amortise with more scenes per step."""
+    from btcdet_b200 import engine, synthetic as S
+    plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, batch, batch * 20000, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                               max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], device=dev).capture()
+    pts, offs = S.batch_points([scenes[j % len(scenes)] for j in range(batch)])
+    p, o = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    ms = []
+    for i in range(warmup + steps):
+        flush.fill_(float(i))
+        e0, e1 = _events()
+        e0.record()
+        plan.load_points(p, o)       # D2D into the graph's static input buffer, inside the timed region as in bench.py
+        plan.step()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    plan.read_counts()
+    med = float(np.median(ms))
+    del plan
+    torch.cuda.empty_cache()
+    return {"scenes_per_step": batch, "value": round(batch / (med * 1e-3), 2), "unit": "scenes/s", "ms_per_step": round(med, 4),
+            "steps": steps, "what": "the headline step at batch %d instead of 16 (one distinct batch, HBM-resident, L2 flushed "
+                                    "between timed steps): the rulebook chain and the per-launch costs amortise" % batch}
+
+
 def chain_leg(dev, steps=10, warmup=3, batch=2):
     from btcdet_b200 import backbones, chain
     torch.manual_seed(0)

@@ -33,13 +33,49 @@ def main():
     ap.add_argument("--grids", default="", help="comma-separated caps on the conv grid: only the captured graph is timed per cap")
     ap.add_argument("--variants", default="16,0,1", help="semicolon-separated tcgen05 tile variants npw,cat,dyn "
                     "(one JSON line each), e.g. '16,1,1;16,0,1;16,1,0'")
+    ap.add_argument("--early", default="", help="comma-separated L:G pairs: first L convolutions capped at G CTAs (captured graph only)")
     args = ap.parse_args()
+    if args.early:
+        early_grid_sweep(args)
+        return
     if args.grids:
         grid_sweep(args)
         return
     for v in args.variants.split(";"):
         npw, cat, dyn = (int(x) for x in v.split(","))
         run(args, npw, cat, dyn)
+
+
+def early_grid_sweep(args):
+    """Captured-graph time with the first L convolutions capped at G CTAs (engine.BackbonePlan(early_conv_grid=(L, G)))."""
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, N = args.batch, 20000
+    pts, offs = S.batch_points([S.lidar_like(N, seed=i) for i in range(B)])
+    pts_d, offs_d = torch.from_numpy(pts).to(dev), torch.from_numpy(offs).to(dev)
+    out = []
+    for spec in [None] + [tuple(int(x) for x in v.split(":")) for v in args.early.split(",")]:
+        torch.manual_seed(0)
+        model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+        plan = engine.BackbonePlan(model.layer_specs(), model.sparse_shape, B, B * N, S.DET_VOXEL_SIZE, S.KITTI_RANGE,
+                                   max_points=S.DET_MAX_POINTS, max_voxels=S.DET_MAX_VOXELS["train"], device=dev,
+                                   early_conv_grid=spec).capture()
+        plan.load_points(pts_d, offs_d)
+        ms = []
+        for r in range(args.reps + 3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.step()
+            e1.record()
+            torch.cuda.synchronize()
+            if r >= 3:
+                ms.append(e0.elapsed_time(e1))
+        out.append({"early_conv_grid": spec, "graph_us": round(float(np.median(ms)) * 1e3, 1)})
+        del plan
+        torch.cuda.empty_cache()
+    from btcdet_b200 import _lib
+    _lib.load().btc_sparse_conv_tc_grid(148)
+    print(json.dumps({"batch": B, "early_grid_sweep": out}), flush=True)
 
 
 def grid_sweep(args):
