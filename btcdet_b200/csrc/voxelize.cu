@@ -234,10 +234,13 @@ int64_t btc_voxelize_workspace_bytes(int64_t n_points, int n_scenes, int max_vox
     return carve(nullptr, n_points, n_scenes, max_voxels, max_points).bytes;
 }
 
-int btc_voxelize(const float* points, int n_points, int n_feat, const int* scene_offsets, int n_scenes,
-                 const float* voxel_size, const float* range, const int* grid, int max_points, int max_voxels,
-                 float* voxels, int* coords, int* num_points, float* voxel_mean, int* n_voxels, void* workspace,
-                 int64_t workspace_bytes, void* stream) {
+// phases: 1 = grouping (hash insert, first-point ranks, per-scene bases, voxel ids + coordinates + counts[n_scenes + 1]),
+//         2 = contents (sorted point lists per voxel, gathered voxels / num_points / MeanVFE features), 3 = both.
+// Everything that only needs coordinates (the coordinate hash and the rulebooks of level 1) can start after phase 1.
+static int voxelize_phases(int phases, const float* points, int n_points, int n_feat, const int* scene_offsets, int n_scenes,
+                           const float* voxel_size, const float* range, const int* grid, int max_points, int max_voxels,
+                           float* voxels, int* coords, int* num_points, float* voxel_mean, int* n_voxels, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
     if (!scene_offsets || !voxel_size || !range || !grid || !voxels || !coords || !num_points || !n_voxels || !workspace)
         return badarg("btc_voxelize: null argument");
     if (n_points < 0 || n_feat < 3 || n_scenes < 1 || max_points < 1 || max_voxels < 1)
@@ -253,11 +256,11 @@ int btc_voxelize(const float* points, int n_points, int n_feat, const int* scene
         g.lo[j] = range[j];
         g.grid[j] = grid[j];
     }
-    BTC_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)w.hsize * 8, st), "voxelize memset keys");
-    BTC_CUDA(cudaMemsetAsync(w.min_idx, 0x7f, (size_t)w.hsize * 4, st), "voxelize memset min_idx");
-    BTC_CUDA(cudaMemsetAsync(w.lists, 0x7f, (size_t)n_scenes * max_voxels * max_points * 4, st), "voxelize memset lists");
     const int T = 256;
     const int nthreads_n = n_points > 0 ? n_points : 1;
+    if (phases & 1) {
+    BTC_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)w.hsize * 8, st), "voxelize memset keys");
+    BTC_CUDA(cudaMemsetAsync(w.min_idx, 0x7f, (size_t)w.hsize * 4, st), "voxelize memset min_idx");
     if (n_points > 0) {
         vox_hash_insert_kernel<<<grid_for(n_points, T), T, 0, st>>>(points, n_points, n_feat, scene_offsets, n_scenes, g,
                                                                     w.keys, w.min_idx, w.hsize - 1, w.pt_slot);
@@ -270,13 +273,17 @@ int btc_voxelize(const float* points, int n_points, int n_feat, const int* scene
     if (rc) return rc;
     vox_scene_bases_kernel<<<1, 32, 0, st>>>(w.rank, w.total, n_points, scene_offsets, n_scenes, max_voxels,
                                              w.scene_rank0, w.scene_base, n_voxels);
-    if (n_points > 0) {
+    if (n_points > 0)
         vox_assign_kernel<<<grid_for(n_points, T), T, 0, st>>>(points, n_points, n_feat, scene_offsets, n_scenes, g,
                                                                w.flags, w.rank, w.pt_slot, w.scene_rank0, w.scene_base,
                                                                max_voxels, w.slot_vid, (int4*)coords);
+    BTC_CHECK_LAUNCH("voxelize grouping");
+    }   // phase 1
+    if (!(phases & 2)) return BTC_OK;
+    BTC_CUDA(cudaMemsetAsync(w.lists, 0x7f, (size_t)n_scenes * max_voxels * max_points * 4, st), "voxelize memset lists");
+    if (n_points > 0)
         vox_insert_points_kernel<<<grid_for(n_points, T), T, 0, st>>>(w.pt_slot, w.slot_vid, n_points, max_points,
                                                                       w.lists);
-    }
     int64_t cap_work = (int64_t)n_scenes * max_voxels * max_points;
     int64_t est = (int64_t)n_points * max_points;  // live work is bounded by the number of points
     if (est < cap_work) cap_work = est;
@@ -284,6 +291,30 @@ int btc_voxelize(const float* points, int n_points, int n_feat, const int* scene
                                                                               max_points, voxels, num_points, voxel_mean);
     BTC_CHECK_LAUNCH("voxelize assign/gather");
     return BTC_OK;
+}
+
+int btc_voxelize(const float* points, int n_points, int n_feat, const int* scene_offsets, int n_scenes,
+                 const float* voxel_size, const float* range, const int* grid, int max_points, int max_voxels,
+                 float* voxels, int* coords, int* num_points, float* voxel_mean, int* n_voxels, void* workspace,
+                 int64_t workspace_bytes, void* stream) {
+    return voxelize_phases(3, points, n_points, n_feat, scene_offsets, n_scenes, voxel_size, range, grid, max_points, max_voxels,
+                           voxels, coords, num_points, voxel_mean, n_voxels, workspace, workspace_bytes, stream);
+}
+
+int btc_voxelize_group(const float* points, int n_points, int n_feat, const int* scene_offsets, int n_scenes,
+                       const float* voxel_size, const float* range, const int* grid, int max_points, int max_voxels,
+                       float* voxels, int* coords, int* num_points, float* voxel_mean, int* n_voxels, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+    return voxelize_phases(1, points, n_points, n_feat, scene_offsets, n_scenes, voxel_size, range, grid, max_points, max_voxels,
+                           voxels, coords, num_points, voxel_mean, n_voxels, workspace, workspace_bytes, stream);
+}
+
+int btc_voxelize_fill(const float* points, int n_points, int n_feat, const int* scene_offsets, int n_scenes,
+                      const float* voxel_size, const float* range, const int* grid, int max_points, int max_voxels,
+                      float* voxels, int* coords, int* num_points, float* voxel_mean, int* n_voxels, void* workspace,
+                      int64_t workspace_bytes, void* stream) {
+    return voxelize_phases(2, points, n_points, n_feat, scene_offsets, n_scenes, voxel_size, range, grid, max_points, max_voxels,
+                           voxels, coords, num_points, voxel_mean, n_voxels, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -267,7 +267,10 @@ class BackbonePlan:
 
         lvl0 = self.levels[0]
         n_conv = 0
-        launches += enqueue(side, [], [("coords", id(lvl0))], self.launch_voxelize)
+        # grouping on the critical path of the rulebook chain; the voxel contents / MeanVFE features (only the first
+        # convolution reads them) on the main stream, which is idle until then
+        launches += enqueue(side, [], [("coords", id(lvl0))], lambda st: self.launch_voxelize(st, 1))
+        launches += enqueue(main, [("coords", id(lvl0))], [("feat0", 0)], lambda st: self.launch_voxelize(st, 2))
         for s in self.steps:
             if s.kind == "conv":
                 nbr, rows, meta = s.args[1], s.args[13], s.args[14]
@@ -322,15 +325,18 @@ class BackbonePlan:
         with torch.cuda.stream(stream):
             return self.launch_index_step(s, st)
 
-    def launch_voxelize(self, st):
-        """points -> voxels / coords / counts / MeanVFE features of level 0 (9 launches)."""
+    def launch_voxelize(self, st, phase=3):
+        """points -> voxels / coords / counts / MeanVFE features of level 0 (9 launches).  phase 1 = grouping only (coords and
+        counts: what the rulebook chain waits for), phase 2 = contents (voxels, MeanVFE features: what the first convolution
+        waits for), 3 = both."""
         lib, B, lvl0 = self.lib, self.batch, self.levels[0]
-        check(lib.btc_voxelize(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
-                               float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
-                               self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
-                               _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
-                               self.vox_ws.numel(), st), "btc_voxelize")
-        return 9
+        fn = {1: lib.btc_voxelize_group, 2: lib.btc_voxelize_fill, 3: lib.btc_voxelize}[phase]
+        check(fn(_ptr(self.points), self.n_cap, 4, _ptr(self.scene_offsets), B,
+                 float_array(self.voxel_size), float_array(self.point_range), int3(self.grid),
+                 self.max_points, self.max_voxels, _ptr(self.voxels), _ptr(lvl0.coords),
+                 _ptr(self.num_points), _ptr(self.feat0), _ptr(self.n_voxels), _ptr(self.vox_ws),
+                 self.vox_ws.numel(), st), "btc_voxelize")
+        return {1: 7, 2: 2, 3: 9}[phase]
 
     def launch_index_step(self, s, st):
         """One step of the rulebook chain (hash build / neighbour table / mask sort) on stream `st`;

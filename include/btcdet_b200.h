@@ -94,6 +94,23 @@ int btc_voxelize(const float* points, int n_points, int n_feat,
                  float* voxels, int* coords, int* num_points, float* voxel_mean,
                  int* n_voxels,
                  void* workspace, int64_t workspace_bytes, void* stream);
+/* The same call in two stream-ordered halves over the same arguments and workspace: _group = grouping (coords, n_voxels;
+ * everything that only needs coordinates — the coordinate hash and the rulebooks — may start behind it), _fill = contents
+ * (voxels, num_points, voxel_mean).  btc_voxelize == _group followed by _fill. */
+int btc_voxelize_group(const float* points, int n_points, int n_feat,
+                       const int* scene_offsets, int n_scenes,
+                       const float* voxel_size, const float* range, const int* grid,
+                       int max_points, int max_voxels,
+                       float* voxels, int* coords, int* num_points, float* voxel_mean,
+                       int* n_voxels,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+int btc_voxelize_fill(const float* points, int n_points, int n_feat,
+                      const int* scene_offsets, int n_scenes,
+                      const float* voxel_size, const float* range, const int* grid,
+                      int max_points, int max_voxels,
+                      float* voxels, int* coords, int* num_points, float* voxel_mean,
+                      int* n_voxels,
+                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Dataset-side coordinate transform of the occupancy branch: absxyz_2_cylinxyz_np / absxyz_2_spherexyz_np
