@@ -21,6 +21,7 @@ SIGNATURES = {
     "btc_voxelize_workspace_bytes": (_i64, [_i64, _i, _i, _i]),
     "btc_voxelize": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_voxelize_group": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "btc_voxelize_hash_view": (_i, [_i64, _i, _i, _i, _p, _p, _p]),
     "btc_voxelize_fill": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "btc_points_to_cylinder": (_i, [_p, _i, _p, _i, _i, _p, _p]),
     "btc_index_entries": (_i64, [_i, _p]),

@@ -293,6 +293,22 @@ static int voxelize_phases(int phases, const float* points, int n_points, int n_
     return BTC_OK;
 }
 
+// The grouping phase leaves a complete coordinate -> row hash in the workspace: keys[slot] = ((b * grid_z + z) * grid_y + y)
+// * grid_x + x (-1 = empty), vals[slot] = voxel row (-1: a voxel beyond its scene's max_voxels).  Same hash function and
+// probing as btc_hash_build, i.e. btc_rulebook_subm_hash can probe it directly with shape (grid_z, grid_y, grid_x) — the
+// level-1 sub-manifold rulebook then needs no hash build of its own.  Byte offsets into the workspace + slot count.
+int btc_voxelize_hash_view(int64_t n_points, int n_scenes, int max_voxels, int max_points, int64_t* keys_offset,
+                           int64_t* vals_offset, int64_t* n_slots) {
+    if (n_points < 0 || n_scenes < 1 || max_voxels < 1 || max_points < 1 || !keys_offset || !vals_offset || !n_slots)
+        return badarg("btc_voxelize_hash_view: bad arguments");
+    char* fake = (char*)(uintptr_t)4096;
+    VoxWorkspace w = carve(fake, n_points, n_scenes, max_voxels, max_points);
+    *keys_offset = (int64_t)((char*)w.keys - fake);
+    *vals_offset = (int64_t)((char*)w.slot_vid - fake);
+    *n_slots = (int64_t)w.hsize;
+    return BTC_OK;
+}
+
 int btc_voxelize(const float* points, int n_points, int n_feat, const int* scene_offsets, int n_scenes,
                  const float* voxel_size, const float* range, const int* grid, int max_points, int max_voxels,
                  float* voxels, int* coords, int* num_points, float* voxel_mean, int* n_voxels, void* workspace,

@@ -36,6 +36,7 @@ class _Level:
     perm: Optional[torch.Tensor] = None
     hash_keys: Optional[torch.Tensor] = None   # coordinate hash — the unsorted voxeliser level
     hash_vals: Optional[torch.Tensor] = None
+    hash_shape: Optional[list] = None          # shape the hash keys were formed with (voxeliser's own hash), else `shape`
 
 
 @dataclass
@@ -209,6 +210,17 @@ class BackbonePlan:
     # ------------------------------------------------------------------------------------
     def _add_index(self, lvl: _Level):
         """Unsorted level (voxeliser order): coordinate hash instead of a 92 M-cell bitmap."""
+        if lvl is self.levels[0] and lvl.shape[1] == self.grid[1] and lvl.shape[2] == self.grid[0] and lvl.shape[0] >= self.grid[2]:
+            # the voxeliser's own hash (keys over its grid, vals = voxel rows) IS this level's coordinate hash: no build.
+            # Its keys use depth grid_z (the sparse shape has one more layer that no voxel can occupy), so the probes run
+            # with that depth — a neighbour in the extra layer is absent either way.
+            ko, vo, ns = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+            check(self.lib.btc_voxelize_hash_view(self.n_cap, self.batch, self.max_voxels, self.max_points, ctypes.byref(ko),
+                                                  ctypes.byref(vo), ctypes.byref(ns)), "btc_voxelize_hash_view")
+            lvl.hash_keys = self.vox_ws[ko.value:ko.value + 8 * ns.value].view(torch.int64)
+            lvl.hash_vals = self.vox_ws[vo.value:vo.value + 4 * ns.value].view(torch.int32)
+            lvl.hash_shape = [int(self.grid[2]), lvl.shape[1], lvl.shape[2]]
+            return
         n_slots = int(self.lib.btc_hash_slots(lvl.cap))
         lvl.hash_keys = torch.empty(n_slots, dtype=torch.int64, device=self.device)
         lvl.hash_vals = torch.empty(n_slots, dtype=torch.int32, device=self.device)
@@ -269,7 +281,7 @@ class BackbonePlan:
         n_conv = 0
         # grouping on the critical path of the rulebook chain; the voxel contents / MeanVFE features (only the first
         # convolution reads them) on the main stream, which is idle until then
-        launches += enqueue(side, [], [("coords", id(lvl0))], lambda st: self.launch_voxelize(st, 1))
+        launches += enqueue(side, [], [("coords", id(lvl0)), ("index", id(lvl0))], lambda st: self.launch_voxelize(st, 1))
         launches += enqueue(main, [("coords", id(lvl0))], [("feat0", 0)], lambda st: self.launch_voxelize(st, 2))
         for s in self.steps:
             if s.kind == "conv":
@@ -352,7 +364,7 @@ class BackbonePlan:
         if s.kind == "subm_rb":
             lvl, ksize, dil, nbr = s.args
             if lvl.hash_keys is not None:
-                check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.shape),
+                check(lib.btc_rulebook_subm_hash(_ptr(lvl.coords), lvl.cap, _ptr(lvl.n_dev), B, int3(lvl.hash_shape or lvl.shape),
                                                  int3(ksize), int3(dil), _ptr(lvl.hash_keys), _ptr(lvl.hash_vals),
                                                  lvl.hash_keys.numel(), _ptr(nbr), st), "btc_rulebook_subm_hash")
             else:

@@ -104,6 +104,12 @@ int btc_voxelize_group(const float* points, int n_points, int n_feat,
                        float* voxels, int* coords, int* num_points, float* voxel_mean,
                        int* n_voxels,
                        void* workspace, int64_t workspace_bytes, void* stream);
+/* After the grouping, the workspace holds a complete coordinate -> voxel-row hash (same hash function / probing as
+ * btc_hash_build; keys over the voxeliser's own grid (grid_z, grid_y, grid_x), -1 = empty; vals = row or -1 for voxels
+ * beyond max_voxels): byte offsets of the two arrays inside the workspace and the slot count, for
+ * btc_rulebook_subm_hash(shape = (grid_z, grid_y, grid_x)). */
+int btc_voxelize_hash_view(int64_t n_points, int n_scenes, int max_voxels, int max_points,
+                           int64_t* keys_offset, int64_t* vals_offset, int64_t* n_slots);
 int btc_voxelize_fill(const float* points, int n_points, int n_feat,
                       const int* scene_offsets, int n_scenes,
                       const float* voxel_size, const float* range, const int* grid,
