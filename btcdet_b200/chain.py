@@ -133,7 +133,6 @@ class PlannedHotPath:
             "rot_z": torch.zeros(self.B, device=d) if with_rot else None,
             "n_occ": torch.zeros(1, dtype=torch.int32, device=d), "n_det": torch.zeros(1, dtype=torch.int32, device=d),
         }
-        self._host_n = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.out = None
         self.checks = None
         self.graph = None
@@ -157,9 +156,8 @@ class PlannedHotPath:
         inp["det_voxel_num_points"][m_det:].zero_()
         if inp["rot_z"] is not None:
             inp["rot_z"].copy_(bd["rot_z"], non_blocking=True)
-        self._host_n[0], self._host_n[1] = m_occ, m_det
-        inp["n_occ"].copy_(self._host_n[0:1], non_blocking=True)
-        inp["n_det"].copy_(self._host_n[1:2], non_blocking=True)
+        inp["n_occ"].fill_(m_occ)          # scalar kernel arguments: no pinned staging buffer a later load() could overwrite
+        inp["n_det"].fill_(m_det)
 
     def _forward(self):
         m, inp, B = self.model, self.inp, self.B

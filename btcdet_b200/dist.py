@@ -70,9 +70,13 @@ def bind_host_to_gpu(device_index, local_rank=0, local_world=1):
     info = {"numa_node": None, "cores": None, "bound": False}
     try:
         import torch
-        p = torch.cuda.get_device_properties(device_index)
-        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+
+        def node_of(idx):
+            p = torch.cuda.get_device_properties(idx)
+            bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+            return int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+
+        node = node_of(device_index)
         info["numa_node"] = node
         if node < 0:
             return info
@@ -82,12 +86,15 @@ def bind_host_to_gpu(device_index, local_rank=0, local_world=1):
         if not mine:
             info["note"] = "the GPU's node has no core in this process' allowed set (%d allowed cores)" % len(allowed)
             return info
-        # ranks that share the node share its cores evenly (at least two cores each: main thread + copy / NCCL threads)
-        per = max(2, len(mine) // max(1, local_world))
-        lo = (local_rank * per) % len(mine)
+        # the ranks whose GPUs hang off the same node share its cores evenly (at least two cores each: main thread + copy /
+        # NCCL threads); with one process per GPU the local rank is the device index
+        peers = [g for g in range(min(torch.cuda.device_count(), max(local_world, 1))) if node_of(g) == node] or [device_index]
+        pos = peers.index(device_index) if device_index in peers else local_rank % len(peers)
+        per = max(2, len(mine) // len(peers))
+        lo = (pos * per) % len(mine)
         sl = (mine + mine)[lo:lo + per]
         os.sched_setaffinity(0, set(sl))
-        info.update({"cores": len(sl), "bound": True})
+        info.update({"cores": len(sl), "bound": True, "ranks_on_node": len(peers)})
     except Exception as e:      # noqa: BLE001
         info["note"] = repr(e)[:120]
     return info
