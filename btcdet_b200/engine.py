@@ -525,9 +525,14 @@ class BackbonePlan:
         pl["pending"].append(slot)
         pl["k"] += 1
 
-    def retrieve(self):
+    def retrieve(self, to_host=True):
         """Result of the oldest submitted batch: (features [n,C], coords [n,4]) as views of pinned host buffers,
-        valid until two further submits.  Only this call waits, and only for that batch."""
+        valid until two further submits.  Only this call waits, and only for that batch.
+        to_host=False: the rows stay on the device — (features, coords) are views of the slot's DEVICE staging buffers for
+        a consumer on the GPU (the reference's BEV backbone reads the backbone output on the device, btcnet.py:56-88),
+        the host only receives the row counts of every level; the caller hands the slot back by recording its own event
+        into `plan._pl["d2h_done"][slot]` or simply by finishing its work on the current stream before the slot's reuse
+        (two submits later)."""
         pl = self._pl
         slot = pl["pending"].pop(0)
         pl["count_ready"][slot].synchronize()          # the row count of that batch (the GPU is already busy with the next)
@@ -539,6 +544,11 @@ class BackbonePlan:
                                     % (c, l.cap))
         if n > pl["rows"]:
             raise _lib.BtcError("result of %d rows exceeds the pipeline staging capacity %d" % (n, pl["rows"]))
+        if not to_host:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())      # consumers on the current stream are ordered before the slot's reuse
+            pl["d2h_done"][slot] = ev
+            return pl["stage_feat"][slot][:n], pl["stage_coords"][slot][:n], ev
         cs = pl["copy_stream"]
         cs.wait_event(pl["count_ready"][slot])
         with torch.cuda.stream(cs):

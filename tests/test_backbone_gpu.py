@@ -203,3 +203,16 @@ def test_pipelined_submit_retrieve_matches_forward(cuda, oracle):
     assert len(got) == len(want)
     for (gf, gc), (wf, wc) in zip(got, want):
         assert torch.equal(gc, wc) and torch.equal(gf, wf)
+    # the same pipeline with the result rows left on the device (retrieve(to_host=False)): views of the slot's device
+    # staging buffers, identical rows, only the counts cross to the host
+    got_dev = []
+    for i, (p, o) in enumerate(batches):
+        plan.submit(p, o)
+        if i >= 1:
+            f, c, ev = plan.retrieve(to_host=False)
+            assert f.is_cuda and c.is_cuda
+            got_dev.append((f.cpu(), c.cpu()))
+    f, c, ev = plan.retrieve(to_host=False)
+    got_dev.append((f.cpu(), c.cpu()))
+    for (gf, gc), (wf, wc) in zip(got_dev, want):
+        assert torch.equal(gc, wc) and torch.equal(gf, wf)

@@ -1,5 +1,4 @@
 set -u
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/s3y_topo.txt 2>&1
-python -c "import os; print('affinity', len(os.sched_getaffinity(0)), 'cpu_count', os.cpu_count())" >> gpurun_out/s3y_topo.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/s3y_bench8.json 2> gpurun_out/s3y_bench8.err; tail -3 gpurun_out/s3y_bench8.err | cut -c1-300; cut -c1-300 gpurun_out/s3y_bench8.json
+timeout 600 python bench.py --no-extra --no-cpu-baseline > gpurun_out/s3z_bench.json 2> gpurun_out/s3z_bench.err; tail -3 gpurun_out/s3z_bench.err
+timeout 600 python -m pytest tests/test_backbone_gpu.py tests/test_static_mode_gpu.py -q -x > gpurun_out/s3z_tests.log 2>&1; tail -2 gpurun_out/s3z_tests.log
