@@ -77,6 +77,13 @@ SIGNATURES = {
     "btc_boxes_bev": (_i, [_p, _i, _p, _i, _i, _p, _p]),
     "btc_nms_workspace_bytes": (_i64, [_i]),
     "btc_nms": (_i, [_p, _i, ctypes.c_float, _i, _p, _p, _p, _i64, _p]),
+    "btc_ball_query_stack": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "btc_group_points_stack": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "btc_group_points_stack_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "btc_trilinear_sparse_workspace_bytes": (_i64, [_i64, _i, _p]),
+    "btc_trilinear_sparse_flag": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _i64, _i64, _i, _p, _p, _i64, _p]),
+    "btc_trilinear_sparse_grad": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _i64, _i64, _i, _p, _p, _i64, _p]),
+    "btc_trilinear_sparse_emit": (_i, [_p, _i, _i, _p, _p, _p, _i64, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _i64, _p]),
     "btc_occ_box_targets_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "btc_occ_box_targets": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i,
                                  _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

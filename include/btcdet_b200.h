@@ -614,6 +614,66 @@ int btc_nms(const float* boxes, int n, float thresh, int normal /* 1: axis-align
             long long* keep /* device [n] */, int* num_out /* device */, void* workspace, int64_t workspace_bytes,
             void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* RoI grid pooling of the second stage: the native ops      */
+/* under ConvHead.roi_conv_pool (btcdet/models/roi_heads/conv_head.py:247-379). */
+/*                                                                            */
+/* btc_ball_query_stack replaces ball_query_wrapper_stack                     */
+/*   (btcdet/ops/pointnet2/pointnet2_stack/src/ball_query.cpp:21-39, kernel    */
+/*   ball_query_gpu.cu:16-60) for ALL radii of one StackSAModuleMSG            */
+/*   (pointnet2_modules.py:10-108 calls it once per radius) in one pass:       */
+/*   idx[r] is [M, nsamples[r]] i32: the first nsamples[r] points of the       */
+/*   query's scene, in index order, with d2 < radii[r]^2 (d2 in the reference  */
+/*   kernel's operation order); shorter rows repeat the first hit; an empty    */
+/*   ball is (-1, 0, 0, ...).  `idx` is a HOST array of n_radii (1..4) device   */
+/*   pointers.  xyz [sum N_b, 3], new_xyz [M, 3], *_batch_cnt [B] i32 device.   */
+/* btc_group_points_stack(_grad) replace group_points_wrapper_stack /          */
+/*   group_points_grad_wrapper_stack (group_points.cpp, kernels                */
+/*   group_points_gpu.cu:16-95): out [M, C, nsample] = features[start_b +      */
+/*   idx[m, s], c]; the gradient is scatter-added (fp32 atomics, like the      */
+/*   reference) into grad_features [N, C], which the caller zeroes.            */
+/* btc_trilinear_sparse_flag / _emit replace                                   */
+/*   reverse_sparse_trilinear_interpolate_torch (btcdet/utils/common_utils.py: */
+/*   247-311: feat.dense() + 8 corner gathers + 8 weights) and the non-zero    */
+/*   row compaction of ConvHead.interpolate_from_3d_features                   */
+/*   (conv_head.py:505-528) without the dense volume: `flag` builds a row-     */
+/*   index volume of the sparse tensor (feats [n, C], coords [n, 4] b z y x,   */
+/*   grid shape (Z, Y, X)), evaluates every target (zyx [T, 3] f32 = the       */
+/*   reference's spatial_target_idxs; scene = b_target[t] or t / per_scene)    */
+/*   and writes the number of rows with a non-zero channel to *count (device); */
+/*   `emit` writes those rows, in target order, to out_feats [out_cap, C],     */
+/*   their coordinates (t / P, unravel(t % P, local_shape)) to out_coords      */
+/*   [out_cap, 4] i32 and (optional) the target index to out_target; rows      */
+/*   beyond out_cap are dropped (the caller compares *count with out_cap).     */
+/*   Products and sums follow the reference's expression order: bit-exact.     */
+/*   Both calls take the SAME workspace (emit reads what flag left in it).     */
+/* ------------------------------------------------------------------------- */
+int btc_ball_query_stack(int B, int M, int n_radii, const float* radii /* host */, const int* nsamples /* host */,
+                         const float* new_xyz, const int* new_xyz_batch_cnt, const float* xyz, const int* xyz_batch_cnt,
+                         int* const* idx /* host array of device pointers */, void* stream);
+int btc_group_points_stack(int B, int M, int C, int nsample, const float* features, const int* features_batch_cnt,
+                           const int* idx, const int* idx_batch_cnt, float* out, void* stream);
+int btc_group_points_stack_grad(int B, int M, int C, int N, int nsample, const float* grad_out, const int* idx,
+                                const int* idx_batch_cnt, const int* features_batch_cnt, float* grad_features,
+                                void* stream);
+int64_t btc_trilinear_sparse_workspace_bytes(int64_t n_targets, int batch, const int* shape /* host (Z, Y, X) */);
+int btc_trilinear_sparse_flag(const float* feats, const int* coords, int n_cap, const int* n_dev, int C, int batch,
+                              const int* shape, const float* zyx, const long long* b_target /* or NULL */,
+                              int64_t n_targets, int64_t per_scene, int normalize, int* count /* device */,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+int btc_trilinear_sparse_emit(const float* feats, int C, int batch, const int* shape, const float* zyx,
+                              const long long* b_target, int64_t n_targets, int64_t per_scene, int normalize, int P,
+                              const int* local_shape /* host (lz, ly, lx), lz*ly*lx == P */, int out_cap,
+                              float* out_feats, int* out_coords, long long* out_target /* or NULL */, void* workspace,
+                              int64_t workspace_bytes, void* stream);
+/* Adjoint of the emitted rows w.r.t. the sparse source features (the backward the reference gets from autograd through
+ * im[b, :, z, y, x]): grad_feats [n, C] (zeroed by the caller) += w_j * grad_out[o] at the active corners of target
+ * out_target[o]; same workspace as flag / emit (reads the row-index volume). */
+int btc_trilinear_sparse_grad(const float* grad_out, const long long* out_target, int n_out, const int* n_out_dev, int C,
+                              int batch, const int* shape, const float* zyx, const long long* b_target, int64_t n_targets,
+                              int64_t per_scene, int normalize, float* grad_feats, void* workspace, int64_t workspace_bytes,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

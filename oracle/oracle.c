@@ -23,6 +23,14 @@
  *                         (btcdet/models/backbones_3d/spconv_backbone.py:12-29)      [App. A.2-A.4]
  *   orc_indice_conv       spconv 1.2.1 src/spconv/spconv_ops.cc indiceConv (Native)   [App. A.5]
  *   orc_indice_maxpool    spconv 1.2.1 src/spconv/maxpool.cu                          [App. A.6]
+ *   orc_ball_query_stack / orc_group_points_stack(_grad)
+ *                         the reference's OWN in-tree kernels (not spconv: parity PINNED, see below):
+ *                         btcdet/ops/pointnet2/pointnet2_stack/src/ball_query_gpu.cu:16-60,
+ *                         group_points_gpu.cu:16-95, restated thread for thread.  d2 follows the SASS nvcc
+ *                         emits for the reference's source line :42 (FMUL, FFMA, FFMA: nvcc's default
+ *                         -fmad=true contracts it), written with fmaf().  Pinned on the GPU box against the
+ *                         reference kernels themselves, compiled from the checkout into
+ *                         oracle/_ref/libpointnet2_ref.so (tests/test_roi_pool_gpu.py).          [SURVEY 8f N1]
  */
 #include <math.h>
 #include <stdint.h>
@@ -314,4 +322,77 @@ void orc_indice_maxpool(const float* features, int n_in, int c, int K, const int
                 if (v > out[(size_t)o * c + ch]) out[(size_t)o * c + ch] = v;
             }
         }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stacked ball query / grouping of the RoI head.                                */
+/* One loop iteration = one thread of the reference kernel.  idx must be zero-initialised by    */
+/* the caller exactly like the reference's Python wrapper does (pointnet2_utils.py:33).          */
+/* ------------------------------------------------------------------------------------------ */
+static void orc_scene_of(int pt, int B, const int* q_cnt, const int* p_cnt, int* scene, int* start) {
+    int bs = 0, acc = q_cnt[0], k, s = 0;
+    for (k = 1; k < B; k++) {
+        if (pt < acc) break;
+        acc += q_cnt[k];
+        bs = k;
+    }
+    for (k = 0; k < bs; k++) s += p_cnt[k];
+    *scene = bs;
+    *start = s;
+}
+
+void orc_ball_query_stack(int B, int M, float radius, int nsample, const float* new_xyz, const int* new_xyz_batch_cnt,
+                          const float* xyz, const int* xyz_batch_cnt, int* idx) {
+    int pt;
+    const float radius2 = radius * radius;
+    for (pt = 0; pt < M; pt++) {
+        int scene, start, k, l, cnt = 0, n;
+        const float* q = new_xyz + (size_t)pt * 3;
+        const float* p;
+        int* row = idx + (size_t)pt * nsample;
+        orc_scene_of(pt, B, new_xyz_batch_cnt, xyz_batch_cnt, &scene, &start);
+        p = xyz + (size_t)start * 3;
+        n = xyz_batch_cnt[scene];
+        for (k = 0; k < n; ++k) {
+            const float dx = q[0] - p[k * 3 + 0], dy = q[1] - p[k * 3 + 1], dz = q[2] - p[k * 3 + 2];
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d2 < radius2) {
+                if (cnt == 0)
+                    for (l = 0; l < nsample; ++l) row[l] = k;
+                row[cnt] = k;
+                ++cnt;
+                if (cnt >= nsample) break;
+            }
+        }
+        if (cnt == 0) row[0] = -1;
+    }
+}
+
+void orc_group_points_stack(int B, int M, int C, int nsample, const float* features, const int* features_batch_cnt,
+                            const int* idx, const int* idx_batch_cnt, float* out) {
+    int pt, c, s;
+    for (pt = 0; pt < M; pt++) {
+        int scene, start;
+        orc_scene_of(pt, B, idx_batch_cnt, features_batch_cnt, &scene, &start);
+        for (c = 0; c < C; c++)
+            for (s = 0; s < nsample; s++)
+                out[((size_t)pt * C + c) * nsample + s] = features[((size_t)start + idx[(size_t)pt * nsample + s]) * C + c];
+    }
+}
+
+/* grad_features [N, C] is accumulated in double and rounded once (the reference's float atomics are order dependent) */
+void orc_group_points_grad_stack(int B, int M, int C, int N, int nsample, const float* grad_out, const int* idx,
+                                 const int* idx_batch_cnt, const int* features_batch_cnt, float* grad_features) {
+    int pt, c, s;
+    size_t i;
+    double* acc = (double*)calloc((size_t)N * C + 1, sizeof(double));
+    for (pt = 0; pt < M; pt++) {
+        int scene, start;
+        orc_scene_of(pt, B, idx_batch_cnt, features_batch_cnt, &scene, &start);
+        for (c = 0; c < C; c++)
+            for (s = 0; s < nsample; s++)
+                acc[((size_t)start + idx[(size_t)pt * nsample + s]) * C + c] += grad_out[((size_t)pt * C + c) * nsample + s];
+    }
+    for (i = 0; i < (size_t)N * C; i++) grad_features[i] = (float)acc[i];
+    free(acc);
 }
