@@ -103,3 +103,38 @@ def batch_points(scenes):
     offs = np.zeros(len(scenes) + 1, dtype=np.int32)
     offs[1:] = np.cumsum([s.shape[0] for s in scenes])
     return np.ascontiguousarray(np.concatenate(scenes, axis=0), dtype=np.float32), offs
+
+
+def roi_head_case(batch=2, n_points=20000, n_rois=128, n_occ=3000, channels=128, seed=0, stride=8):
+    """Synthetic inputs of the RoI head (`ConvHead.roi_conv_pool`, conv_head.py:247-379), numpy:
+    rois [B, n_rois, 7] (the scene's boxes, jittered and repeated), points [sum N, 5] (b, x, y, z, intensity),
+    occ_pnts [sum n_occ, 4] (x, y, z, probability) + their scene index, and the rows of a `x_combine`-like sparse
+    tensor at `stride` (coords [n, 4] b z y x over [2, 200, 176], features [n, channels] >= 0 with exact zeros): the
+    occupied cells are those that contain points."""
+    rng = np.random.default_rng(1000 + seed)
+    pts, rois, occ, occ_b, coords = [], [], [], [], []
+    vs = np.array(DET_VOXEL_SIZE) * stride
+    shape = [2, 200, 176]
+    for b in range(batch):
+        p, boxes = lidar_like(n_points, seed=seed * 16 + b, return_boxes=True)
+        pts.append(np.concatenate([np.full((p.shape[0], 1), b, np.float32), p], axis=1))
+        pick = rng.integers(0, boxes.shape[0], n_rois)
+        r = boxes[pick, :7].copy()
+        r[:, :3] += rng.normal(0.0, 0.3, (n_rois, 3)).astype(np.float32)
+        r[:, 3:6] *= rng.uniform(0.9, 1.1, (n_rois, 3)).astype(np.float32)
+        r[:, 6] += rng.normal(0.0, 0.1, n_rois).astype(np.float32)
+        rois.append(r)
+        o = boxes[rng.integers(0, boxes.shape[0], n_occ), :3] + rng.normal(0.0, 0.8, (n_occ, 3))
+        occ.append(np.concatenate([o, rng.uniform(0.3, 1.0, (n_occ, 1))], axis=1).astype(np.float32))
+        occ_b.append(np.full(n_occ, b, np.int64))
+        x = np.floor((p[:, 0] - KITTI_RANGE[0]) / vs[0]).astype(np.int64)
+        y = np.floor((p[:, 1] - KITTI_RANGE[1]) / vs[1]).astype(np.int64)
+        z = np.clip(np.floor((p[:, 2] - KITTI_RANGE[2]) / (vs[2] * 2.5)).astype(np.int64), 0, shape[0] - 1)
+        ok = (x >= 0) & (x < shape[2]) & (y >= 0) & (y < shape[1])
+        cells = np.unique(np.stack([z[ok], y[ok], x[ok]], axis=1), axis=0)
+        coords.append(np.concatenate([np.full((cells.shape[0], 1), b, np.int64), cells], axis=1))
+    coords = np.concatenate(coords, axis=0).astype(np.int32)
+    feats = np.maximum(rng.standard_normal((coords.shape[0], channels)), 0.0).astype(np.float32)
+    return {"batch_size": batch, "rois": np.stack(rois).astype(np.float32), "points": np.concatenate(pts).astype(np.float32),
+            "occ_pnts": np.concatenate(occ), "added_occ_b_ind": np.concatenate(occ_b), "x_coords": coords,
+            "x_features": feats, "x_shape": shape}

@@ -128,9 +128,12 @@ def cuda_as_cpu():
     for name in _FACTORIES:
         saved[name] = getattr(torch, name)
         setattr(torch, name, wrap(saved[name]))
+    tensor_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **kw: self        # `.cuda()` in constructors (loss_utils.py:196)
     try:
         yield
     finally:
+        torch.Tensor.cuda = tensor_cuda
         for name, fn in saved.items():
             setattr(torch, name, fn)
 
@@ -150,3 +153,48 @@ class Cfg(dict):
         if isinstance(d, dict):
             return Cfg({k: Cfg.wrap(v) for k, v in d.items()})
         return d
+
+
+def load_roi_head_modules(device="cpu"):
+    """The reference's RoI head (`btcdet/models/roi_heads/conv_head.py`) with its import chain: the
+    compiled extensions it reaches are replaced by this repo's drop-ins (`btcdet_b200.pointnet2_stack_cuda`,
+    `btcdet_b200.iou3d_nms_cuda`), everything else is the reference's own Python executed where it lies.
+    Returns {"conv_head": module, "ConvHead": class, "cfg": the ROI_HEAD section of btcdet_kitti_car.yaml (Cfg)}."""
+    import yaml
+    mods = load_reference_modules(device)
+    from btcdet_b200 import iou3d_nms_cuda, pointnet2_stack_cuda
+    _ns("btcdet.ops.iou3d_nms", os.path.join(REF, "btcdet/ops/iou3d_nms"))
+    sys.modules["btcdet.ops.iou3d_nms.iou3d_nms_cuda"] = iou3d_nms_cuda
+    sys.modules["btcdet.ops.iou3d_nms"].iou3d_nms_cuda = iou3d_nms_cuda
+    _ns("btcdet.ops.pointnet2", os.path.join(REF, "btcdet/ops/pointnet2"))
+    _ns("btcdet.ops.pointnet2.pointnet2_stack", os.path.join(REF, "btcdet/ops/pointnet2/pointnet2_stack"))
+    sys.modules["btcdet.ops.pointnet2.pointnet2_stack.pointnet2_stack_cuda"] = pointnet2_stack_cuda
+    sys.modules["btcdet.ops.pointnet2.pointnet2_stack"].pointnet2_stack_cuda = pointnet2_stack_cuda
+    _ns("btcdet.models.roi_heads", os.path.join(REF, "btcdet/models/roi_heads"))
+    _ns("btcdet.models.roi_heads.target_assigner", os.path.join(REF, "btcdet/models/roi_heads/target_assigner"))
+    _ns("btcdet.models.model_utils", os.path.join(REF, "btcdet/models/model_utils"))
+    with cuda_as_cpu():
+        _load("btcdet.ops.iou3d_nms.iou3d_nms_utils", "btcdet/ops/iou3d_nms/iou3d_nms_utils.py")
+        _load("btcdet.ops.pointnet2.pointnet2_stack.pointnet2_utils", "btcdet/ops/pointnet2/pointnet2_stack/pointnet2_utils.py")
+        _load("btcdet.ops.pointnet2.pointnet2_stack.pointnet2_modules", "btcdet/ops/pointnet2/pointnet2_stack/pointnet2_modules.py")
+        _load("btcdet.utils.box_utils", "btcdet/utils/box_utils.py")
+        _load("btcdet.utils.box_coder_utils", "btcdet/utils/box_coder_utils.py")
+        _load("btcdet.utils.loss_utils", "btcdet/utils/loss_utils.py")
+        _load("btcdet.models.model_utils.model_nms_utils", "btcdet/models/model_utils/model_nms_utils.py")
+        _load("btcdet.models.roi_heads.target_assigner.proposal_target_layer",
+              "btcdet/models/roi_heads/target_assigner/proposal_target_layer.py")
+        _load("btcdet.models.roi_heads.roi_head_template", "btcdet/models/roi_heads/roi_head_template.py")
+        ch = _load("btcdet.models.roi_heads.conv_head", "btcdet/models/roi_heads/conv_head.py")
+    with open(os.path.join(REF, "tools/cfgs/model_configs/btcdet_kitti_car.yaml")) as fh:
+        cfg = Cfg.wrap(yaml.safe_load(fh))
+    mods.update({"conv_head": ch, "ConvHead": ch.ConvHead, "cfg": cfg.MODEL.ROI_HEAD})
+    return mods
+
+
+def build_conv_head(mods, voxel_size, point_cloud_range, num_rawpoint_features=4):
+    """ConvHead exactly as `Detector3DTemplate.build_roi_head` constructs it (detector3d_template.py:344-358)."""
+    import copy
+    with cuda_as_cpu():
+        return mods["ConvHead"](input_channels=128, model_cfg=copy.deepcopy(mods["cfg"]), num_class=1,
+                                det_voxel_size=voxel_size, point_cloud_range=point_cloud_range,
+                                num_rawpoint_features=num_rawpoint_features, pre_conv_num_bev_features=256)

@@ -184,7 +184,7 @@ def test_emulated_trilinear_kernels_are_bit_exact(emul, normalize, batch, shape,
     from oracle import roi_pool as R
     rng = np.random.default_rng(batch * 10 + C)
     Pn = lshape[0] * lshape[1] * lshape[2]
-    per_scene = Pn * 5
+    per_scene = Pn * (2 if Pn > 50 else 5)
     coords, feats = _sparse_source(rng, batch, shape, min(60 * batch, batch * shape[0] * shape[1] * shape[2] // 2), C)
     zyx = _targets(rng, batch, shape, per_scene)
     T = zyx.shape[0]
@@ -251,3 +251,40 @@ def test_drop_in_module_surface_and_cpu_rejection():
 
     with pytest.raises(RuntimeError):
         roi_pool.trilinear_gather_rows(T, zyx, 1, [1, 1, 1])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+def test_oracle_rows_are_the_reference_conv_head_method():
+    """oracle.roi_pool.target_indices + interpolate_rows == ConvHead.create_local_conv_grid /
+    interpolate_from_3d_features (conv_head.py:207-223, 505-528) of the reference's own class, constructed from the
+    reference's yaml, on the synthetic RoI-head case (CPU): same rows, same coordinates, bit for bit."""
+    from btcdet_b200 import synthetic as S
+    from oracle import roi_pool as R
+    mods = ref_loader.load_roi_head_modules()
+    head = ref_loader.build_conv_head(mods, S.DET_VOXEL_SIZE, S.KITTI_RANGE)
+    case = S.roi_head_case(batch=2, n_points=6000, n_rois=6, n_occ=100, channels=16)
+    rois = torch.from_numpy(case["rois"])
+    feats, coords, shape = torch.from_numpy(case["x_features"]), torch.from_numpy(case["x_coords"]), case["x_shape"]
+    with ref_loader.cuda_as_cpu():
+        grid_pts, _ = head.get_global_grid_points_of_roi(rois, grid_size=head.grid_size, e2e=False, dim_times=head.dim_times)
+        sm = head.size_map["x_combine"]
+        conv_pts, dense_idx = head.create_local_conv_grid(grid_pts.view(-1, 3), rois, sm["local_grid_size"], sm["dims"],
+                                                          sm["scene_times"])
+
+        class Feat(object):
+            spatial_shape = shape
+            indices = coords
+
+            @staticmethod
+            def dense():
+                return R.dense_volume(feats, coords, 2, shape)
+
+        want_c, want_f = head.interpolate_from_3d_features(conv_pts, dense_idx, Feat, head.downsample_times_map["x_combine"])
+    assert tuple(conv_pts.shape) == (2, 6 * 27 * 96, 3) and tuple(dense_idx.shape) == (2 * 6 * 27, 96, 3)
+    zyx = R.target_indices(conv_pts, S.KITTI_RANGE, S.DET_VOXEL_SIZE, [8, 8, 8])
+    got_c, got_f, _ = R.interpolate_rows(feats, coords, 2, shape, zyx, conv_pts.shape[1], [2, 4, 12])
+    assert want_f.shape[0] > 200
+    assert torch.equal(got_f, want_f) and torch.equal(got_c.float(), want_c)
+    # the product's host-side index expression is the same torch expression
+    from btcdet_b200 import roi_pool
+    assert torch.equal(roi_pool.target_indices(conv_pts, S.KITTI_RANGE, S.DET_VOXEL_SIZE, [8, 8, 8]), zyx)
