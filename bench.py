@@ -403,7 +403,8 @@ def run_ours(args, rank, world):
                 res["gpu_native_baseline"] = {"error": repr(exc)}
             for key, fn in (("batch32", lambda: bench_legs.batch_leg(model, scenes, dev, 32)),
                             ("chain", lambda: bench_legs.chain_leg(dev)),
-                            ("stress", lambda: bench_legs.stress_leg(dev, float(roof["peak"]) if roof else 6552.0))):
+                            ("stress", lambda: bench_legs.stress_leg(dev, float(roof["peak"]) if roof else 6552.0)),
+                            ("roi_pool", lambda: bench_legs.roi_pool_leg(dev))):
                 try:
                     res[key] = fn()
                 except Exception as exc:

@@ -293,3 +293,80 @@ def stress_leg(dev, peak_gbs, reps=5):
             "gather_gemm_16x16": row(ms_g, 4 * m * 16 * 2 + 8 * pairs_s + 4 * 27 * 16 * 16),
             "what": "config 5 (stress): 2 x 100k-point clouds, voxel [0.025,0.025,0.05]; eager calls incl. their allocations and "
                     "the one host read of a strided rulebook; bytes = SURVEY §8(d) algorithmic bytes"}
+
+
+def roi_pool_leg(dev, steps=10, warmup=3, batch=2, n_rois=128):
+    """SURVEY §8(f) N1 — the native ops under `ConvHead.roi_conv_pool` (conv_head.py:247-379) at the yaml's training
+    shape (2 scenes x 128 RoIs x 27 grid points, 96-cell mini grids): both stacked ball queries (4 + 3 radii, one launch
+    each), the fused reverse trilinear gather from the stride-8 sparse tensor, and the three SparseConv3d(128 -> 128) of
+    the mini grids + dense().  Product code only; reference-side numbers are in profiles/r2_roi_pool_report.json."""
+    import spconv
+    from btcdet_b200 import pointnet2_stack_cuda as p2, roi_pool, synthetic as S
+    case = S.roi_head_case(batch=batch, n_points=20000, n_rois=n_rois)
+    rng = np.random.default_rng(7)
+    rois = case["rois"]
+    g = np.stack(np.meshgrid(np.arange(3), np.arange(3), np.arange(3), indexing="ij"), -1).reshape(-1, 3)
+    grid = (rois[:, :, None, :3] + ((g + 0.5) / 3.0 - 0.5)[None, None] * rois[:, :, None, 3:6]).astype(np.float32)   # un-rotated 3x3x3
+    q = torch.from_numpy(np.ascontiguousarray(grid.reshape(-1, 3))).to(dev)
+    qcnt = torch.full((batch,), n_rois * 27, dtype=torch.int32, device=dev)
+    pts = case["points"]
+    xyz = torch.from_numpy(np.ascontiguousarray(pts[:, 1:4])).to(dev)
+    cnt = torch.from_numpy(np.bincount(pts[:, 0].astype(np.int64), minlength=batch).astype(np.int32)).to(dev)
+    occ = torch.from_numpy(np.ascontiguousarray(case["occ_pnts"][:, :3])).to(dev)
+    occ_cnt = torch.from_numpy(np.bincount(case["added_occ_b_ind"], minlength=batch).astype(np.int32)).to(dev)
+    M = int(q.shape[0])
+    raw_r, raw_n, occ_r, occ_n = [0.4, 0.8, 1.2, 2.4], [16, 16, 32, 64], [0.8, 1.2, 2.4], [16, 16, 32]
+    raw_idx = [torch.zeros((M, n), dtype=torch.int32, device=dev) for n in raw_n]
+    occ_idx = [torch.zeros((M, n), dtype=torch.int32, device=dev) for n in occ_n]
+    sp = spconv.SparseConvTensor(torch.from_numpy(case["x_features"]).to(dev), torch.from_numpy(case["x_coords"]).to(dev),
+                                 case["x_shape"], batch)
+    lz, ly, lx = np.meshgrid(np.arange(2), np.arange(4), np.arange(12), indexing="ij")
+    cell = np.stack([(lx.ravel() + 0.5) * 0.4 - 2.4, (ly.ravel() + 0.5) * 0.4 - 0.8, (lz.ravel() + 0.5) * 0.8 - 0.8], axis=1)
+    cpts = torch.from_numpy((grid[:, :, :, None, :] + cell[None, None, None]).reshape(batch, -1, 3).astype(np.float32)).to(dev)
+    zyx = roi_pool.target_indices(cpts, S.KITTI_RANGE, S.DET_VOXEL_SIZE, [8, 8, 8])
+    per_scene = int(cpts.shape[1])
+    torch.manual_seed(0)
+    convs = spconv.SparseSequential(
+        spconv.SparseConv3d(128, 128, [3, 3, 3], stride=[1, 1, 2], padding=[1, 1, 1], bias=False, indice_key="n1_0"),
+        spconv.SparseConv3d(128, 128, [3, 3, 3], stride=[1, 2, 2], padding=[1, 1, 1], bias=False, indice_key="n1_1"),
+        spconv.SparseConv3d(128, 128, [2, 2, 3], stride=[2, 2, 3], padding=[0, 0, 0], bias=False, indice_key="n1_2")).to(dev).eval()
+    state = {}
+
+    def ball():
+        p2.ball_query_multi(raw_r, raw_n, q, qcnt, xyz, cnt, raw_idx)
+        p2.ball_query_multi(occ_r, occ_n, q, qcnt, occ, occ_cnt, occ_idx)
+
+    def gather():
+        state["rows"] = roi_pool.trilinear_gather_rows(sp, zyx, per_scene, [2, 4, 12])
+
+    def conv():
+        c, r = state["rows"]
+        t = spconv.SparseConvTensor(r, c, [2, 4, 12], batch * n_rois * 27)
+        state["out"] = convs(t).dense()
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(steps):
+            e0, e1 = _events()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms))
+
+    with torch.no_grad():
+        ms_b, ms_g, ms_c = timed(ball), timed(gather), timed(conv)
+    total = ms_b + ms_g + ms_c
+    n_rows = int(state["rows"][1].shape[0])
+    alg = int(zyx.shape[0]) * (12 + 32) + n_rows * (128 * 4 + 16) + int(sp.features.shape[0]) * 128 * 4
+    return {"value": round(batch / (total * 1e-3), 1), "unit": "scenes/s", "ms": round(total, 4),
+            "ball_query_ms": round(ms_b, 4), "trilinear_gather_ms": round(ms_g, 4), "mini_grid_convs_ms": round(ms_c, 4),
+            "queries": M, "targets": int(zyx.shape[0]), "gathered_rows": n_rows, "out_shape": list(state["out"].shape),
+            "trilinear_alg_bytes": alg, "trilinear_gbs": round(alg / (ms_g * 1e-3) / 1e9, 1),
+            "what": "N1 ops at the yaml's training shape (2 scenes x 128 RoIs x 27 grid points): 4 + 3 radii stacked ball "
+                    "queries in two launches, fused reverse trilinear gather (exact mode: one count read), three "
+                    "SparseConv3d(128->128) on 6912 mini grids of [2,4,12] + dense(); eager calls incl. allocations"}
