@@ -288,3 +288,67 @@ def test_oracle_rows_are_the_reference_conv_head_method():
     # the product's host-side index expression is the same torch expression
     from btcdet_b200 import roi_pool
     assert torch.equal(roi_pool.target_indices(conv_pts, S.KITTI_RANGE, S.DET_VOXEL_SIZE, [8, 8, 8]), zyx)
+
+
+# ---- randomised shapes (hypothesis): the emulated kernels against the oracle ------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=30, deadline=None, derandomize=True)
+@given(st.data())
+def test_emulated_ball_query_random_ragged_batches(oracle, emul, data):
+    from oracle import roi_pool as R
+    B = data.draw(st.integers(1, 4))
+    counts = [data.draw(st.integers(0, 90)) for _ in range(B)]
+    qcounts = [data.draw(st.integers(0, 9)) for _ in range(B)]
+    n_r = data.draw(st.integers(1, 4))
+    radii = [data.draw(st.sampled_from([0.3, 0.5, 0.9, 1.7, 4.0])) for _ in range(n_r)]
+    nsamples = [data.draw(st.sampled_from([1, 2, 7, 16, 33, 64])) for _ in range(n_r)]
+    rng = np.random.default_rng(data.draw(st.integers(0, 10 ** 6)))
+    xyz, cnt, q, qcnt = _scene(rng, counts, qcounts, spread=2.0)
+    if sum(counts) == 0:
+        xyz = np.zeros((1, 3), np.float32)               # a valid pointer; no scene has points
+    M = q.shape[0]
+    if M == 0:
+        return
+    outs = [np.full((M, ns), -77, np.int32) for ns in nsamples]
+    ptrs = (ctypes.c_void_p * n_r)(*[o.ctypes.data for o in outs])
+    assert emul.emul_ball_query_stack(B, M, n_r, _p(np.array(radii, np.float32)), _p(np.array(nsamples, np.int32)), _p(q),
+                                      _p(qcnt), _p(xyz), _p(cnt), ptrs, data.draw(st.integers(1, 3))) == 0
+    for r in range(n_r):
+        assert np.array_equal(outs[r], R.ball_query_stack(radii[r], nsamples[r], xyz, cnt, q, qcnt)), (r, counts, qcounts)
+
+
+@settings(max_examples=20, deadline=None, derandomize=True)
+@given(st.data())
+def test_emulated_trilinear_random_shapes(emul, data):
+    from oracle import roi_pool as R
+    batch = data.draw(st.integers(1, 3))
+    shape = [data.draw(st.integers(1, 4)), data.draw(st.integers(1, 9)), data.draw(st.integers(1, 9))]
+    C = data.draw(st.sampled_from([1, 3, 31, 32, 33, 70]))
+    lshape = [data.draw(st.integers(1, 2)), data.draw(st.integers(1, 3)), data.draw(st.integers(1, 4))]
+    normalize = data.draw(st.booleans())
+    Pn = lshape[0] * lshape[1] * lshape[2]
+    per_scene = Pn * data.draw(st.integers(1, 4))
+    rng = np.random.default_rng(data.draw(st.integers(0, 10 ** 6)))
+    cells = batch * shape[0] * shape[1] * shape[2]
+    n = data.draw(st.integers(0, min(cells, 40)))
+    coords, feats = _sparse_source(rng, batch, shape, n, C) if n else (np.zeros((0, 4), np.int32), np.zeros((0, C), np.float32))
+    T = batch * per_scene
+    zyx = np.stack([rng.uniform(-1.5, shape[0] + 0.5, T), rng.uniform(-1.5, shape[1] + 0.5, T),
+                    rng.uniform(-1.5, shape[2] + 0.5, T)], 1).astype(np.float32)
+    zyx[::5] = np.floor(zyx[::5])
+    want_c, want_f, want_t = R.interpolate_rows(torch.from_numpy(feats), torch.from_numpy(coords), batch, shape,
+                                                torch.from_numpy(zyx), per_scene, lshape, normalize=normalize)
+    k = want_f.shape[0]
+    out_f = np.full((T, C), np.nan, np.float32)
+    out_c = np.full((T, 4), -9, np.int32)
+    out_t = np.full((T,), -9, np.int64)
+    src_f = feats if n else np.zeros((1, C), np.float32)
+    src_c = coords if n else np.zeros((1, 4), np.int32)
+    total = emul.emul_trilinear_sparse(_p(src_f), _p(src_c), n, C, batch, _p(np.array(shape, np.int32)), _p(zyx), None, T,
+                                       per_scene, int(normalize), Pn, _p(np.array(lshape, np.int32)), T, _p(out_f), _p(out_c),
+                                       _p(out_t), 2)
+    assert total == k
+    assert np.array_equal(out_f[:k], want_f.numpy()) and np.array_equal(out_c[:k], want_c.numpy().astype(np.int32))
+    assert np.array_equal(out_t[:k], want_t.numpy())
