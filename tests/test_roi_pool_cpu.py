@@ -352,3 +352,29 @@ def test_emulated_trilinear_random_shapes(emul, data):
     assert total == k
     assert np.array_equal(out_f[:k], want_f.numpy()) and np.array_equal(out_c[:k], want_c.numpy().astype(np.int32))
     assert np.array_equal(out_t[:k], want_t.numpy())
+
+
+def test_oracle_and_emulated_kernel_against_the_reference_generated_fixture(emul):
+    """tests/golden/roi_pool_ref.npz = the reference's ConvHead (built from its yaml) run on the CPU by
+    tests/golden/make_roi_pool_golden.py.  Runs without a reference checkout: the oracle AND the kernel source under the
+    emulation reproduce the reference's coordinates and rows bit for bit from the reference's own grid points."""
+    from btcdet_b200 import synthetic as S
+    from oracle import roi_pool as R
+    g = np.load(os.path.join(HERE, "golden", "roi_pool_ref.npz"))
+    conv_pts = torch.from_numpy(g["conv_grid_points"])
+    shape, lshape, stride = g["x_shape"].tolist(), g["local_grid_size"].tolist(), g["stride"].tolist()
+    feats, coords = np.ascontiguousarray(g["x_features"]), np.ascontiguousarray(g["x_coords"])
+    zyx = R.target_indices(conv_pts, S.KITTI_RANGE, S.DET_VOXEL_SIZE, stride)
+    per_scene = conv_pts.shape[1]
+    got_c, got_f, _ = R.interpolate_rows(torch.from_numpy(feats), torch.from_numpy(coords), 2, shape, zyx, per_scene, lshape)
+    assert got_f.shape[0] == g["out_features"].shape[0] > 500
+    assert np.array_equal(got_f.numpy(), g["out_features"]) and np.array_equal(got_c.float().numpy(), g["out_coords"])
+    T, C = zyx.shape[0], feats.shape[1]
+    n = got_f.shape[0]
+    out_f, out_c = np.zeros((n, C), np.float32), np.zeros((n, 4), np.int32)
+    zyx_np = np.ascontiguousarray(zyx.numpy())
+    total = emul.emul_trilinear_sparse(_p(feats), _p(coords), coords.shape[0], C, 2, _p(np.array(shape, np.int32)), _p(zyx_np),
+                                       None, T, per_scene, 0, lshape[0] * lshape[1] * lshape[2],
+                                       _p(np.array(lshape, np.int32)), n, _p(out_f), _p(out_c), None, 4)
+    assert total == n
+    assert np.array_equal(out_f, g["out_features"]) and np.array_equal(out_c.astype(np.float32), g["out_coords"])
