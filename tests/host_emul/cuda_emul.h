@@ -1,11 +1,14 @@
-// TEST INFRASTRUCTURE ONLY — a lock-step warp emulation of the few CUDA device features the RoI-pooling kernels use, so
-// that the CPU test-suite can execute the KERNEL SOURCE (btcdet_b200/csrc/roi_pool_kernels.cuh, unchanged) on the host
-// and compare it with the oracle where no GPU exists.  Nothing here is shipped or reachable from the product
-// (btcdet_b200/, spconv/): the product has no CPU path.
+// TEST INFRASTRUCTURE ONLY — a lock-step emulation of the CUDA device features the index / pooling / RoI kernels use, so
+// that the CPU test-suite can execute the KERNEL SOURCE (btcdet_b200/csrc/*.cu, *.cuh) on the host and compare it with the
+// oracle and the golden vectors where no GPU exists.  Nothing here is shipped or reachable from the product
+// (btcdet_b200/, spconv/): the product has no CPU path, and this emulation is far too slow to be one.
 //
-// Model: one block = one warp = 32 OS threads that meet at a barrier inside every warp collective (__ballot_sync,
-// __shfl_sync), which is exact for kernels whose collectives are reached convergently (all of these are).  Blocks run
-// one after the other.  Rounded intrinsics map to the host's IEEE operations (compile with -ffp-contract=off).
+// Model: a block = blockDim.x OS threads; blocks run one after the other, in index order (which also makes single-pass
+// look-back scans terminate).  __syncthreads is a barrier over the block, every warp collective (__ballot_sync,
+// __shfl_*_sync, __reduce_or_sync) a barrier over the warp's 32 threads — exact for kernels whose collectives are
+// reached convergently (a thread that returns early drops out of both barriers, as on the hardware).  `__shared__`
+// variables are function-level statics (one block at a time), the dynamic shared memory is a per-launch buffer.
+// Rounded intrinsics map to the host's IEEE operations (compile with -ffp-contract=off); atomics are std::atomic_ref.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -13,8 +16,11 @@
 #include <atomic>
 #include <barrier>
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -23,76 +29,191 @@ struct Idx {
     unsigned x = 0, y = 0, z = 0;
 };
 struct WarpState {
-    std::barrier<> bar{32};
+    explicit WarpState(int n) : bar(n) {}
+    std::barrier<> bar;
     unsigned bits[32];
+};
+struct BlockState {
+    explicit BlockState(int n) : bar(n) {
+        for (int w = 0; w * 32 < n; ++w) warps.emplace_back(new WarpState(std::min(32, n - w * 32)));
+    }
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<WarpState>> warps;
 };
 inline thread_local Idx t_idx, b_idx, b_dim, g_dim;
 inline thread_local WarpState* warp = nullptr;
+inline thread_local BlockState* block = nullptr;
+inline thread_local unsigned lane_id = 0;   // lane = linear thread index % 32
+inline unsigned char* dyn_smem = nullptr;   // dynamic shared memory of the running block
 
-// Runs `body` as `blocks` blocks of one warp each.
-inline void launch(unsigned blocks, const std::function<void()>& body) {
-    WarpState ws;
+// Runs `body` for every thread of a (grid x block) launch with `smem` bytes of dynamic shared memory.  One OS thread per
+// thread of a block; the same threads run the blocks one after the other (block barriers are per block: a thread that
+// returned early has dropped out of them; `next` keeps the blocks from overlapping).
+inline void launch(dim3 grid, dim3 blk, size_t smem, const std::function<void()>& body) {
+    std::vector<unsigned char> dyn(smem + 64);
+    dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+    const unsigned block_threads = blk.x * blk.y * blk.z;
+    const unsigned nblocks = grid.x * grid.y * grid.z;
+    if (block_threads == 0 || nblocks == 0) return;
+    std::vector<std::unique_ptr<BlockState>> states;
+    states.reserve(nblocks);
+    for (unsigned b = 0; b < nblocks; ++b) states.emplace_back(new BlockState((int)block_threads));
+    std::barrier<> next((int)block_threads);
     std::vector<std::thread> th;
-    for (unsigned lane = 0; lane < 32; ++lane)
-        th.emplace_back([&, lane] {
-            warp = &ws;
-            t_idx.x = lane;
-            b_dim.x = 32;
-            g_dim.x = blocks;
-            for (unsigned b = 0; b < blocks; ++b) {
-                b_idx.x = b;
+    th.reserve(block_threads);
+    for (unsigned t = 0; t < block_threads; ++t)
+        th.emplace_back([&, t] {
+            lane_id = t & 31;
+            t_idx.x = t % blk.x; t_idx.y = (t / blk.x) % blk.y; t_idx.z = t / (blk.x * blk.y);
+            b_dim.x = blk.x; b_dim.y = blk.y; b_dim.z = blk.z;
+            g_dim.x = grid.x; g_dim.y = grid.y; g_dim.z = grid.z;
+            for (unsigned b = 0; b < nblocks; ++b) {
+                BlockState& bs = *states[b];
+                block = &bs;
+                warp = bs.warps[t >> 5].get();     // warps are formed over the linear thread index
+                b_idx.x = b % grid.x; b_idx.y = (b / grid.x) % grid.y; b_idx.z = b / (grid.x * grid.y);
                 body();
-                ws.bar.arrive_and_wait();
+                warp->bar.arrive_and_drop();      // a finished thread no longer takes part in collectives / barriers
+                bs.bar.arrive_and_drop();
+                next.arrive_and_wait();
             }
         });
     for (auto& t : th) t.join();
+    dyn_smem = nullptr;
 }
+// the form the RoI tests use: `blocks` blocks of one warp
+inline void launch(unsigned blocks, const std::function<void()>& body) { launch(dim3(blocks), dim3(32), 0, body); }
 }  // namespace emul
 
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif
+#undef __shared__
+#define __shared__ static
 #define threadIdx emul::t_idx
 #define blockIdx emul::b_idx
 #define blockDim emul::b_dim
 #define gridDim emul::g_dim
+#define warpSize 32
 
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
+inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
+inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-inline void __syncthreads() {}
+inline int __ffsll(unsigned long long v) { return __builtin_ffsll((long long)v); }
+inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline void __syncthreads() { emul::block->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emul::warp->bar.arrive_and_wait(); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
-inline unsigned __ballot_sync(unsigned, bool p) {
-    auto* w = emul::warp;
-    w->bits[emul::t_idx.x] = p ? 1u : 0u;
-    w->bar.arrive_and_wait();
-    unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m |= w->bits[i] << i;
-    w->bar.arrive_and_wait();
-    return m;
-}
+// ---- warp collectives -------------------------------------------------------------------------------------------------
+namespace emul {
 template <class T>
-inline T __shfl_sync(unsigned, T v, int src) {
-    static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    auto* w = emul::warp;
-    std::memcpy(&w->bits[emul::t_idx.x], &v, 4);
+inline T exchange(T v, int src) {   // every lane publishes v, reads lane `src`'s
+    static_assert(sizeof(T) == 4, "32-bit collectives only");
+    WarpState* w = warp;
+    std::memcpy(&w->bits[lane_id], &v, 4);
     w->bar.arrive_and_wait();
     T r;
     std::memcpy(&r, &w->bits[src & 31], 4);
     w->bar.arrive_and_wait();
     return r;
 }
+}  // namespace emul
+inline unsigned __ballot_sync(unsigned, bool p) {
+    auto* w = emul::warp;
+    w->bits[emul::lane_id] = p ? 1u : 0u;
+    w->bar.arrive_and_wait();
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (w->bits[i] & 1u) << i;
+    w->bar.arrive_and_wait();
+    return m;
+}
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    auto* w = emul::warp;
+    w->bits[emul::lane_id] = v;
+    w->bar.arrive_and_wait();
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= w->bits[i];
+    w->bar.arrive_and_wait();
+    return m;
+}
+inline int __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+inline int __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) { return emul::exchange(v, src); }
 template <class T>
 inline T __shfl_up_sync(unsigned, T v, int d) {
-    int lane = (int)emul::t_idx.x;
-    T r = __shfl_sync(0xffffffffu, v, lane >= d ? lane - d : lane);
+    const int lane = (int)(emul::lane_id);
+    return emul::exchange(v, lane >= d ? lane - d : lane);
+}
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, int d) {
+    const int lane = (int)(emul::lane_id);
+    return emul::exchange(v, lane + d < 32 ? lane + d : lane);
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int m) {
+    const int lane = (int)(emul::lane_id);
+    return emul::exchange(v, lane ^ m);
+}
+
+// ---- atomics ----------------------------------------------------------------------------------------------------------
+template <class T>
+inline T atomicAdd(T* p, T v) { return std::atomic_ref<T>(*p).fetch_add(v); }
+template <class T>
+inline T atomicOr(T* p, T v) { return std::atomic_ref<T>(*p).fetch_or(v); }
+template <class T>
+inline T atomicAnd(T* p, T v) { return std::atomic_ref<T>(*p).fetch_and(v); }
+template <class T>
+inline T atomicExch(T* p, T v) { return std::atomic_ref<T>(*p).exchange(v); }
+template <class T>
+inline T atomicCAS(T* p, T expected, T desired) {
+    std::atomic_ref<T>(*p).compare_exchange_strong(expected, desired);
+    return expected;
+}
+template <class T>
+inline T atomicMin(T* p, T v) {
+    std::atomic_ref<T> a(*p);
+    T old = a.load();
+    while (v < old && !a.compare_exchange_weak(old, v)) {}
+    return old;
+}
+template <class T>
+inline T atomicMax(T* p, T v) {
+    std::atomic_ref<T> a(*p);
+    T old = a.load();
+    while (v > old && !a.compare_exchange_weak(old, v)) {}
+    return old;
+}
+using std::max;
+using std::min;
+
+// nvcc's templated overload (cuda_runtime.h, __CUDACC__ only): opting a kernel into large dynamic shared memory is a no-op here
+template <class R, class... A>
+inline cudaError_t cudaFuncSetAttribute(R (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }
+
+// block-wide OR of a predicate with the barrier semantics of __syncthreads
+inline int __syncthreads_or(int p) {
+    static std::atomic<int> acc{0};
+    emul::block->bar.arrive_and_wait();
+    if (p) acc.store(1);
+    emul::block->bar.arrive_and_wait();
+    const int r = acc.load();
+    emul::block->bar.arrive_and_wait();
+    acc.store(0);
+    emul::block->bar.arrive_and_wait();
     return r;
 }
-inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
-using std::min;
-using std::max;

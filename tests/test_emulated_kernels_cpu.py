@@ -1,0 +1,168 @@
+"""The GPU parity tests' own test functions (tests/test_parity_gpu.py) executed on the CPU against the KERNEL SOURCE of
+btcdet_b200/csrc/{voxelize,coord_index,rulebook,pool_dense,points_transform,roi_pool}.cu compiled for the host under the
+lock-step emulation of tests/host_emul/ (tests/host_emul/build_emul.py: the real `btc_*` C entry points, numpy / CPU-torch
+buffers standing in for device memory).  TEST INFRASTRUCTURE: the product has no CPU path — this module swaps the loaded
+library, the stream getter and the is-CUDA check of `btcdet_b200.ops` for the duration of a test and puts them back.
+Only the small cases run here (one OS thread per CUDA thread); the full sizes run on the B200 (`-m gpu`)."""
+import contextlib
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, os.path.join(HERE, "host_emul"))
+import ref_loader  # noqa: E402  (cuda_as_cpu: device="cuda" -> "cpu", Tensor.cuda() -> identity)
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    import build_emul
+    from btcdet_b200 import _lib
+    lib = ctypes.CDLL(build_emul.build())
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if hasattr(lib, name):            # the tcgen05 / FFMA / mask files are not part of the emulated build
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    return lib
+
+
+@contextlib.contextmanager
+def emulated(lib):
+    from btcdet_b200 import _lib, ops
+    saved = (_lib._lib, ops._stream, ops._require_cuda, ref_loader.ON_CUDA)
+    _lib._lib, ops._stream, ops._require_cuda, ref_loader.ON_CUDA = lib, (lambda: None), (lambda *a, **k: None), False
+    try:
+        with ref_loader.cuda_as_cpu():
+            yield
+    finally:
+        _lib._lib, ops._stream, ops._require_cuda, ref_loader.ON_CUDA = saved
+
+
+def test_voxeliser_kernels_bit_exact_under_emulation(oracle, emul_lib):
+    import tests.test_parity_gpu as G
+    with emulated(emul_lib):
+        G.test_voxelize_edge_cases(None, oracle)
+        G.test_voxelize_bit_exact(None, oracle, "config1_uniform2k")
+
+
+def test_rulebook_kernels_bit_exact_under_emulation(oracle, emul_lib):
+    import tests.test_parity_gpu as G
+    with emulated(emul_lib):
+        G.test_rulebook_empty_and_single(None, oracle)
+        G.test_rulebook_sort_rows(None, 127, 27)
+        G.test_rulebook_sort_rows(None, 2049, 8)
+
+
+def test_rulebook_pyramids_bit_exact_under_emulation(oracle, emul_lib):
+    """The det pyramid's geometries (sub-manifold tables through the hash and through the rank bitmap, k3 s2 p1, k3 s2
+    p(0,1,1), k(3,1,1) s(2,1,1), strided output index reused by the next sub-manifold layer) and the occupancy
+    backbone's (dilating k3 s1 p1, two transposed convolutions) on small grids: output order, neighbour tables and the
+    spconv-format pair lists against the oracle, bit for bit."""
+    import tests.test_parity_gpu as G
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(4)
+    with emulated(emul_lib):
+        batch, shape = 2, [21, 48, 40]
+        flat = rng.choice(batch * int(np.prod(shape)), 1200, replace=False)
+        coords = np.stack([flat // int(np.prod(shape)), (flat // (shape[1] * shape[2])) % shape[0],
+                           (flat // shape[2]) % shape[1], flat % shape[2]], 1).astype(np.int32)
+        for lvl, (ksize, stride, pad) in enumerate([(3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0)]):
+            c = torch.from_numpy(coords)
+            rb = ops.rulebook_subm(c, batch, shape, 3)
+            G._check_rulebook(oracle, rb, coords, batch, shape, 3, 1, 1, True, False)
+            if lvl == 0:
+                rb_bitmap = ops.rulebook_subm(c, batch, shape, 3, index=ops.build_index(c, batch, shape, need_perm=True))
+                assert torch.equal(rb_bitmap.nbr_out, rb.nbr_out)
+            rb = ops.rulebook_conv(c, batch, shape, ksize, stride, pad)
+            coords = G._check_rulebook(oracle, rb, coords, batch, shape, ksize, stride, pad, False, False)
+            rb2 = ops.rulebook_subm(rb.out_coords, batch, rb.out_shape, 3, index=rb.out_index)
+            G._check_rulebook(oracle, rb2, coords, batch, rb.out_shape, 3, 1, 1, True, False)
+            shape = rb.out_shape
+        batch, shape = 2, [9, 21, 25]
+        flat = rng.choice(batch * int(np.prod(shape)), 700, replace=False)
+        coords = np.stack([flat // int(np.prod(shape)), (flat // (shape[1] * shape[2])) % shape[0],
+                           (flat // shape[2]) % shape[1], flat % shape[2]], 1).astype(np.int32)
+        for ksize, stride, pad, tr in [(3, 1, 1, False), (3, 2, 1, False), (3, 2, 1, False), (3, 2, 1, True), (3, 2, 1, True)]:
+            rb = ops.rulebook_conv(torch.from_numpy(coords), batch, shape, ksize, stride, pad, transposed=tr)
+            coords = G._check_rulebook(oracle, rb, coords, batch, shape, ksize, stride, pad, False, tr)
+            shape = rb.out_shape
+        assert shape == [9, 21, 25]
+
+
+def test_pool_dense_revoxelise_kernels_under_emulation(oracle, emul_lib):
+    """SparseMaxPool3d forward / backward (zero-init quirk), dense() / its backward, and the sorted re-voxelisation
+    (torch.unique(dim=0) + stable slots) on small inputs."""
+    import tests.test_parity_gpu as G
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(9)
+    with emulated(emul_lib):
+        batch, shape = 2, [9, 24, 20]
+        flat = rng.choice(batch * int(np.prod(shape)), 900, replace=False)
+        coords = np.stack([flat // int(np.prod(shape)), (flat // (shape[1] * shape[2])) % shape[0],
+                           (flat // shape[2]) % shape[1], flat % shape[2]], 1).astype(np.int32)
+        feat = rng.standard_normal((coords.shape[0], 3)).astype(np.float32)
+        outids, pairs, pair_num, _ = oracle.get_indice_pairs(coords, batch, shape, 3, 2, 1)
+        rb = ops.rulebook_conv(torch.from_numpy(coords), batch, shape, 3, 2, 1)
+        f = torch.from_numpy(feat).requires_grad_()
+        out = ops.SparseMaxPoolFunction.apply(f, rb)
+        np.testing.assert_array_equal(out.detach().numpy(), oracle.indice_maxpool(feat, pairs, pair_num, outids.shape[0]))
+        out.sum().backward()
+        assert np.all(f.grad.numpy() >= 0) and f.grad.sum() > 0
+        fd = torch.from_numpy(feat).requires_grad_()
+        d = ops.ToDenseFunction.apply(fd, torch.from_numpy(coords), batch, shape)
+        np.testing.assert_array_equal(d.detach().numpy(), oracle.dense(feat, coords, shape, batch))
+        wgt = torch.randn_like(d)
+        (d * wgt).sum().backward()
+        li = torch.from_numpy(coords).long()
+        np.testing.assert_array_equal(fd.grad.numpy(), wgt[li[:, 0], :, li[:, 1], li[:, 2], li[:, 3]].numpy())
+        # re-voxelisation
+        g = torch.Generator().manual_seed(0)
+        base = torch.stack([torch.randint(0, 2, (300,), generator=g), torch.randint(0, 9, (300,), generator=g),
+                            torch.randint(0, 24, (300,), generator=g), torch.randint(0, 20, (300,), generator=g)], 1)
+        pc = torch.cat([base, base[:120], base[:30]], 0)
+        pc = pc[torch.randperm(pc.shape[0], generator=g)]
+        pf = torch.randn(pc.shape[0], 6, generator=g)
+        vox, cnt, vc = ops.revoxelize_sorted(pc, pf, 2, shape)
+        u, inv, counts = torch.unique(pc, dim=0, sorted=True, return_inverse=True, return_counts=True)
+        assert torch.equal(vc, u) and torch.equal(cnt, counts) and vox.shape == (u.shape[0], int(counts.max()), 6)
+        ref, seen = torch.zeros_like(vox), {}
+        for i in range(pc.shape[0]):
+            v = int(inv[i])
+            ref[v, seen.get(v, 0)] = pf[i]
+            seen[v] = seen.get(v, 0) + 1
+        assert torch.equal(vox, ref)
+
+
+def test_transform_conv_golden_and_iou_kernels_under_emulation(oracle, emul_lib):
+    """a2 coordinate transform (numpy's op order; angles to the GPU test's 4 ulp), BASELINE configs[0] against the
+    committed golden fixture (voxelise -> SubM rulebook -> fp32 FFMA gather-GEMM), a strided FFMA convolution with bias /
+    folded affine / ReLU, its backward against autograd, and the rotated BEV IoU against the float64 oracle."""
+    import tests.test_iou3d_gpu as GI
+    import tests.test_parity_gpu as G
+    import tests.test_points_transform_gpu as GP
+    with emulated(emul_lib):
+        GP.test_points_to_cylinder_and_sphere(None, 0, 20000)
+        G.test_config1_golden(None, oracle)
+        G.test_sparse_conv_forward_within_tolerance(None, oracle, 6, 16, "conv")
+    # rotated BEV IoU / overlap straight through the C entry point (tolerances of tests/test_iou3d_gpu.py)
+    from oracle import iou3d
+    a, b = GI.random_boxes(60, 3), GI.random_boxes(50, 4)
+    a[:, 0] += 40.0
+    b[:, 0] += 40.0
+    for mode, tol in ((0, 2e-4), (1, 2e-3)):
+        out = np.zeros((60, 50), np.float32)
+        assert emul_lib.btc_boxes_bev(a.ctypes.data, 60, b.ctypes.data, 50, mode, out.ctypes.data, None) == 0
+        want = iou3d.boxes_bev(a, b, bool(mode))
+        assert np.abs(out - want).max() < tol and (want > 0).sum() > 50
+    # NMS: 64 x 64 mask blocks + the greedy scan by one warp, keep list and count in "device" memory
+    bx = GI._gap_boxes(150, 7, 0.3)
+    want = iou3d.greedy_nms(iou3d.boxes_bev(bx, bx), 0.3)
+    keep, num = np.full(len(bx), -1, np.int64), np.zeros(1, np.int32)
+    ws = np.zeros(int(emul_lib.btc_nms_workspace_bytes(len(bx))) + 64, np.uint8)
+    assert emul_lib.btc_nms(bx.ctypes.data, len(bx), 0.3, 0, keep.ctypes.data, num.ctypes.data, ws.ctypes.data, ws.size, None) == 0
+    assert 5 < len(want) < len(bx) and int(num[0]) == len(want) and keep[:len(want)].tolist() == want.tolist()
