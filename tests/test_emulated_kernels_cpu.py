@@ -166,3 +166,72 @@ def test_transform_conv_golden_and_iou_kernels_under_emulation(oracle, emul_lib)
     ws = np.zeros(int(emul_lib.btc_nms_workspace_bytes(len(bx))) + 64, np.uint8)
     assert emul_lib.btc_nms(bx.ctypes.data, len(bx), 0.3, 0, keep.ctypes.data, num.ctypes.data, ws.ctypes.data, ws.size, None) == 0
     assert 5 < len(want) < len(bx) and int(num[0]) == len(want) and keep[:len(want)].tolist() == want.tolist()
+
+
+# ---- randomised geometries (hypothesis): rulebook kernels against the oracle -----------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None, derandomize=True)
+@given(st.data())
+def test_rulebooks_random_geometries_under_emulation(oracle, emul_lib, data):
+    """Kernel sizes 1..3, strides 1..3, paddings 0..2, dilation with stride 1, regular / transposed / sub-manifold, on
+    small random grids and batches: output coordinates (ascending flat key), both neighbour tables and the spconv-format
+    pair lists equal the oracle's (the straight-line fast paths and the general path are both reached)."""
+    import tests.test_parity_gpu as G
+    from btcdet_b200 import ops
+    batch = data.draw(st.integers(1, 3))
+    shape = [data.draw(st.integers(2, 9)), data.draw(st.integers(3, 14)), data.draw(st.integers(3, 14))]
+    cells = batch * shape[0] * shape[1] * shape[2]
+    n = data.draw(st.integers(1, min(cells, 120)))
+    rng = np.random.default_rng(data.draw(st.integers(0, 10 ** 6)))
+    flat = rng.choice(cells, n, replace=False)
+    if data.draw(st.booleans()):
+        flat = np.sort(flat)
+    coords = np.stack([flat // (shape[0] * shape[1] * shape[2]), (flat // (shape[1] * shape[2])) % shape[0],
+                       (flat // shape[2]) % shape[1], flat % shape[2]], 1).astype(np.int32)
+    kind = data.draw(st.sampled_from(["conv", "transposed", "subm"]))
+    with emulated(emul_lib):
+        c = torch.from_numpy(coords)
+        if kind == "subm":
+            ksize = [data.draw(st.sampled_from([1, 3])) for _ in range(3)]
+            rb = ops.rulebook_subm(c, batch, shape, ksize)
+            G._check_rulebook(oracle, rb, coords, batch, shape, ksize, 1, [k // 2 for k in ksize], True, False)
+            return
+        ksize = [data.draw(st.integers(1, 3)) for _ in range(3)]
+        stride = [data.draw(st.integers(1, 3)) for _ in range(3)]
+        pad = [data.draw(st.integers(0, min(2, k - 1))) for k in ksize]
+        tr = kind == "transposed"
+        out_shape = (ops.deconv_output_shape(shape, ksize, stride, pad, [1, 1, 1], [0, 0, 0]) if tr
+                     else ops.conv_output_shape(shape, ksize, stride, pad, [1, 1, 1]))
+        if min(out_shape) <= 0 or batch * out_shape[0] * out_shape[1] * out_shape[2] > 60000:
+            return
+        rb = ops.rulebook_conv(c, batch, shape, ksize, stride, pad, transposed=tr)
+        G._check_rulebook(oracle, rb, coords, batch, shape, ksize, stride, pad, False, tr)
+
+
+@settings(max_examples=20, deadline=None, derandomize=True)
+@given(st.data())
+def test_voxeliser_random_scenes_under_emulation(oracle, emul_lib, data):
+    """Random small scenes (empty scenes, points outside the range, both caps biting): voxel order, coordinates, counts
+    and the point rows equal the sequential oracle's, bit for bit."""
+    import tests.test_parity_gpu as G
+    n_scenes = data.draw(st.integers(1, 3))
+    rng = np.random.default_rng(data.draw(st.integers(0, 10 ** 6)))
+    vs = [data.draw(st.sampled_from([0.25, 0.5, 1.0])) for _ in range(3)]
+    rg = [0.0, -2.0, -1.0, 4.0, 2.0, 1.0]
+    mp, mv = data.draw(st.integers(1, 4)), data.draw(st.sampled_from([3, 20, 400]))
+    scenes = []
+    for _ in range(n_scenes):
+        n = data.draw(st.integers(0, 300))
+        p = rng.uniform([-0.5, -2.5, -1.2, 0.0], [4.5, 2.5, 1.2, 1.0], (n, 4)).astype(np.float32)
+        if n and data.draw(st.booleans()):
+            p[: n // 2, :3] = np.round(p[: n // 2, :3] * 4) / 4          # points exactly on voxel edges
+        scenes.append(p)
+    with emulated(emul_lib):
+        ov, oc, on = oracle.voxelize_batch(scenes, vs, rg, mp, mv)
+        gv, gc, gn, gmean, nv = G._gpu_voxelize(scenes, vs, rg, mp, mv, want_mean=True)
+    assert gc.shape == oc.shape
+    np.testing.assert_array_equal(gc, oc)
+    np.testing.assert_array_equal(gn, on)
+    np.testing.assert_array_equal(gv, ov)
