@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "btcdet_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-LIB = os.path.join(OUT, "libbtcdet_b200_emul.so")
+SAN = os.environ.get("BTC_EMUL_SANITIZE", "")      # e.g. "address": an AddressSanitizer build (run pytest under LD_PRELOAD=libasan)
+LIB = os.path.join(OUT, "libbtcdet_b200_emul%s.so" % ("_" + SAN if SAN else ""))
 FILES = ["coord_index.cu", "voxelize.cu", "rulebook.cu", "pool_dense.cu", "points_transform.cu", "roi_pool.cu",
          "sparse_conv.cu", "iou3d_nms.cu"]
 
@@ -113,14 +114,16 @@ def build(force=False):
         cpp = os.path.join(OUT, f.replace(".cu", ".emul.cpp"))
         with open(cpp, "w") as fh:
             fh.write('#include "cuda_emul.h"\n' + (STUBS if f == FILES[0] else "") + transform(src))
-        obj = cpp.replace(".cpp", ".o")
-        res = subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w", "-DBTC_SM=100",
+        obj = cpp.replace(".cpp", (".%s.o" % SAN) if SAN else ".o")
+        res = subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w", "-DBTC_SM=100"] +
+                             (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + SAN] if SAN else []) + [
                               "-I" + HERE, "-I" + CSRC, "-I/usr/local/cuda/include", "-c", cpp, "-o", obj],
                              capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("g++ failed for %s:\n%s" % (f, res.stderr[:4000]))
         objs.append(obj)
-    subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", LIB] + objs, check=True, capture_output=True)
+    subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic"] + (["-fsanitize=" + SAN] if SAN else []) + ["-o", LIB] + objs,
+                   check=True, capture_output=True)
     return LIB
 
 

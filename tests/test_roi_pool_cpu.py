@@ -23,12 +23,14 @@ def emul():
     src = os.path.join(HERE, "host_emul", "roi_pool_emul.cpp")
     out_dir = os.path.join(HERE, "host_emul", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libroi_pool_emul.so")
+    san = os.environ.get("BTC_EMUL_SANITIZE", "")      # "address": AddressSanitizer build (run pytest under LD_PRELOAD=libasan)
+    lib = os.path.join(out_dir, "libroi_pool_emul%s.so" % ("_" + san if san else ""))
     deps = [src, os.path.join(HERE, "host_emul", "cuda_emul.h"),
             os.path.join(ROOT, "btcdet_b200", "csrc", "roi_pool_kernels.cuh"), os.path.join(ROOT, "btcdet_b200", "csrc", "common.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w",
-                        "-I/usr/local/cuda/include", src, "-o", lib], check=True, capture_output=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w"] +
+                       (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + san] if san else []) +
+                       ["-I/usr/local/cuda/include", src, "-o", lib], check=True, capture_output=True)
     lib = ctypes.CDLL(lib)
     lib.emul_ball_query_stack.argtypes = [I, I, I, P, P, P, P, P, P, P, I]
     lib.emul_group_points_stack.argtypes = [I, I, I, I, P, P, P, P, P, I]
