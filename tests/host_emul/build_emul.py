@@ -19,7 +19,7 @@ OUT = os.path.join(HERE, "_build")
 SAN = os.environ.get("BTC_EMUL_SANITIZE", "")      # e.g. "address": an AddressSanitizer build (run pytest under LD_PRELOAD=libasan)
 LIB = os.path.join(OUT, "libbtcdet_b200_emul%s.so" % ("_" + SAN if SAN else ""))
 FILES = ["coord_index.cu", "voxelize.cu", "rulebook.cu", "pool_dense.cu", "points_transform.cu", "roi_pool.cu",
-         "sparse_conv.cu", "iou3d_nms.cu"]
+         "sparse_conv.cu", "iou3d_nms.cu", "occ_masks.cu", "box_masks.cu"]
 
 
 def _match(text, i, open_ch, close_ch):

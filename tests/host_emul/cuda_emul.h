@@ -217,3 +217,16 @@ inline int __syncthreads_or(int p) {
     emul::block->bar.arrive_and_wait();
     return r;
 }
+
+// conversions with explicit rounding (round to nearest even, like the host's default rounding mode)
+inline long long __double2ll_rn(double v) { return std::llrint(v); }
+inline long long __float2ll_rn(float v) { return std::llrintf(v); }
+inline int __float2int_rn(float v) { return (int)std::lrintf(v); }
+inline int __float2int_rd(float v) { return (int)std::floor(v); }
+inline int __float2int_rz(float v) { return (int)v; }
+inline double __ll2double_rn(long long v) { return (double)v; }
+inline float __ll2float_rn(long long v) { return (float)v; }
+inline float __int2float_rn(int v) { return (float)v; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline float __frcp_rn(float a) { return 1.0f / a; }

@@ -235,3 +235,19 @@ def test_voxeliser_random_scenes_under_emulation(oracle, emul_lib, data):
     np.testing.assert_array_equal(gc, oc)
     np.testing.assert_array_equal(gn, on)
     np.testing.assert_array_equal(gv, ov)
+
+
+def test_mask_kernels_under_emulation(oracle, emul_lib):
+    """Occupancy / occlusion masks (rows a5-a8, a12) and the box-driven targets (a9-a11) on the host: the border-clamp known
+    answer, the fixture generated by the reference's own OccTargets3D on the CPU (integer-only masks exact, the occluded
+    set within the bound the GPU test uses for that cross-device fixture — the host's libm is one more libm), exact loss-map
+    algebra, the edge cases, and the box targets against the CPU oracle."""
+    import tests.test_box_masks_gpu as GB
+    import tests.test_occ_gpu as GO
+    with emulated(emul_lib):
+        GO.test_occ_masks_empty_and_edge(None)
+        GO.test_occ_masks_vs_reference_fixture(None, oracle)
+        GB.test_end_to_end_targets_close_to_reference_fixture(None, oracle)
+        GB.test_loss_maps_exact(None, oracle)
+        GB.test_box_targets_edge_cases(None, oracle)
+        GB.test_box_targets_match_oracle_on_device(None, oracle, [11], 6000, False, False)
