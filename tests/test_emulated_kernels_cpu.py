@@ -172,7 +172,7 @@ def test_transform_conv_golden_and_iou_kernels_under_emulation(oracle, emul_lib)
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
-@settings(max_examples=25, deadline=None, derandomize=True)
+@settings(max_examples=16, deadline=None, derandomize=True)
 @given(st.data())
 def test_rulebooks_random_geometries_under_emulation(oracle, emul_lib, data):
     """Kernel sizes 1..3, strides 1..3, paddings 0..2, dilation with stride 1, regular / transposed / sub-manifold, on
@@ -210,7 +210,7 @@ def test_rulebooks_random_geometries_under_emulation(oracle, emul_lib, data):
         G._check_rulebook(oracle, rb, coords, batch, shape, ksize, stride, pad, False, tr)
 
 
-@settings(max_examples=20, deadline=None, derandomize=True)
+@settings(max_examples=12, deadline=None, derandomize=True)
 @given(st.data())
 def test_voxeliser_random_scenes_under_emulation(oracle, emul_lib, data):
     """Random small scenes (empty scenes, points outside the range, both caps biting): voxel order, coordinates, counts
