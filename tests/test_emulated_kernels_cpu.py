@@ -251,3 +251,47 @@ def test_mask_kernels_under_emulation(oracle, emul_lib):
         GB.test_loss_maps_exact(None, oracle)
         GB.test_box_targets_edge_cases(None, oracle)
         GB.test_box_targets_match_oracle_on_device(None, oracle, [11], 6000, False, False)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+def test_sync_free_proposal_layer_equals_the_reference_method_under_emulation(emul_lib):
+    """btcdet_b200.proposal.proposal_layer against `RoIHeadTemplate.proposal_layer` (roi_head_template.py:46-101) of the
+    reference's own ConvHead instance, both on the emulated library: identical rois / scores / labels, with tied scores,
+    a scene with fewer kept boxes than NMS_POST_MAXSIZE and both NMS types."""
+    import tests.test_iou3d_gpu as GI
+    from btcdet_b200 import iou3d_nms_cuda as iou, proposal, synthetic as S
+    mods = ref_loader.load_roi_head_modules()
+    head = ref_loader.build_conv_head(mods, S.DET_VOXEL_SIZE, S.KITTI_RANGE)
+    rng = np.random.default_rng(12)
+    boxes = np.stack([GI._gap_boxes(260, 20 + b, 0.7)[:200] for b in range(2)])           # clustered: NMS has work
+    scores = np.round(rng.uniform(0, 1, (2, 200, 1)), 2).astype(np.float32)               # two decimals: many ties
+    saved = (iou._check_boxes, iou._stream)
+    iou._check_boxes, iou._stream = (lambda *a: None), (lambda: None)
+    try:
+        with emulated(emul_lib):
+            for nms_type, pre, post, thresh in (("nms_gpu", 150, 40, 0.7), ("nms_gpu", 4096, 300, 0.1), ("nms_normal_gpu", 100, 16, 0.5)):
+                cfg = ref_loader.Cfg({"NMS_TYPE": nms_type, "MULTI_CLASSES_NMS": False, "NMS_PRE_MAXSIZE": pre,
+                                      "NMS_POST_MAXSIZE": post, "NMS_THRESH": thresh})
+                mk = lambda: {"batch_size": 2, "batch_box_preds": torch.from_numpy(boxes.copy()),   # noqa: E731
+                              "batch_cls_preds": torch.from_numpy(scores.copy())}
+                want = head.proposal_layer(mk(), nms_config=cfg)
+                got = proposal.proposal_layer(mk(), cfg)
+                for k in ("rois", "roi_scores", "roi_labels"):
+                    assert torch.equal(got[k], want[k]), (nms_type, k)
+                assert got["has_class_labels"] == want["has_class_labels"]
+                kept = int((want["roi_scores"] > 0).sum())
+                assert 10 < kept <= 2 * post
+    finally:
+        iou._check_boxes, iou._stream = saved
+
+
+def test_proposal_layer_against_the_oracle_nms_under_emulation(emul_lib):
+    import tests.test_zz_proposal_gpu as GZ
+    from btcdet_b200 import iou3d_nms_cuda as iou
+    saved = (iou._check_boxes, iou._stream)
+    iou._check_boxes, iou._stream = (lambda *a: None), (lambda: None)
+    try:
+        with emulated(emul_lib):
+            GZ.test_proposal_layer_against_the_oracle_nms(None)
+    finally:
+        iou._check_boxes, iou._stream = saved
