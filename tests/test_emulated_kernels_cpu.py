@@ -295,3 +295,42 @@ def test_proposal_layer_against_the_oracle_nms_under_emulation(emul_lib):
             GZ.test_proposal_layer_against_the_oracle_nms(None)
     finally:
         iou._check_boxes, iou._stream = saved
+
+
+def test_ffma_conv_backward_under_emulation(oracle, emul_lib):
+    """dX / dW / db of the fp32 kernels (FFMA gather-GEMM over the mirrored table, slab-split outer products + atomics,
+    column sums) against autograd through the oracle formulation, on a small scene."""
+    import tests.test_parity_gpu as G
+    from btcdet_b200 import ops
+    rng = np.random.default_rng(0)
+    batch, shape = 1, [11, 40, 36]
+    flat = rng.choice(int(np.prod(shape)), 500, replace=False)
+    coords = np.stack([np.zeros_like(flat), flat // (shape[1] * shape[2]), (flat // shape[2]) % shape[1], flat % shape[2]],
+                      1).astype(np.int32)
+    with emulated(emul_lib):
+        for kind, cin, cout in [("subm", 16, 32), ("conv", 6, 20)]:
+            if kind == "subm":
+                outids, pairs, pair_num, _ = oracle.get_indice_pairs(coords, 1, shape, 3, subm=True)
+                rb = ops.rulebook_subm(torch.from_numpy(coords), 1, shape, 3)
+            else:
+                outids, pairs, pair_num, _ = oracle.get_indice_pairs(coords, 1, shape, 3, 2, 1)
+                rb = ops.rulebook_conv(torch.from_numpy(coords), 1, shape, 3, 2, 1)
+            feat = torch.from_numpy(rng.standard_normal((coords.shape[0], cin)).astype(np.float32))
+            w = torch.from_numpy((rng.standard_normal((27, cin, cout)) * 0.1).astype(np.float32))
+            b = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+            go = torch.from_numpy(rng.standard_normal((outids.shape[0], cout)).astype(np.float32))
+            f1, w1, b1 = feat.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+            out = torch.zeros(outids.shape[0], cout)
+            pr = torch.from_numpy(pairs).long()
+            for k in range(27):
+                nh = int(pair_num[k])
+                if nh:
+                    out = out.index_add(0, pr[1, k, :nh], f1[pr[0, k, :nh]] @ w1[k])
+            (out + b1).backward(go)
+            f2, w2, b2 = (t.clone().requires_grad_() for t in (feat, w, b))
+            y = ops.SparseConvFunction.apply(f2, w2, b2, rb, 1)
+            assert G.rel_err(y.detach().numpy(), (out + b1).detach().numpy()) < G.REL_TOL
+            y.backward(go)
+            assert G.rel_err(f2.grad.numpy(), f1.grad.numpy()) < G.REL_TOL
+            assert G.rel_err(w2.grad.numpy(), w1.grad.numpy()) < G.REL_TOL
+            assert G.rel_err(b2.grad.numpy(), b1.grad.numpy()) < G.REL_TOL
