@@ -99,6 +99,9 @@ cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memse
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+// the tcgen05 tile is not part of the emulated build: the shim's shape query says "not supported" and the fp32 FFMA tile runs
+int btc_sparse_conv_tc_supported(int, int, int) { return 0; }
+int btc_sparse_conv_tc_split_supported(int, int, int, int, int) { return 0; }
 }
 '''
 

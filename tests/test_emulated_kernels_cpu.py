@@ -334,3 +334,4 @@ def test_ffma_conv_backward_under_emulation(oracle, emul_lib):
             assert G.rel_err(f2.grad.numpy(), f1.grad.numpy()) < G.REL_TOL
             assert G.rel_err(w2.grad.numpy(), w1.grad.numpy()) < G.REL_TOL
             assert G.rel_err(b2.grad.numpy(), b1.grad.numpy()) < G.REL_TOL
+
