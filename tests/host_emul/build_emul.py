@@ -119,7 +119,7 @@ def build(force=False):
             fh.write('#include "cuda_emul.h"\n' + (STUBS if f == FILES[0] else "") + transform(src))
         obj = cpp.replace(".cpp", (".%s.o" % SAN) if SAN else ".o")
         res = subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w", "-DBTC_SM=100"] +
-                             (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + SAN] if SAN else []) + [
+                             (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + SAN, "-DEMUL_THREADS"] if SAN else []) + [
                               "-I" + HERE, "-I" + CSRC, "-I/usr/local/cuda/include", "-c", cpp, "-o", obj],
                              capture_output=True, text=True)
         if res.returncode != 0:

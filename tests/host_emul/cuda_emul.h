@@ -23,11 +23,21 @@
 #include <memory>
 #include <thread>
 #include <vector>
+#include <cstdio>
+#include <sys/mman.h>
+#include <ucontext.h>
 
 namespace emul {
 struct Idx {
     unsigned x = 0, y = 0, z = 0;
 };
+inline thread_local Idx t_idx, b_idx, b_dim, g_dim;
+inline thread_local unsigned lane_id = 0;   // lane = linear thread index % 32
+inline unsigned char* dyn_smem = nullptr;   // dynamic shared memory of the running block
+
+#ifdef EMUL_THREADS
+// ---- engine 1: one OS thread per CUDA thread (what the sanitizer builds use: ThreadSanitizer then sees every CUDA thread
+// as a thread and the barriers / atomics as the only synchronisation) -------------------------------------------------
 struct WarpState {
     explicit WarpState(int n) : bar(n) {}
     std::barrier<> bar;
@@ -40,15 +50,14 @@ struct BlockState {
     std::barrier<> bar;
     std::vector<std::unique_ptr<WarpState>> warps;
 };
-inline thread_local Idx t_idx, b_idx, b_dim, g_dim;
 inline thread_local WarpState* warp = nullptr;
 inline thread_local BlockState* block = nullptr;
-inline thread_local unsigned lane_id = 0;   // lane = linear thread index % 32
-inline unsigned char* dyn_smem = nullptr;   // dynamic shared memory of the running block
+inline unsigned* warp_bits() { return warp->bits; }
+inline void warp_barrier() { warp->bar.arrive_and_wait(); }
+inline void block_barrier() { block->bar.arrive_and_wait(); }
 
-// Runs `body` for every thread of a (grid x block) launch with `smem` bytes of dynamic shared memory.  One OS thread per
-// thread of a block; the same threads run the blocks one after the other (block barriers are per block: a thread that
-// returned early has dropped out of them; `next` keeps the blocks from overlapping).
+// The same threads run the blocks one after the other (block barriers are per block: a thread that returned early has
+// dropped out of them; `next` keeps the blocks from overlapping).
 inline void launch(dim3 grid, dim3 blk, size_t smem, const std::function<void()>& body) {
     std::vector<unsigned char> dyn(smem + 64);
     dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
@@ -81,6 +90,119 @@ inline void launch(dim3 grid, dim3 blk, size_t smem, const std::function<void()>
     for (auto& t : th) t.join();
     dyn_smem = nullptr;
 }
+#else
+// ---- engine 2 (default): one FIBER per CUDA thread, all on the calling OS thread.  A barrier is a context switch to the
+// next fiber that can run, so a block costs microseconds instead of futex storms; execution is deterministic; a barrier
+// that can never complete (divergent collectives) aborts with a message instead of hanging. -----------------------------
+struct Barrier {
+    int gen = 0, arrived = 0, alive = 0;
+};
+struct Fiber {
+    ucontext_t ctx;
+    unsigned tid = 0;
+    bool done = false;
+    const int* wait_gen = nullptr;
+    int wait_val = 0;
+};
+struct FiberBlock {
+    ucontext_t sched;
+    std::vector<Fiber> fibers;
+    Fiber* cur = nullptr;
+    Barrier block_bar;
+    Barrier warp_bar[32];
+    unsigned bits[32][32];
+    const std::function<void()>* body = nullptr;
+    dim3 blk;
+};
+inline FiberBlock* fb = nullptr;
+
+inline void fiber_wait(Barrier& b) {
+    const int g = b.gen;
+    if (++b.arrived >= b.alive) {       // last one in: release the others, go on
+        b.arrived = 0;
+        ++b.gen;
+        return;
+    }
+    Fiber* me = fb->cur;
+    me->wait_gen = &b.gen;
+    me->wait_val = g;
+    swapcontext(&me->ctx, &fb->sched);
+    me->wait_gen = nullptr;
+}
+inline void fiber_leave(Barrier& b) {   // a finished thread no longer takes part
+    --b.alive;
+    if (b.alive > 0 && b.arrived >= b.alive) {
+        b.arrived = 0;
+        ++b.gen;
+    }
+}
+inline void fiber_entry() {
+    (*fb->body)();
+    Fiber* me = fb->cur;
+    me->done = true;
+    fiber_leave(fb->warp_bar[me->tid >> 5]);
+    fiber_leave(fb->block_bar);
+    swapcontext(&me->ctx, &fb->sched);
+}
+inline unsigned* warp_bits() { return fb->bits[fb->cur->tid >> 5]; }
+inline void warp_barrier() { fiber_wait(fb->warp_bar[fb->cur->tid >> 5]); }
+inline void block_barrier() { fiber_wait(fb->block_bar); }
+
+inline void launch(dim3 grid, dim3 blk, size_t smem, const std::function<void()>& body) {
+    std::vector<unsigned char> dyn(smem + 64);
+    dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+    const unsigned n = blk.x * blk.y * blk.z;
+    const unsigned nblocks = grid.x * grid.y * grid.z;
+    if (n == 0 || nblocks == 0) return;
+    constexpr size_t kStack = 256 * 1024;
+    char* stacks = (char*)mmap(nullptr, kStack * n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (stacks == MAP_FAILED) { std::fprintf(stderr, "cuda_emul: cannot map fiber stacks\n"); std::abort(); }
+    FiberBlock state;
+    FiberBlock* outer = fb;
+    fb = &state;
+    state.body = &body;
+    state.blk = blk;
+    state.fibers.resize(n);
+    b_dim.x = blk.x; b_dim.y = blk.y; b_dim.z = blk.z;
+    g_dim.x = grid.x; g_dim.y = grid.y; g_dim.z = grid.z;
+    for (unsigned b = 0; b < nblocks; ++b) {
+        b_idx.x = b % grid.x; b_idx.y = (b / grid.x) % grid.y; b_idx.z = b / (grid.x * grid.y);
+        state.block_bar = Barrier{0, 0, (int)n};
+        for (unsigned w = 0; w * 32 < n; ++w) state.warp_bar[w] = Barrier{0, 0, (int)std::min(32u, n - w * 32)};
+        for (unsigned t = 0; t < n; ++t) {
+            Fiber& f = state.fibers[t];
+            f.tid = t; f.done = false; f.wait_gen = nullptr;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = stacks + kStack * t;
+            f.ctx.uc_stack.ss_size = kStack;
+            f.ctx.uc_link = &state.sched;
+            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+        }
+        unsigned remaining = n;
+        while (remaining) {
+            bool progressed = false;
+            for (unsigned t = 0; t < n; ++t) {
+                Fiber& f = state.fibers[t];
+                if (f.done || (f.wait_gen && *f.wait_gen == f.wait_val)) continue;
+                progressed = true;
+                state.cur = &f;
+                lane_id = t & 31;
+                t_idx.x = t % blk.x; t_idx.y = (t / blk.x) % blk.y; t_idx.z = t / (blk.x * blk.y);
+                swapcontext(&state.sched, &f.ctx);
+                if (f.done) --remaining;
+            }
+            if (!progressed) {
+                std::fprintf(stderr, "cuda_emul: deadlock — a barrier / warp collective was not reached by every live thread of "
+                                     "block %u (divergent collective?)\n", b);
+                std::abort();
+            }
+        }
+    }
+    munmap(stacks, kStack * n);
+    fb = outer;
+    dyn_smem = nullptr;
+}
+#endif
 // the form the RoI tests use: `blocks` blocks of one warp
 inline void launch(unsigned blocks, const std::function<void()>& body) { launch(dim3(blocks), dim3(32), 0, body); }
 }  // namespace emul
@@ -113,8 +235,8 @@ inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __ffsll(unsigned long long v) { return __builtin_ffsll((long long)v); }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
-inline void __syncthreads() { emul::block->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emul::warp->bar.arrive_and_wait(); }
+inline void __syncthreads() { emul::block_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emul::warp_barrier(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
@@ -123,31 +245,31 @@ namespace emul {
 template <class T>
 inline T exchange(T v, int src) {   // every lane publishes v, reads lane `src`'s
     static_assert(sizeof(T) == 4, "32-bit collectives only");
-    WarpState* w = warp;
-    std::memcpy(&w->bits[lane_id], &v, 4);
-    w->bar.arrive_and_wait();
+    unsigned* bits = warp_bits();
+    std::memcpy(&bits[lane_id], &v, 4);
+    warp_barrier();
     T r;
-    std::memcpy(&r, &w->bits[src & 31], 4);
-    w->bar.arrive_and_wait();
+    std::memcpy(&r, &bits[src & 31], 4);
+    warp_barrier();
     return r;
 }
 }  // namespace emul
 inline unsigned __ballot_sync(unsigned, bool p) {
-    auto* w = emul::warp;
-    w->bits[emul::lane_id] = p ? 1u : 0u;
-    w->bar.arrive_and_wait();
+    unsigned* bits = emul::warp_bits();
+    bits[emul::lane_id] = p ? 1u : 0u;
+    emul::warp_barrier();
     unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m |= (w->bits[i] & 1u) << i;
-    w->bar.arrive_and_wait();
+    for (int i = 0; i < 32; ++i) m |= (bits[i] & 1u) << i;
+    emul::warp_barrier();
     return m;
 }
 inline unsigned __reduce_or_sync(unsigned, unsigned v) {
-    auto* w = emul::warp;
-    w->bits[emul::lane_id] = v;
-    w->bar.arrive_and_wait();
+    unsigned* bits = emul::warp_bits();
+    bits[emul::lane_id] = v;
+    emul::warp_barrier();
     unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m |= w->bits[i];
-    w->bar.arrive_and_wait();
+    for (int i = 0; i < 32; ++i) m |= bits[i];
+    emul::warp_barrier();
     return m;
 }
 inline int __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
@@ -208,13 +330,13 @@ inline cudaError_t cudaFuncSetAttribute(R (*)(A...), cudaFuncAttribute, int) { r
 // block-wide OR of a predicate with the barrier semantics of __syncthreads
 inline int __syncthreads_or(int p) {
     static std::atomic<int> acc{0};
-    emul::block->bar.arrive_and_wait();
+    emul::block_barrier();
     if (p) acc.store(1);
-    emul::block->bar.arrive_and_wait();
+    emul::block_barrier();
     const int r = acc.load();
-    emul::block->bar.arrive_and_wait();
+    emul::block_barrier();
     acc.store(0);
-    emul::block->bar.arrive_and_wait();
+    emul::block_barrier();
     return r;
 }
 

@@ -29,7 +29,7 @@ def emul():
             os.path.join(ROOT, "btcdet_b200", "csrc", "roi_pool_kernels.cuh"), os.path.join(ROOT, "btcdet_b200", "csrc", "common.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w"] +
-                       (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + san] if san else []) +
+                       (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + san, "-DEMUL_THREADS"] if san else []) +
                        ["-I/usr/local/cuda/include", src, "-o", lib], check=True, capture_output=True)
     lib = ctypes.CDLL(lib)
     lib.emul_ball_query_stack.argtypes = [I, I, I, P, P, P, P, P, P, P, I]
