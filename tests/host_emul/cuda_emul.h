@@ -3,12 +3,14 @@
 // oracle and the golden vectors where no GPU exists.  Nothing here is shipped or reachable from the product
 // (btcdet_b200/, spconv/): the product has no CPU path, and this emulation is far too slow to be one.
 //
-// Model: a block = blockDim.x OS threads; blocks run one after the other, in index order (which also makes single-pass
-// look-back scans terminate).  __syncthreads is a barrier over the block, every warp collective (__ballot_sync,
-// __shfl_*_sync, __reduce_or_sync) a barrier over the warp's 32 threads — exact for kernels whose collectives are
-// reached convergently (a thread that returns early drops out of both barriers, as on the hardware).  `__shared__`
-// variables are function-level statics (one block at a time), the dynamic shared memory is a per-launch buffer.
-// Rounded intrinsics map to the host's IEEE operations (compile with -ffp-contract=off); atomics are std::atomic_ref.
+// Model: every CUDA thread of a block is its own execution context — a ucontext fiber on the calling thread by default, an
+// OS thread with -DEMUL_THREADS (the sanitizer builds); blocks run one after the other, in index order (which also makes
+// single-pass look-back scans terminate).  __syncthreads is a barrier over the block, every warp collective
+// (__ballot_sync, __shfl_*_sync, __reduce_or_sync) a barrier over the warp's 32 threads — exact for kernels whose
+// collectives are reached convergently (a thread that returns early drops out of both barriers, as on the hardware; the
+// fiber engine aborts with a message when a barrier can never complete).  `__shared__` variables are function-level
+// statics (one block at a time), the dynamic shared memory is a per-launch buffer.  Rounded intrinsics map to the host's
+// IEEE operations (compile with -ffp-contract=off); atomics are std::atomic_ref.
 #pragma once
 #include <cuda_runtime.h>
 
