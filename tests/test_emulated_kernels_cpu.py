@@ -47,7 +47,8 @@ def test_voxeliser_kernels_bit_exact_under_emulation(oracle, emul_lib):
     import tests.test_parity_gpu as G
     with emulated(emul_lib):
         G.test_voxelize_edge_cases(None, oracle)
-        G.test_voxelize_bit_exact(None, oracle, "config1_uniform2k")
+        for case in ("config1_uniform2k", "lidar20k", "batch3", "cap_voxels", "occ_grid"):     # the GPU test's full sizes
+            G.test_voxelize_bit_exact(None, oracle, case)
 
 
 def test_rulebook_kernels_bit_exact_under_emulation(oracle, emul_lib):
@@ -335,3 +336,15 @@ def test_ffma_conv_backward_under_emulation(oracle, emul_lib):
             assert G.rel_err(w2.grad.numpy(), w1.grad.numpy()) < G.REL_TOL
             assert G.rel_err(b2.grad.numpy(), b1.grad.numpy()) < G.REL_TOL
 
+
+
+@pytest.mark.skipif(not os.environ.get("BTC_EMUL_FULL"), reason="minutes of CPU time: set BTC_EMUL_FULL=1")
+def test_full_size_rulebook_pyramids_under_emulation(oracle, emul_lib):
+    """The GPU tests' full-size rulebook cases (20k-point scene on the KITTI grid [41,1600,1408], both backbones' pyramids,
+    max-pool / dense, re-voxelisation) on the emulated library: ~5 min."""
+    import tests.test_parity_gpu as G
+    with emulated(emul_lib):
+        G.test_rulebooks_det_pyramid_bit_exact(None, oracle, 1, False)
+        G.test_rulebooks_occ_pyramid_with_transposed_bit_exact(None, oracle)
+        G.test_maxpool_and_dense(None, oracle)
+        G.test_revoxelize_sorted_matches_torch_unique(None)
