@@ -14,16 +14,21 @@ struct TriWs {
     int64_t bytes;
 };
 
+// Layout of the workspace; with workspace == nullptr only `bytes` is meaningful (size query).
 TriWs tri_ws(void* workspace, int64_t cells, int64_t T) {
-    TriWs w;
-    char* p = (char*)workspace;
-    int64_t off = 0;
-    w.vol = (int*)(p + off);        off += align_up(cells * 4, 256);
-    w.flags = (int*)(p + off);      off += align_up(T * 4, 256);
-    w.rank = (int*)(p + off);       off += align_up(T * 4, 256);
-    w.block_sums = (int*)(p + off); off += align_up((int64_t)(scan_num_blocks(T) + 2) * 4, 256);
-    w.total = (int*)(p + off);      off += 256;
-    w.bytes = off;
+    const int64_t o_flags = align_up(cells * 4, 256);
+    const int64_t o_rank = o_flags + align_up(T * 4, 256);
+    const int64_t o_sums = o_rank + align_up(T * 4, 256);
+    const int64_t o_total = o_sums + align_up((int64_t)(scan_num_blocks(T) + 2) * 4, 256);
+    TriWs w = {nullptr, nullptr, nullptr, nullptr, nullptr, o_total + 256};
+    if (workspace) {
+        char* p = (char*)workspace;
+        w.vol = (int*)p;
+        w.flags = (int*)(p + o_flags);
+        w.rank = (int*)(p + o_rank);
+        w.block_sums = (int*)(p + o_sums);
+        w.total = (int*)(p + o_total);
+    }
     return w;
 }
 
