@@ -348,3 +348,42 @@ def test_full_size_rulebook_pyramids_under_emulation(oracle, emul_lib):
         G.test_rulebooks_occ_pyramid_with_transposed_bit_exact(None, oracle)
         G.test_maxpool_and_dense(None, oracle)
         G.test_revoxelize_sorted_matches_torch_unique(None)
+
+
+def test_trilinear_entry_points_under_emulation(emul_lib):
+    """btc_trilinear_sparse_flag / _emit / _grad through the emulated library (workspace layout, the device-wide flag scan,
+    the count, capacity clamp) against the torch oracle."""
+    from oracle import roi_pool as R
+    import tests.test_roi_pool_cpu as TR
+    rng = np.random.default_rng(21)
+    batch, shape, C, lshape, per_scene = 2, [2, 20, 17], 8, [2, 4, 12], 96 * 4
+    coords, feats = TR._sparse_source(rng, batch, shape, 150, C)
+    zyx = TR._targets(rng, batch, shape, per_scene)
+    T = zyx.shape[0]
+    want_c, want_f, want_t = R.interpolate_rows(torch.from_numpy(feats), torch.from_numpy(coords), batch, shape,
+                                                torch.from_numpy(zyx), per_scene, lshape)
+    n = want_f.shape[0]
+    shp, lsh = (ctypes.c_int * 3)(*shape), (ctypes.c_int * 3)(*lshape)
+    ws_bytes = int(emul_lib.btc_trilinear_sparse_workspace_bytes(T, batch, shp))
+    ws = np.zeros(ws_bytes + 256, np.uint8)
+    wp = (ws.ctypes.data + 255) & ~255
+    count = np.full(1, -1, np.int32)
+    assert emul_lib.btc_trilinear_sparse_flag(feats.ctypes.data, coords.ctypes.data, coords.shape[0], None, C, batch, shp,
+                                              zyx.ctypes.data, None, T, per_scene, 0, count.ctypes.data, wp, ws_bytes, None) == 0
+    assert int(count[0]) == n > 20
+    for cap in (n, n - 7):
+        out_f, out_c = np.zeros((cap, C), np.float32), np.zeros((cap, 4), np.int32)
+        out_t = np.full(cap, -1, np.int64)
+        assert emul_lib.btc_trilinear_sparse_emit(feats.ctypes.data, C, batch, shp, zyx.ctypes.data, None, T, per_scene, 0, 96, lsh,
+                                                  cap, out_f.ctypes.data, out_c.ctypes.data, out_t.ctypes.data, wp, ws_bytes, None) == 0
+        assert np.array_equal(out_f, want_f.numpy()[:cap]) and np.array_equal(out_c, want_c.numpy()[:cap].astype(np.int32))
+        assert np.array_equal(out_t, want_t.numpy()[:cap])
+    g_rows = rng.standard_normal((n, C)).astype(np.float32)
+    grad = np.zeros_like(feats)
+    assert emul_lib.btc_trilinear_sparse_grad(g_rows.ctypes.data, out_t.ctypes.data if cap == n else want_t.numpy().ctypes.data, n,
+                                              None, C, batch, shp, zyx.ctypes.data, None, T, per_scene, 0, grad.ctypes.data, wp,
+                                              ws_bytes, None) == 0
+    ft = torch.from_numpy(feats).clone().requires_grad_(True)
+    _, rows, _ = R.interpolate_rows(ft, torch.from_numpy(coords), batch, shape, torch.from_numpy(zyx), per_scene, lshape)
+    rows.backward(torch.from_numpy(g_rows))
+    assert np.allclose(grad, ft.grad.numpy(), rtol=1e-5, atol=1e-5)
