@@ -387,3 +387,90 @@ def test_trilinear_entry_points_under_emulation(emul_lib):
     _, rows, _ = R.interpolate_rows(ft, torch.from_numpy(coords), batch, shape, torch.from_numpy(zyx), per_scene, lshape)
     rows.backward(torch.from_numpy(g_rows))
     assert np.allclose(grad, ft.grad.numpy(), rtol=1e-5, atol=1e-5)
+
+
+# ---- the spconv shim's host logic on the emulated library ------------------------------------------------------------
+@contextlib.contextmanager
+def shim_on_host(lib):
+    """As `emulated`, plus: tensors report is_cuda (the shim and the ops refuse CPU tensors — there is no CPU path — so the
+    test makes the host buffers look like device buffers for the duration of the block)."""
+    torch.Tensor.is_cuda = property(lambda self: True)
+    try:
+        with emulated(lib):
+            yield
+    finally:
+        del torch.Tensor.is_cuda
+
+
+def test_spconv_shim_backbone_on_the_emulated_library(oracle, emul_lib):
+    """`backbones.VoxelBackBone8x` through the `spconv` package (SparseSequential, SubM / strided layers sharing indice
+    keys, BatchNorm + ReLU in between) on two small scenes: every level's indices exact, features within 1e-4 of the
+    oracle network.  (The emulated build has no tcgen05 tile: every layer takes the fp32 FFMA tile.)"""
+    import tests.test_backbone_gpu as GB
+    from btcdet_b200 import backbones, synthetic as S
+    torch.manual_seed(0)
+    model = backbones.randomize_bn_(backbones.VoxelBackBone8x(4)).eval()
+    scenes = [S.lidar_like(1000, seed=100 + b) for b in range(2)]
+    v, c, npts = oracle.voxelize_batch(scenes, S.DET_VOXEL_SIZE, S.KITTI_RANGE, 5, 16000)
+    mean = (v.sum(1) / np.maximum(npts, 1)[:, None]).astype(np.float32)
+    ref = GB._oracle_forward(model, mean, c, 2)
+    with shim_on_host(emul_lib), torch.no_grad():
+        out = model({"voxel_features": torch.from_numpy(mean), "voxel_coords": torch.from_numpy(c), "batch_size": 2})
+    got = dict(out["multi_scale_3d_features"], out=out["encoded_spconv_tensor"])
+    for name, r in ref.items():
+        g = got[name]
+        assert list(g.spatial_shape) == r.spatial_shape, name
+        np.testing.assert_array_equal(g.indices.numpy(), r.indices, err_msg=name)
+        assert GB.rel_err(g.features.numpy(), r.features) < GB.REL_TOL, name
+    assert got["out"].spatial_shape == [2, 200, 176] and got["out"].features.shape[0] > 50
+
+
+@pytest.mark.skipif(not os.environ.get("BTC_EMUL_FULL"), reason="~2 min of CPU time: set BTC_EMUL_FULL=1")
+def test_reference_topologies_on_the_emulated_library(oracle, emul_lib):
+    """The dataflow of the reference's two backbones through the shim (tests/models_mirror.py): VoxelBackBone8xOcc —
+    SparseMaxPool3d side channel, sparse_cat, cached 'spconv3' / 'spconv4' rulebooks, dense() + gather — and
+    VoxelBackBoneDeconv + the occupancy head — dilating SparseConv3d, two SparseConvTranspose3d, SubM heads, dense()."""
+    import spconv
+    import tests.test_backbone_gpu as GB
+    from btcdet_b200 import synthetic as S
+    from oracle.occ_masks import OccGeometry
+    from tests import models_mirror, oracle_net
+    batch = 2
+    model = GB._randomize(models_mirror.DetBackboneMirror(6, 4), 3)
+    scenes = [S.lidar_like(900, seed=300 + b) for b in range(batch)]
+    v, coords, npts = oracle.voxelize_batch(scenes, S.DET_VOXEL_SIZE, S.KITTI_RANGE, 5, 16000)
+    rng = np.random.default_rng(0)
+    feats = np.concatenate([(v.sum(1) / np.maximum(npts, 1)[:, None]), rng.uniform(0, 1, (v.shape[0], 2))], 1).astype(np.float32)
+    occ_feats = np.abs(rng.standard_normal((v.shape[0], 2))).astype(np.float32)
+    ref = model.run(models_mirror.OracleBackend(), oracle_net.to_oracle_tensor(feats, coords, model.sparse_shape, batch), occ_feats)
+    with shim_on_host(emul_lib), torch.no_grad():
+        x = spconv.SparseConvTensor(torch.from_numpy(feats), torch.from_numpy(coords), model.sparse_shape, batch)
+        got = model.run(models_mirror.ShimBackend(), x, torch.from_numpy(occ_feats))
+    for name in ("x_conv2", "x_conv3", "out", "x_combine"):
+        np.testing.assert_array_equal(got[name].indices.numpy(), ref[name].indices, err_msg=name)
+        assert GB.rel_err(got[name].features.numpy(), ref[name].features) < GB.REL_TOL, name
+    assert got["x_combine"].features.shape[1] == 128 and list(got["out"].spatial_shape) == [2, 200, 176]
+    # occupancy backbone + head
+    geo = OccGeometry()
+    model = GB._randomize(models_mirror.OccBackboneMirror(4), 5)
+    gen = oracle.VoxelGeneratorV2(geo.voxel_size, geo.point_cloud_range, S.OCC_MAX_POINTS, S.OCC_MAX_VOXELS["train"])
+    fs, cs = [], []
+    for b in range(batch):
+        pts = S.lidar_like(500, seed=400 + b)
+        cyl = np.stack([np.linalg.norm(pts[:, :2], axis=1), np.arctan2(-pts[:, 1], pts[:, 0]) * 180. / np.pi, pts[:, 2],
+                        pts[:, 3]], -1).astype(np.float32)
+        r = gen.generate(cyl)
+        fs.append(r["voxels"].sum(1) / np.maximum(r["num_points_per_voxel"], 1)[:, None])
+        cs.append(np.pad(r["coordinates"], ((0, 0), (1, 0)), constant_values=b))
+    feats, coords = np.concatenate(fs).astype(np.float32), np.concatenate(cs).astype(np.int32)
+    feats = feats / np.array([70.0, 40.0, 3.0, 1.0], np.float32)
+    ref = model.run(models_mirror.OracleBackend(), oracle_net.to_oracle_tensor(feats, coords, model.sparse_shape, batch))
+    with shim_on_host(emul_lib), torch.no_grad():
+        x = spconv.SparseConvTensor(torch.from_numpy(feats), torch.from_numpy(coords), model.sparse_shape, batch)
+        got = model.run(models_mirror.ShimBackend(), x)
+        dense_cls = got["cls"].dense()
+    for name in ("encoded", "cls", "res"):
+        np.testing.assert_array_equal(got[name].indices.numpy(), ref[name].indices, err_msg=name)
+        assert GB.rel_err(got[name].features.numpy(), ref[name].features) < GB.REL_TOL, name
+    assert list(got["encoded"].spatial_shape) == [9, 157, 209]
+    np.testing.assert_array_equal(dense_cls.numpy(), oracle.dense(got["cls"].features.numpy(), ref["cls"].indices, [9, 157, 209], batch))
