@@ -474,3 +474,28 @@ def test_reference_topologies_on_the_emulated_library(oracle, emul_lib):
         assert GB.rel_err(got[name].features.numpy(), ref[name].features) < GB.REL_TOL, name
     assert list(got["encoded"].spatial_shape) == [9, 157, 209]
     np.testing.assert_array_equal(dense_cls.numpy(), oracle.dense(got["cls"].features.numpy(), ref["cls"].indices, [9, 157, 209], batch))
+
+
+def test_bench_roi_pool_leg_runs_on_the_emulated_library(emul_lib, monkeypatch):
+    """tools/bench_legs.py::roi_pool_leg end to end (both stacked ball queries, the fused gather, the three mini-grid
+    convolutions through the shim, dense()) at a tiny size: the leg's host code, which only ever runs inside bench.py on a
+    GPU box, checked where the CPU suite runs."""
+    import time
+    from btcdet_b200 import pointnet2_stack_cuda as p2, roi_pool
+    from tools import bench_legs
+
+    class Ev(object):
+        def record(self):
+            self.t = time.time()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    monkeypatch.setattr(bench_legs, "_events", lambda: (Ev(), Ev()))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(p2, "_stream", lambda: None)
+    monkeypatch.setattr(roi_pool, "_stream", lambda: None)
+    with shim_on_host(emul_lib):
+        out = bench_legs.roi_pool_leg("cpu", steps=1, warmup=0, batch=2, n_rois=2)
+    assert out["queries"] == 2 * 2 * 27 and out["targets"] == 2 * 2 * 27 * 96
+    assert out["out_shape"] == [108, 128, 1, 1, 1] and out["gathered_rows"] > 0 and out["value"] > 0
