@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "btcdet_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 SAN = os.environ.get("BTC_EMUL_SANITIZE", "")      # e.g. "address": an AddressSanitizer build (run pytest under LD_PRELOAD=libasan)
-LIB = os.path.join(OUT, "libbtcdet_b200_emul%s.so" % ("_" + SAN if SAN else ""))
+LIB = os.path.join(OUT, "libbtcdet_b200_emul%s%s.so" % ("_" + SAN if SAN else "", "_fibers" if SAN and os.environ.get("BTC_EMUL_FIBERS") else ""))
 FILES = ["coord_index.cu", "voxelize.cu", "rulebook.cu", "pool_dense.cu", "points_transform.cu", "roi_pool.cu",
          "sparse_conv.cu", "iou3d_nms.cu", "occ_masks.cu", "box_masks.cu"]
 
@@ -117,9 +117,10 @@ def build(force=False):
         cpp = os.path.join(OUT, f.replace(".cu", ".emul.cpp"))
         with open(cpp, "w") as fh:
             fh.write('#include "cuda_emul.h"\n' + (STUBS if f == FILES[0] else "") + transform(src))
-        obj = cpp.replace(".cpp", (".%s.o" % SAN) if SAN else ".o")
+        obj = cpp.replace(".cpp", (".%s%s.o" % (SAN, "f" if os.environ.get("BTC_EMUL_FIBERS") else "")) if SAN else ".o")
         res = subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w", "-DBTC_SM=100"] +
-                             (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + SAN, "-DEMUL_THREADS"] if SAN else []) + [
+                             (["-g", "-fno-omit-frame-pointer", "-fsanitize=" + SAN] + ([] if os.environ.get("BTC_EMUL_FIBERS") else ["-DEMUL_THREADS"])
+                              if SAN else []) + [
                               "-I" + HERE, "-I" + CSRC, "-I/usr/local/cuda/include", "-c", cpp, "-o", obj],
                              capture_output=True, text=True)
         if res.returncode != 0:
