@@ -12,7 +12,7 @@ OPTS=detect_leaks=0:verify_asan_link_order=0:halt_on_error=1:detect_stack_use_af
 if [ "$1" = "--full" ]; then
   shift
   BTC_EMUL_FULL=1 BTC_EMUL_FIBERS=1 BTC_EMUL_SANITIZE=address LD_PRELOAD=$ASAN ASAN_OPTIONS=$OPTS \
-    python -m pytest tests/test_emulated_kernels_cpu.py -x -q -p no:cacheprovider "$@"
+    python -m pytest tests/test_emulated_kernels_cpu.py -x -q -p no:cacheprovider --timeout=3600 "$@"
 else
   BTC_EMUL_SANITIZE=address LD_PRELOAD=$ASAN ASAN_OPTIONS=$OPTS \
     python -m pytest tests/test_emulated_kernels_cpu.py tests/test_roi_pool_cpu.py -x -q -p no:cacheprovider "$@"
